@@ -1,0 +1,116 @@
+"""Build the reference's own native code for the hot path into oracle/_ref/ (TEST INFRASTRUCTURE ONLY).
+
+Nothing here is product code.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs may load what this script produces.
+
+What gets built, straight from the sources where they lie under /root/reference (never copied):
+
+  oracle/_ref/nms_rotated_ref*.so   torch extension = utils/nms_rotated/src/{nms_rotated_cpu.cpp,
+                                    nms_rotated_cuda.cu, box_iou_rotated_utils.h} + a 20-line pybind shim
+                                    written here (the reference's own nms_rotated_ext.cpp also wants
+                                    poly_nms_cuda.cu, which needs THC and cannot build on torch>=1.11).
+                                    Exposes nms_rotated_cpu / nms_rotated_cuda exactly as the reference
+                                    declares them (src/nms_rotated_ext.cpp:8-22).
+  oracle/_ref/libref_iou.so         torch-free nvcc build of a 10-line kernel that instantiates the
+                                    reference's single_box_iou_rotated<float> device function
+                                    (src/box_iou_rotated_utils.h:334-360) on N pairs, so the GPU tests can
+                                    compare IoU values bit for bit.
+
+/root/reference exists only in the authoring container; on the GPU box the prebuilt files travel with
+the snapshot (oracle/_ref is git-ignored, not gpurun-ignored).
+"""
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+OUT = HERE / "_ref"
+REF = Path("/root/reference")
+SRC = REF / "utils" / "nms_rotated" / "src"
+
+SHIM = r'''
+// pybind shim for the reference kernels (declarations as in utils/nms_rotated/src/nms_rotated_ext.cpp:8-22)
+#include <ATen/ATen.h>
+#include <torch/extension.h>
+at::Tensor nms_rotated_cuda(const at::Tensor& dets, const at::Tensor& scores, const float iou_threshold);
+at::Tensor nms_rotated_cpu(const at::Tensor& dets, const at::Tensor& scores, const float iou_threshold);
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.def("nms_rotated_cpu", [](const at::Tensor& d, const at::Tensor& s, double t) {
+    return nms_rotated_cpu(d.contiguous(), s.contiguous(), (float)t); });
+  m.def("nms_rotated_cuda", [](const at::Tensor& d, const at::Tensor& s, double t) {
+    return nms_rotated_cuda(d.contiguous(), s.contiguous(), (float)t); });
+}
+'''
+
+IOU_HARNESS = r'''
+// instantiates the reference device function on N independent pairs (test infrastructure)
+#include "%(hdr)s"
+#include <cuda_runtime.h>
+__global__ void ref_iou_pairs_kernel(const float* a, const float* b, float* out, long n) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = single_box_iou_rotated<float>(a + 5 * i, b + 5 * i);
+}
+extern "C" int ref_iou_pairs(const float* a, const float* b, float* out, long n, void* stream) {
+  if (n <= 0) return 0;
+  ref_iou_pairs_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a, b, out, n);
+  return (int)cudaGetLastError();
+}
+'''
+
+
+def build(force: bool = False) -> bool:
+    """Returns True if oracle/_ref is usable afterwards."""
+    have = list(OUT.glob("nms_rotated_ref*.so")) and (OUT / "libref_iou.so").exists()
+    if not REF.exists():
+        return bool(have)
+    if have and not force:
+        return True
+    OUT.mkdir(exist_ok=True)
+    work = OUT / "_build"
+    work.mkdir(exist_ok=True)
+    (work / "ref_shim.cpp").write_text(SHIM)
+    (work / "ref_iou_harness.cu").write_text(IOU_HARNESS % {"hdr": str(SRC / "box_iou_rotated_utils.h")})
+
+    # 1) torch-free IoU harness
+    subprocess.check_call([
+        "nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-shared", "-Xcompiler", "-fPIC",
+        "-o", str(OUT / "libref_iou.so"), str(work / "ref_iou_harness.cu")])
+
+    # 2) the reference torch extension (CPU kernel + CUDA kernel K1), same nvcc defines as the
+    #    reference's setup.py:18-22
+    os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0a")
+    os.environ.setdefault("MAX_JOBS", "4")
+    from torch.utils.cpp_extension import load
+    mod = load(
+        name="nms_rotated_ref",
+        sources=[str(work / "ref_shim.cpp"), str(SRC / "nms_rotated_cpu.cpp"), str(SRC / "nms_rotated_cuda.cu")],
+        extra_include_paths=[str(SRC)],
+        extra_cuda_cflags=["-D__CUDA_NO_HALF_OPERATORS__", "-D__CUDA_NO_HALF_CONVERSIONS__",
+                           "-D__CUDA_NO_HALF2_OPERATORS__"],
+        with_cuda=True,
+        build_directory=str(work),
+        verbose=False,
+    )
+    so = Path(mod.__file__)
+    shutil.copy2(so, OUT / so.name)
+    return True
+
+
+def load_ref():
+    """Import the prebuilt reference extension (tests only)."""
+    import importlib.util
+    import torch  # noqa: F401  (the extension links against libtorch)
+    sos = sorted(OUT.glob("nms_rotated_ref*.so"))
+    if not sos:
+        raise FileNotFoundError("oracle/_ref/nms_rotated_ref*.so not built; run python oracle/build_ref.py")
+    spec = importlib.util.spec_from_file_location("nms_rotated_ref", sos[0])
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+if __name__ == "__main__":
+    ok = build(force="--force" in sys.argv)
+    print("oracle/_ref:", "ok" if ok else "unavailable")

@@ -1,0 +1,85 @@
+"""ctypes binding of liby5obb.so — the C ABI declared in include/y5obb.h.
+
+There is no CPU fallback and no alternative backend: if the library is missing or a call fails this
+module raises.  PyTorch is used only for device memory and streams.
+"""
+import ctypes
+from ctypes import c_void_p, c_int, c_int64, c_float, c_size_t, c_char_p
+from pathlib import Path
+
+import torch
+
+_PKG = Path(__file__).resolve().parent
+_LIBPATH = _PKG / "liby5obb.so"
+_lib = None
+
+_ERR = {1: "Y5OBB_EINVAL (bad argument)", 2: "Y5OBB_EWORKSPACE (workspace too small)",
+        3: "Y5OBB_ECUDA (CUDA call failed)", 4: "Y5OBB_EARCH (device is not sm_100)"}
+
+# name -> (restype, argtypes); mirrors include/y5obb.h one to one (tests/test_abi.py checks the set)
+PROTOTYPES = {
+    "y5obb_abi_version": (c_int, []),
+    "y5obb_last_cuda_error": (c_int, []),
+    "y5obb_build_info": (c_char_p, []),
+    "y5obb_nms_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
+    "y5obb_nms_rotated_f32": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_int, c_void_p, c_void_p,
+                                      c_void_p, c_size_t, c_void_p]),
+    "y5obb_nms_rotated_batched_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_float,
+                                              c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                              c_void_p]),
+    "y5obb_rbox_iou_pairs_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+}
+
+NMS_STRICT_GT = 1
+NMS_DROP_SMALL = 2
+
+
+def lib() -> ctypes.CDLL:
+    """Load liby5obb.so (built in-tree by yolov5_obb_b200.build / __graft_entry__.build)."""
+    global _lib
+    if _lib is None:
+        if not _LIBPATH.exists():
+            raise RuntimeError(f"{_LIBPATH} is missing: run `python -m yolov5_obb_b200.build` "
+                               "(there is no CPU or PyTorch fallback for this path)")
+        L = ctypes.CDLL(str(_LIBPATH))
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(L, name)  # AttributeError if the ABI and this table disagree
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        extra = ""
+        if rc == 3:
+            extra = f" cudaError={lib().y5obb_last_cuda_error()}"
+        raise RuntimeError(f"{what} failed: {_ERR.get(rc, rc)}{extra}")
+
+
+def ptr(t) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def stream_ptr(device=None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+_WS = {}
+
+
+def workspace(nbytes: int, device, tag: str = "default") -> torch.Tensor:
+    """Grow-only cached byte buffer per (device, tag).  Stream-ordered reuse: callers on the same
+    stream may share a tag; different streams must use different tags."""
+    key = (torch.device(device).index or 0, tag)
+    buf = _WS.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=device)
+        _WS[key] = buf
+    return buf
+
+
+def require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: yolov5_obb_b200 has no CPU path "
+                           "(the CPU restatement lives in oracle/ and is test infrastructure)")

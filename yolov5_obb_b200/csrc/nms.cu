@@ -1,0 +1,485 @@
+// Device-resident rotated NMS for sm_100a.
+//
+// Replaces the reference's sort -> 64x64 IoU bit-matrix -> N^2/8-byte D2H -> serial host scan
+// (/root/reference/utils/nms_rotated/src/nms_rotated_cuda.cu:71-134) with five launches that never
+// leave the GPU:
+//   k_make_keys   64-bit key = (image << 32) | ~orderable(score); value = input index
+//   cub radix     one stable sort orders every image's boxes by descending score (ties: lower index)
+//   k_segments / k_plan   per-image extents, work-unit and mask offsets (device side, no sync)
+//   k_prep        per-box trig/area/circumradius once (the reference recomputes them per pair)
+//   k_tiles       persistent CTAs pull (row block, 8 col blocks) units of the UPPER triangle only;
+//                 phase 1 = exact far-pair reject into a shared-memory candidate list,
+//                 phase 2 = all lanes evaluate candidates with the bit-faithful IoU (rbox_iou.cuh),
+//                 phase 3 = one 64-bit mask word per row
+//   k_reduce      one CTA per image runs the greedy scan over the bit-matrix in shared memory and
+//                 writes the compacted keep list in score order
+// Algorithmic bytes per box: 24 in (5 floats + score) + 8 out per kept box; the bit-matrix is
+// internal traffic (8 bytes per 64x64 tile row, upper triangle only).
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+#include "rbox_iou.cuh"
+
+namespace y5obb {
+
+thread_local int g_last_cuda_error = 0;
+
+namespace {
+
+constexpr int TB = 64;            // boxes per block == bits per mask word
+constexpr int CHUNK = 8;          // col blocks per work unit
+constexpr int TILE_THREADS = 128;
+constexpr int REDUCE_THREADS = 1024;
+constexpr int MAX_IMAGES = 1 << 20;
+
+struct NmsSeg {
+  int64_t unit_off;  // first work unit of this image
+  int64_t mask_off;  // first mask word of this image
+  int32_t off;       // first sorted position
+  int32_t n;         // boxes in this image
+  int32_t nblk;      // ceil(n / 64)
+  int32_t pad;
+};
+
+struct NmsCtrl {
+  unsigned long long next_unit;
+  long long total_units;
+  long long mask_capacity_words;
+  int err;
+  int pad;
+};
+
+__device__ __forceinline__ uint32_t orderable_desc(float s) {
+  s = s + 0.0f;  // -0 -> +0
+  uint32_t u = __float_as_uint(s);
+  u ^= (u >> 31) ? 0xFFFFFFFFu : 0x80000000u;  // ascending order on unsigned compare
+  return ~u;                                     // descending
+}
+
+// units of an image with nb blocks, rows ordered by m = nb - rb (m = 1 .. nb): row with m blocks of
+// columns has ceil(m / CHUNK) units.
+__host__ __device__ inline long long units_for(long long nb) {
+  long long q = nb / CHUNK, r = nb % CHUNK;
+  return (CHUNK / 2) * q * (q + 1) + (q + 1) * r;
+}
+
+__global__ void k_make_keys(const float* __restrict__ dets, const float* __restrict__ scores,
+                            const int32_t* __restrict__ image_ids, int64_t n, int n_images, int flags,
+                            uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int img = image_ids ? image_ids[i] : 0;
+  if (img < 0 || img >= n_images) img = n_images;  // dump segment
+  if (flags & Y5OBB_NMS_DROP_SMALL) {
+    float w = dets[5 * i + 2], h = dets[5 * i + 3];
+    if (fminf(w, h) < 0.001f) img = n_images;
+  }
+  keys[i] = ((uint64_t)(uint32_t)img << 32) | orderable_desc(scores[i]);
+  vals[i] = (uint32_t)i;
+}
+
+// seg_start[b] = first sorted position whose image id is >= b, for b in [0, n_images]
+__global__ void k_segments(const uint64_t* __restrict__ keys, int64_t n, int n_images, int32_t* __restrict__ seg_start) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  int prev = (i == 0) ? -1 : (int)(keys[i - 1] >> 32);
+  int cur = (i == n) ? n_images : (int)(keys[i] >> 32);
+  for (int b = prev + 1; b <= cur; ++b) seg_start[b] = (int32_t)i;
+}
+
+__global__ void k_plan(const int32_t* __restrict__ seg_start, int n_images, long long mask_capacity_words,
+                       NmsSeg* __restrict__ seg, NmsCtrl* ctrl) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  long long units = 0, words = 0;
+  for (int b = 0; b < n_images; ++b) {
+    NmsSeg s;
+    s.off = seg_start[b];
+    s.n = seg_start[b + 1] - seg_start[b];
+    s.nblk = (s.n + TB - 1) / TB;
+    s.unit_off = units;
+    s.mask_off = words;
+    s.pad = 0;
+    units += units_for(s.nblk);
+    words += (long long)s.n * s.nblk;
+    seg[b] = s;
+  }
+  NmsSeg tail;
+  tail.off = seg_start[n_images];
+  tail.n = 0;
+  tail.nblk = 0;
+  tail.unit_off = units;
+  tail.mask_off = words;
+  tail.pad = 0;
+  seg[n_images] = tail;
+  ctrl->next_unit = 0;
+  ctrl->mask_capacity_words = mask_capacity_words;
+  if (words > mask_capacity_words) {
+    ctrl->err = 1;  // max_per_image was exceeded: refuse rather than overrun the workspace
+    ctrl->total_units = 0;
+  } else {
+    ctrl->err = 0;
+    ctrl->total_units = units;
+  }
+}
+
+__global__ void k_prep(const float* __restrict__ dets, const uint32_t* __restrict__ order, int64_t n,
+                       PreBox* __restrict__ pre) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* d = dets + 5 * (int64_t)order[i];
+  pre[i] = make_prebox(d[0], d[1], d[2], d[3], d[4]);
+}
+
+__device__ __forceinline__ void load_prebox(PreBox* dst, const PreBox* src) {
+  const float4* s = reinterpret_cast<const float4*>(src);
+  float4* d = reinterpret_cast<float4*>(dst);
+  d[0] = s[0];
+  d[1] = s[1];
+}
+
+__global__ void __launch_bounds__(TILE_THREADS)
+k_tiles(const PreBox* __restrict__ pre, const NmsSeg* __restrict__ seg, int n_images, NmsCtrl* ctrl,
+        unsigned long long* __restrict__ mask, uint8_t* __restrict__ rowflag, float thr, int strict) {
+  __shared__ __align__(16) PreBox s_row[TB];
+  __shared__ __align__(16) PreBox s_col[TB];
+  __shared__ unsigned long long s_mask[TB];
+  __shared__ unsigned short s_cand[TB * TB];
+  __shared__ int s_ncand;
+  __shared__ long long s_unit;
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const long long total = ctrl->total_units;
+
+  for (;;) {
+    if (tid == 0) s_unit = (long long)atomicAdd(&ctrl->next_unit, 1ull);
+    __syncthreads();
+    const long long u = s_unit;
+    if (u >= total) break;
+
+    // image lookup: last b with unit_off <= u
+    int lo = 0, hi = n_images - 1;
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (seg[mid].unit_off <= u) lo = mid; else hi = mid - 1;
+    }
+    const NmsSeg S = seg[lo];
+    const long long lu = u - S.unit_off;
+    // decode lu -> (m, k): groups of CHUNK consecutive m share the chunk count q + 1
+    long long q = (long long)((sqrt(1.0 + 8.0 * (double)lu / CHUNK) - 1.0) * 0.5);
+    if (q < 0) q = 0;
+    while ((CHUNK / 2) * (q + 1) * (q + 2) <= lu) ++q;
+    while (q > 0 && (CHUNK / 2) * q * (q + 1) > lu) --q;
+    const long long rem = lu - (CHUNK / 2) * q * (q + 1);
+    const int m = (int)(CHUNK * q + 1 + rem / (q + 1));
+    const int k = (int)(rem % (q + 1));
+    const int rb = S.nblk - m;
+    const int cb0 = rb + CHUNK * k;
+    const int cb1 = min(cb0 + CHUNK, S.nblk);
+    const int nrow = min(TB, S.n - rb * TB);
+
+    if (tid < nrow) load_prebox(&s_row[tid], &pre[S.off + rb * TB + tid]);
+
+    for (int cb = cb0; cb < cb1; ++cb) {
+      const int ncol = min(TB, S.n - cb * TB);
+      if (tid >= TB && tid - TB < ncol) load_prebox(&s_col[tid - TB], &pre[S.off + cb * TB + (tid - TB)]);
+      if (tid < TB) s_mask[tid] = 0ull;
+      if (tid == 0) s_ncand = 0;
+      __syncthreads();
+
+      {  // phase 1: exact reject of pairs whose circumscribed circles do not touch
+        const int r = tid & (TB - 1);
+        const int half = tid >> 6;
+        const bool rvalid = r < nrow;
+        const float rx = s_row[r].cx, ry = s_row[r].cy, rr = s_row[r].rad;
+#pragma unroll 4
+        for (int jj = 0; jj < TB / 2; ++jj) {
+          const int j = half * (TB / 2) + jj;
+          bool c = false;
+          if (rvalid && j < ncol && (cb > rb || j > r)) {
+            float dx = rx - s_col[j].cx, dy = ry - s_col[j].cy;
+            float R = rr + s_col[j].rad;
+            c = (dx * dx + dy * dy) <= R * R;
+          }
+          const unsigned bal = __ballot_sync(0xffffffffu, c);
+          if (bal) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_ncand, __popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (c) s_cand[base + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)((r << 6) | j);
+          }
+        }
+      }
+      __syncthreads();
+
+      {  // phase 2: every lane takes candidates off the list
+        const int nc = s_ncand;
+        for (int c = tid; c < nc; c += TILE_THREADS) {
+          const int pr = s_cand[c];
+          const int r = pr >> 6, j = pr & 63;
+          const float v = rbox_iou(s_row[r], s_col[j]);
+          const bool sup = strict ? (v > thr) : (v >= thr);
+          if (sup) atomicOr(&s_mask[r], 1ull << j);
+        }
+      }
+      __syncthreads();
+
+      if (tid < nrow) {
+        const unsigned long long w = s_mask[tid];
+        mask[S.mask_off + (long long)(rb * TB + tid) * S.nblk + cb] = w;
+        if (w) rowflag[S.off + rb * TB + tid] = 1;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(REDUCE_THREADS)
+k_reduce(const NmsSeg* __restrict__ seg, const NmsCtrl* __restrict__ ctrl,
+         const unsigned long long* __restrict__ mask, const uint8_t* __restrict__ rowflag,
+         const uint32_t* __restrict__ order, long long max_keep, int n_images,
+         int64_t* __restrict__ keep_out, int64_t* __restrict__ n_keep_out, int64_t* __restrict__ seg_off_out) {
+  extern __shared__ unsigned long long remv[];
+  __shared__ unsigned long long s_diag[TB];
+  __shared__ int s_orrows[TB];
+  __shared__ int s_nor;
+  __shared__ unsigned long long s_kept;
+
+  const int tid = threadIdx.x;
+  const int b = blockIdx.x;
+  const NmsSeg S = seg[b];
+  if (tid == 0) {
+    seg_off_out[b] = S.off;
+    if (b == 0) seg_off_out[n_images] = seg[n_images].off;
+  }
+  if (ctrl->err) {
+    if (tid == 0) n_keep_out[b] = -1;
+    return;
+  }
+  for (int w = tid; w < S.nblk; w += REDUCE_THREADS) remv[w] = 0ull;
+  if (tid == 0) s_nor = 0;
+  __syncthreads();
+
+  long long count = 0;
+  const unsigned long long* M = mask + S.mask_off;
+  for (int blk = 0; blk < S.nblk; ++blk) {
+    const int rows = min(TB, S.n - blk * TB);
+    unsigned long long cur = remv[blk];
+    if (rows < TB) cur |= ~0ull << rows;
+    if (cur == ~0ull) continue;  // whole block already suppressed (uniform branch)
+
+    if (tid < TB) s_diag[tid] = (tid < rows) ? M[(long long)(blk * TB + tid) * S.nblk + blk] : 0ull;
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long kept = 0ull;
+#pragma unroll
+      for (int i = 0; i < TB; ++i) {
+        const unsigned long long bit = 1ull << i;
+        if (!(cur & bit)) {
+          kept |= bit;
+          cur |= s_diag[i];
+        }
+      }
+      if (max_keep > 0) {
+        long long room = max_keep - count;
+        while ((long long)__popcll(kept) > room) kept &= ~(1ull << (63 - __clzll(kept)));
+      }
+      s_kept = kept;
+    }
+    __syncthreads();
+    const unsigned long long kept = s_kept;
+    if (tid < TB && ((kept >> tid) & 1ull)) {
+      const long long pos = count + __popcll(kept & ((1ull << tid) - 1ull));
+      const int srow = blk * TB + tid;
+      keep_out[S.off + pos] = (int64_t)order[S.off + srow];
+      if (rowflag[S.off + srow]) s_orrows[atomicAdd(&s_nor, 1)] = srow;
+    }
+    count += __popcll(kept);
+    __syncthreads();
+    const int nor = s_nor;
+    if (nor) {
+      for (int w = blk + 1 + tid; w < S.nblk; w += REDUCE_THREADS) {
+        unsigned long long acc = 0ull;
+        for (int r = 0; r < nor; ++r) acc |= M[(long long)s_orrows[r] * S.nblk + w];
+        if (acc) remv[w] |= acc;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) s_nor = 0;
+    if (max_keep > 0 && count >= max_keep) break;
+  }
+  if (tid == 0) n_keep_out[b] = count;
+}
+
+__global__ void k_zero_outputs(int n_images, int64_t* n_keep_out, int64_t* seg_off_out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_images) n_keep_out[i] = 0;
+  if (i <= n_images) seg_off_out[i] = 0;
+}
+
+__global__ void k_iou_pairs(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  PreBox A = make_prebox(a[5 * i], a[5 * i + 1], a[5 * i + 2], a[5 * i + 3], a[5 * i + 4]);
+  PreBox B = make_prebox(b[5 * i], b[5 * i + 1], b[5 * i + 2], b[5 * i + 3], b[5 * i + 4]);
+  out[i] = rbox_iou(A, B);
+}
+
+struct NmsWs {
+  uint64_t *keys_a, *keys_b;
+  uint32_t *vals_a, *vals_b;
+  PreBox* pre;
+  uint8_t* rowflag;
+  int32_t* seg_start;
+  NmsSeg* seg;
+  NmsCtrl* ctrl;
+  void* cub_tmp;
+  size_t cub_bytes;
+  unsigned long long* mask;
+  long long mask_words;
+  size_t total;
+};
+
+size_t cub_sort_bytes(int64_t n) {
+  size_t bytes = 0;
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr,
+                                                  (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 0, 64, 0);
+  if (e != cudaSuccess || bytes == 0) {
+    (void)cudaGetLastError();
+    bytes = (size_t)(32u << 20) + (size_t)n * 4;  // generous bound when no device can be queried
+  }
+  return bytes;
+}
+
+NmsWs carve_nms(void* base, int64_t n, int64_t n_images, int64_t max_per_image) {
+  NmsWs w;
+  Carver c(base);
+  if (max_per_image <= 0 || max_per_image > n) max_per_image = n;
+  w.keys_a = c.take<uint64_t>(n);
+  w.keys_b = c.take<uint64_t>(n);
+  w.vals_a = c.take<uint32_t>(n);
+  w.vals_b = c.take<uint32_t>(n);
+  w.pre = c.take<PreBox>(n);
+  w.rowflag = c.take<uint8_t>(n);
+  w.seg_start = c.take<int32_t>(n_images + 2);
+  w.seg = c.take<NmsSeg>(n_images + 2);
+  w.ctrl = c.take<NmsCtrl>(1);
+  w.cub_bytes = cub_sort_bytes(n);
+  w.cub_tmp = c.take<char>(w.cub_bytes);
+  long long nb = (max_per_image + TB - 1) / TB;
+  w.mask_words = (long long)n * nb;
+  w.mask = c.take<unsigned long long>((size_t)w.mask_words);
+  w.total = c.used();
+  return w;
+}
+
+int nms_impl(const float* dets, const float* scores, const int32_t* image_ids, int64_t n, int64_t n_images,
+             int64_t max_per_image, float thr, int flags, int64_t max_keep, int64_t* keep_out, int64_t* n_keep_out,
+             int64_t* seg_off_out, void* workspace, size_t ws_bytes, cudaStream_t st) {
+  if (n < 0 || n_images < 1 || n_images > MAX_IMAGES || n > 0x7FFFFFF0ll) return Y5OBB_EINVAL;
+  if (!keep_out || !n_keep_out || !seg_off_out) return Y5OBB_EINVAL;
+  if (n == 0) {
+    k_zero_outputs<<<(unsigned)((n_images + 1 + 255) / 256), 256, 0, st>>>((int)n_images, n_keep_out, seg_off_out);
+    Y5_LAUNCH_CHECK();
+    return Y5OBB_OK;
+  }
+  if (!dets || !scores || !workspace) return Y5OBB_EINVAL;
+  if (max_per_image <= 0 || max_per_image > n) max_per_image = n;
+  NmsWs w = carve_nms(workspace, n, n_images, max_per_image);
+  if (w.total > ws_bytes) return Y5OBB_EWORKSPACE;
+
+  const unsigned g = (unsigned)((n + 255) / 256);
+  k_make_keys<<<g, 256, 0, st>>>(dets, scores, image_ids, n, (int)n_images, flags, w.keys_a, w.vals_a);
+  Y5_LAUNCH_CHECK();
+  int img_bits = 1;
+  while ((1ll << img_bits) <= n_images) ++img_bits;
+  size_t cub_bytes = w.cub_bytes;
+  Y5_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, cub_bytes, w.keys_a, w.keys_b, w.vals_a, w.vals_b, (int)n, 0,
+                                          32 + img_bits, st));
+  Y5_CUDA(cudaMemsetAsync(w.rowflag, 0, (size_t)n, st));
+  k_segments<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(w.keys_b, n, (int)n_images, w.seg_start);
+  Y5_LAUNCH_CHECK();
+  k_plan<<<1, 32, 0, st>>>(w.seg_start, (int)n_images, w.mask_words, w.seg, w.ctrl);
+  Y5_LAUNCH_CHECK();
+  k_prep<<<g, 256, 0, st>>>(dets, w.vals_b, n, w.pre);
+  Y5_LAUNCH_CHECK();
+
+  // persistent tile kernel: a few CTAs per SM, bounded by the number of units that can exist
+  long long max_units = 0;
+  {
+    long long nb = (max_per_image + TB - 1) / TB;
+    long long imgs_full = n / max_per_image + 1;
+    max_units = units_for(nb) * imgs_full;
+  }
+  long long grid = (long long)sm_count() * 8;
+  if (grid > max_units) grid = max_units;
+  if (grid < 1) grid = 1;
+  k_tiles<<<(unsigned)grid, TILE_THREADS, 0, st>>>(w.pre, w.seg, (int)n_images, w.ctrl, w.mask, w.rowflag, thr,
+                                                   (flags & Y5OBB_NMS_STRICT_GT) ? 1 : 0);
+  Y5_LAUNCH_CHECK();
+
+  const size_t smem = (size_t)((max_per_image + TB - 1) / TB) * sizeof(unsigned long long);
+  if (smem > 200 * 1024) return Y5OBB_EINVAL;  // > 1.6 M boxes in one image
+  static size_t smem_set = 0;
+  if (smem > 32 * 1024 && smem > smem_set) {
+    Y5_CUDA(cudaFuncSetAttribute(k_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+    smem_set = 200 * 1024;
+  }
+  k_reduce<<<(unsigned)n_images, REDUCE_THREADS, smem, st>>>(w.seg, w.ctrl, w.mask, w.rowflag, w.vals_b,
+                                                            (long long)max_keep, (int)n_images, keep_out, n_keep_out,
+                                                            seg_off_out);
+  Y5_LAUNCH_CHECK();
+  return Y5OBB_OK;
+}
+
+}  // namespace
+}  // namespace y5obb
+
+using namespace y5obb;
+
+extern "C" {
+
+int y5obb_abi_version(void) { return 1; }
+int y5obb_last_cuda_error(void) { return g_last_cuda_error; }
+const char* y5obb_build_info(void) { return "liby5obb sm_100a " __DATE__ " " __TIME__; }
+
+size_t y5obb_nms_workspace_bytes(int64_t n_total, int64_t n_images, int64_t max_per_image) {
+  if (n_total <= 0) return 256;
+  if (n_images < 1) n_images = 1;
+  NmsWs w = carve_nms(nullptr, n_total, n_images, max_per_image);
+  return w.total + 256;
+}
+
+int y5obb_nms_rotated_f32(const float* dets5, const float* scores, int64_t n, float iou_thr, int flags,
+                          int64_t* keep_out, int64_t* n_keep_out, void* workspace, size_t workspace_bytes,
+                          void* stream) {
+  // the two-entry seg_off output lives at the head of the workspace
+  if (n > 0 && (!workspace || workspace_bytes < 512)) return Y5OBB_EWORKSPACE;
+  if (n == 0) {
+    if (!n_keep_out) return Y5OBB_EINVAL;
+    Y5_CUDA(cudaMemsetAsync(n_keep_out, 0, sizeof(int64_t), (cudaStream_t)stream));
+    return Y5OBB_OK;
+  }
+  int64_t* seg_off = static_cast<int64_t*>(workspace);
+  return nms_impl(dets5, scores, nullptr, n, 1, n, iou_thr, flags, 0, keep_out, n_keep_out, seg_off,
+                  static_cast<char*>(workspace) + 256, workspace_bytes - 256, (cudaStream_t)stream);
+}
+
+int y5obb_nms_rotated_batched_f32(const float* dets5, const float* scores, const int32_t* image_ids,
+                                  int64_t n_total, int64_t n_images, int64_t max_per_image, float iou_thr, int flags,
+                                  int64_t max_keep, int64_t* keep_out, int64_t* n_keep_out, int64_t* seg_off_out,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+  return nms_impl(dets5, scores, image_ids, n_total, n_images, max_per_image, iou_thr, flags, max_keep, keep_out,
+                  n_keep_out, seg_off_out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int y5obb_rbox_iou_pairs_f32(const float* a5, const float* b5, float* iou_out, int64_t n, void* stream) {
+  if (n < 0) return Y5OBB_EINVAL;
+  if (n == 0) return Y5OBB_OK;
+  if (!a5 || !b5 || !iou_out) return Y5OBB_EINVAL;
+  k_iou_pairs<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a5, b5, iou_out, n);
+  Y5_LAUNCH_CHECK();
+  return Y5OBB_OK;
+}
+
+}  // extern "C"
