@@ -66,6 +66,51 @@ int y5obb_nms_rotated_batched_f32(const float* dets5, const float* scores, const
  * utils/nms_rotated/src/box_iou_rotated_utils.h:334-360 (single_box_iou_rotated<float>). */
 int y5obb_rbox_iou_pairs_f32(const float* a5, const float* b5, float* iou_out, int64_t n, void* stream);
 
+
+/* ---- convolution (tcgen05 implicit GEMM) ---------------------------------------------------
+ * Replaces the cuDNN/ATen calls behind models/common.py:37-49 (Conv.forward_fuse = conv + folded-BN
+ * bias + SiLU), :94-104 (Bottleneck residual), :267-274 (Concat, as a channel-offset store),
+ * nn.Upsample(2x nearest) (models/yolov5*.yaml head) and models/yolo.py:49-81 (Detect).
+ * Activations are NHWC bf16; a tensor argument is a channel SLICE of a wider buffer: `ptr` points at
+ * the slice's first channel of pixel 0 and `*_pix_stride` is the element distance between pixels.
+ * Weights are bf16 packed [KH*KW][cout_pad][cin_pad] (K-major), bias fp32 [cout_pad]; the paddings and
+ * the tile shape come from y5obb_conv_tiling so that host packing and kernel agree. */
+typedef struct y5obb_conv y5obb_conv_t;
+
+#define Y5OBB_CONV_MODE_CONV 0    /* bf16 NHWC output (+ optional residual / 2x up-sampled copy) */
+#define Y5OBB_CONV_MODE_DETECT 1  /* Detect head: fp32 [B, rows, no] output, optional sigmoid+decode */
+
+typedef struct {
+  const void* in;            /* bf16 NHWC slice */
+  int64_t in_pix_stride;
+  int B, Hin, Win, Cin;
+  const void* w;             /* packed weights */
+  const float* bias;
+  int Cout, KH, KW, stride, pad;
+  int mode, act;             /* act: 0 = identity, 1 = SiLU */
+  void* out;                 /* bf16 NHWC slice (MODE_CONV) */
+  int64_t out_pix_stride;
+  const void* res;           /* optional residual slice added after the activation (Bottleneck.add) */
+  int64_t res_pix_stride;
+  void* out2x;               /* optional second destination receiving the 2x nearest up-sampled result */
+  int64_t out2x_pix_stride;
+  float* det_out;            /* MODE_DETECT: fp32, row = b*det_rows_per_image + det_row_off + (a*H + h)*W + w */
+  int64_t det_rows_per_image, det_row_off;
+  int det_no;                /* outputs per anchor (nc + 5 + 180) */
+  int det_decode;            /* 1: sigmoid + xy/wh decode (eval branch, yolo.py:71-74); 0: raw logits (train) */
+  float det_stride;          /* level stride in pixels */
+  float det_anchor[6];       /* anchor (w,h) in pixels for the 3 anchors of this level */
+} y5obb_conv_desc;
+
+int y5obb_conv_tiling(int cin, int cout, int mode, int det_no, int* block_k, int* block_n, int* cin_pad,
+                      int* cout_pad, int* n_tiles_n);
+/* Builds TMA descriptors and launch geometry for fixed buffers (host call, no stream work). */
+int y5obb_conv_create(const y5obb_conv_desc* desc, y5obb_conv_t** out);
+int y5obb_conv_run(const y5obb_conv_t* conv, void* stream);
+int y5obb_conv_info(const y5obb_conv_t* conv, double* flops, double* hbm_bytes, int* grid, int* block_n,
+                    int* block_k, int* stages);
+void y5obb_conv_destroy(y5obb_conv_t* conv);
+
 #ifdef __cplusplus
 }
 #endif

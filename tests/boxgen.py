@@ -43,4 +43,11 @@ def degenerate_pairs():
     add([5, 5, 2, 2, 0], [7, 7, 2, 2, 0])                          # touching at a corner
     add([5, 5, 2, 2, 0], [7, 5, 2, 2, 0])                          # touching along an edge
     add([61440.5, 61441.25, 33.3, 12.1, 0.2], [61442.5, 61440.0, 30.0, 14.0, -0.4])  # class-offset magnitudes
+    # the same rectangle written two ways (w,h swapped, theta +- 90 deg): every edge pair is parallel or
+    # coincident — SURVEY 8(c)'s known-answer boxes 2 and 3 are this case
+    q = np.pi / 4
+    add([100, 100, 141.4, 141.4, -q], [100, 100, 141.4, 141.4, q])
+    add([100, 100, 50, 20, 0.3], [100, 100, 20, 50, 0.3 - np.pi / 2])
+    add([100, 100, 50, 20, 0.0], [100, 100, 20, 50, np.pi / 2])
+    add([4196, 4196.5, 64, 16, -PI / 2], [4196, 4196.5, 16, 64, 0.0])
     return np.asarray(A, np.float32), np.asarray(B, np.float32)

@@ -78,8 +78,11 @@ def test_iou_degenerate_bitexact_and_vs_cpu_oracle():
     a, b = degenerate_pairs()
     ours, ref = _our_iou_pairs(a, b), _ref_iou_pairs(a, b)
     assert np.array_equal(ours.view(np.uint32), ref.view(np.uint32)), (ours, ref)
+    # the CPU restatement agrees except on the last 4 pairs (one rectangle written two ways: all edges
+    # parallel/coincident), where FMA contraction changes which candidate points survive — there the
+    # reference's own CPU and CUDA builds disagree with each other as well
     cpu = oracle.iou_pairs(a, b, variant=1)
-    np.testing.assert_allclose(ours, cpu, rtol=0, atol=2e-5)
+    np.testing.assert_allclose(ours[:-4], cpu[:-4], rtol=0, atol=2e-5)
 
 
 def test_iou_vs_cpu_oracle_tolerance():
@@ -122,11 +125,14 @@ def _margin_ok(d, s, thr, keep, mode):
 
 @pytest.mark.parametrize("strict", [True, False])
 def test_keep_vs_cpu_oracle_both_comparison_rules(strict):
-    d, s, _ = rboxes(1500, 400, 33, n_classes=2)
     mode = 1 if strict else 0
-    exp = oracle.nms_rotated(d, s, 0.3, mode=mode)
-    if not _margin_ok(d, s, 0.3, exp, mode):
-        pytest.skip("a decisive IoU sits within 1e-4 of the threshold for this seed")
+    for seed in range(33, 60):
+        d, s, _ = rboxes(1500, 400, seed, n_classes=2)
+        exp = oracle.nms_rotated(d, s, 0.3, mode=mode)
+        if _margin_ok(d, s, 0.3, exp, mode):
+            break
+    else:
+        pytest.skip("no seed without a decisive IoU within 1e-4 of the threshold")
     ours = _nms(d, s, 0.3, strict_gt=strict)
     assert np.array_equal(ours, exp)
 
@@ -142,10 +148,17 @@ def test_ge_vs_gt_differ_on_exact_threshold():
     assert _nms(d, s, 1.0, strict_gt=False).tolist() == [0]
 
 
-def test_golden_fixtures():
+def test_golden_fixtures(ref_ext):
     g = np.load(ROOT / "tests" / "golden" / "nms_golden.npz")
     for k in sorted({x.split("/")[0] for x in g.files}):
         d, s, thr = g[f"{k}/dets"], g[f"{k}/scores"], float(g[f"{k}/thr"])
+        if k.startswith("kat"):
+            # SURVEY 8(c) known-answer boxes: 2 and 3 are the same square written two ways, a degenerate
+            # pair on which the reference's own CPU and CUDA arithmetic disagree (FMA contraction), so the
+            # device result is pinned to the reference CUDA kernel, not to the CPU fixture
+            ref = ref_ext.nms_rotated_cuda(torch.from_numpy(d).to(DEV), torch.from_numpy(s).to(DEV), thr).cpu().numpy()
+            assert np.array_equal(_nms(d, s, thr, strict_gt=True), ref), k
+            continue
         # fixtures hold the reference CPU extension's keep (>=, host hull); margin-checked at creation
         ours = _nms(d, s, thr, strict_gt=False)
         assert np.array_equal(ours, g[f"{k}/keep_cpu"]), k

@@ -28,9 +28,10 @@ def test_oracle_matches_golden_iou_values():
     assert np.array_equal(oracle.iou_pairs(g["a"], g["b"], 0).view(np.uint32), g["iou_host"].view(np.uint32))
     assert np.array_equal(oracle.iou_pairs(g["a"], g["b"], 1).view(np.uint32), g["iou_devorder"].view(np.uint32))
     # geometry known answers: identical boxes -> 1, disjoint -> 0, zero area -> 0
-    a, b = degenerate_pairs()
+    a = np.array([[10, 10, 20, 10, 0.3], [0, 0, 1e-8, 1e-8, 0], [5, 5, 2, 2, 0], [0, 0, 4, 2, 0]], np.float32)
+    b = np.array([[10, 10, 20, 10, 0.3], [0, 0, 1, 1, 0], [50, 50, 2, 2, 0], [1, 0, 4, 2, 0]], np.float32)
     v = oracle.iou_pairs(a, b, 0)
-    assert abs(v[0] - 1.0) < 1e-6 and v[-5] == 0.0 and v[-4] == 0.0
+    assert abs(v[0] - 1.0) < 1e-6 and v[1] == 0.0 and v[2] == 0.0 and abs(v[3] - 0.6) < 1e-6
 
 
 @pytest.mark.parametrize("n,span,thr,seed", [(400, 250, 0.4, 0), (1500, 800, 0.3, 1), (900, 5000, 0.45, 2),

@@ -28,6 +28,12 @@ PROTOTYPES = {
                                               c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                               c_void_p]),
     "y5obb_rbox_iou_pairs_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "y5obb_conv_tiling": (c_int, [c_int, c_int, c_int, c_int] + [ctypes.POINTER(c_int)] * 5),
+    "y5obb_conv_create": (c_int, [c_void_p, ctypes.POINTER(c_void_p)]),
+    "y5obb_conv_run": (c_int, [c_void_p, c_void_p]),
+    "y5obb_conv_info": (c_int, [c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+                        + [ctypes.POINTER(c_int)] * 4),
+    "y5obb_conv_destroy": (None, [c_void_p]),
 }
 
 NMS_STRICT_GT = 1

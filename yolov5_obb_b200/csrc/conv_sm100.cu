@@ -1,0 +1,541 @@
+// Implicit-GEMM NHWC bf16 convolution for sm_100a: TMA -> shared memory -> tcgen05.mma -> TMEM ->
+// fused epilogue (folded-BN bias, SiLU, residual add, concat-offset store, 2x nearest up-sample copy,
+// or the Detect head's permute + sigmoid + grid/anchor decode).
+//
+// Replaces, for the layers of models/yolov5{n,s,m,l,x}.yaml, the cuDNN/ATen calls behind
+//   /root/reference/models/common.py:37-49   (Conv.forward_fuse: conv + bias + SiLU)
+//   /root/reference/models/common.py:94-104  (Bottleneck: x + cv2(cv1(x)))   -> residual epilogue
+//   /root/reference/models/common.py:267-274 (Concat)                          -> channel-offset store
+//   /root/reference/models/yolo.py:49-81     (Detect: 1x1 conv, view/permute, sigmoid, decode)
+//
+// GEMM view: D[128 output pixels, BN channels] = sum over (tap, 64-channel chunk) A_tap[128, BK] * W_tap[BN, BK]^T
+//   A tile  = one 4-D TMA box {BK ch, Wt, Ht, 1} of the NHWC input at the tap's shifted origin; zero
+//             padding, ragged channel counts and ragged image edges are TMA out-of-bounds zero fill;
+//             stride-2 convs use the tensor map's element strides.
+//   W tile  = 2-D TMA box {BK, BN} of weights packed [tap][Cout_pad][Cin_pad] (K-major).
+//   Both land in 32/64/128-byte swizzled K-major layouts that tcgen05.mma consumes directly.
+// One persistent CTA per SM, 6 warps: TMA producer, MMA issuer (+TMEM owner), 4 epilogue warps;
+// two TMEM accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Roofline: tensor pipe for the wide layers (2*128*BN*K flop per tile), HBM for the narrow ones
+// (algorithmic bytes = input pixels*Cin*2 + output pixels*Cout*2 [+ residual] per image).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace y5obb {
+namespace {
+
+constexpr int BM = 128;  // output pixels per tile == TMEM lanes
+constexpr int MAX_STAGES = 8;
+constexpr int NUM_THREADS = 192;
+constexpr int SMEM_BUDGET = 200 * 1024;
+
+enum Mode : int { MODE_CONV = 0, MODE_DETECT = 1 };
+
+struct ConvK {
+  CUtensorMap tmA;
+  CUtensorMap tmB;
+  // geometry
+  int B, Hout, Wout;
+  int Wt, Ht, tiles_w, tiles_h;
+  int n_tiles_m, n_tiles_n;
+  int BN, BK;
+  int Cout, cout_pad;
+  int kchunks, KH, KW, stride, pad;
+  int stages;
+  uint32_t a_bytes, b_bytes, b_stage_bytes;
+  uint32_t idesc;
+  // epilogue
+  int mode, act;
+  const float* bias;
+  __nv_bfloat16* out;
+  long long out_pix_stride;
+  const __nv_bfloat16* res;
+  long long res_pix_stride;
+  __nv_bfloat16* out2x;
+  long long out2x_pix_stride;
+  // detect
+  float* det_out;
+  long long det_rows_per_image, det_row_off;
+  int det_no, det_decode;
+  float det_stride;
+  float det_anchor[6];
+};
+
+struct TileCoord {
+  int b, h0, w0, n0, nt;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvK& p, int t) {
+  TileCoord c;
+  c.nt = t % p.n_tiles_n;
+  int mt = t / p.n_tiles_n;
+  int per_img = p.tiles_h * p.tiles_w;
+  c.b = mt / per_img;
+  int r = mt - c.b * per_img;
+  int th = r / p.tiles_w;
+  c.h0 = th * p.Ht;
+  c.w0 = (r - th * p.tiles_w) * p.Wt;
+  c.n0 = c.nt * p.BN;
+  return c;
+}
+
+__device__ __forceinline__ float silu(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+__device__ __forceinline__ float sigmoidf(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvK p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
+  __shared__ __align__(8) uint64_t tmem_full[2];
+  __shared__ __align__(8) uint64_t tmem_empty[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  // 1024-byte aligned operand ring (the swizzle pattern repeats every 8 rows = up to 1024 bytes)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t stage_bytes = p.a_bytes + p.b_stage_bytes;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.n_tiles_m * p.n_tiles_n;
+  const int k_iters = p.KH * p.KW * p.kchunks;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&p.tmA);
+    ptx::prefetch_tmap(&p.tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full[a], 1);
+      ptx::mbar_init(&tmem_empty[a], 128);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(&tmem_base_smem, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const TileCoord c = decode_tile(p, t);
+        for (int kh = 0; kh < p.KH; ++kh)
+          for (int kw = 0; kw < p.KW; ++kw) {
+            const int tap = kh * p.KW + kw;
+            const int wi = c.w0 * p.stride + kw - p.pad;
+            const int hi = c.h0 * p.stride + kh - p.pad;
+            for (int kc = 0; kc < p.kchunks; ++kc) {
+              ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
+              uint8_t* sa = smem + (size_t)s * stage_bytes;
+              uint8_t* sb = sa + p.a_bytes;
+              ptx::mbar_expect_tx(&full_bar[s], p.a_bytes + p.b_bytes);
+              ptx::tma_load_4d(sa, &p.tmA, &full_bar[s], kc * p.BK, wi, hi, c.b);
+              ptx::tma_load_2d(sb, &p.tmB, &full_bar[s], kc * p.BK, tap * p.cout_pad + c.n0);
+              if (++s == p.stages) {
+                s = 0;
+                ph ^= 1u;
+              }
+            }
+          }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      const uint32_t row_bytes = (uint32_t)p.BK * 2u;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+        ptx::mbar_wait(&tmem_empty[acc], acc_ph ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+        for (int k = 0; k < k_iters; ++k) {
+          ptx::mbar_wait(&full_bar[s], ph);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + (size_t)s * stage_bytes);
+          const uint32_t sb = sa + p.a_bytes;
+          const uint64_t da = ptx::make_kmajor_desc(sa, row_bytes);
+          const uint64_t db = ptx::make_kmajor_desc(sb, row_bytes);
+          const int nk = p.BK >> 4;
+          for (int j = 0; j < nk; ++j) {
+            // advance 16 K-elements = 32 bytes inside the swizzle span: +2 in the (addr >> 4) field
+            ptx::umma_bf16(d_tmem, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), p.idesc, (k | j) ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty_bar[s]);
+          if (++s == p.stages) {
+            s = 0;
+            ph ^= 1u;
+          }
+        }
+        ptx::umma_commit(&tmem_full[acc]);
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int hl = row / p.Wt;
+    const int wl = row - hl * p.Wt;
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const TileCoord c = decode_tile(p, t);
+      const int acc = it & 1;
+      const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+      const int h = c.h0 + hl, w = c.w0 + wl;
+      const bool valid = (h < p.Hout) && (w < p.Wout);
+      const long long pix = ((long long)c.b * p.Hout + h) * p.Wout + w;
+
+      ptx::mbar_wait(&tmem_full[acc], acc_ph);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(q * 32) << 16);
+
+      if (p.mode == MODE_CONV) {
+        __nv_bfloat16* orow = p.out + pix * p.out_pix_stride + c.n0;
+        const __nv_bfloat16* rrow = p.res ? p.res + pix * p.res_pix_stride + c.n0 : nullptr;
+        __nv_bfloat16* urow = nullptr;
+        if (p.out2x) urow = p.out2x + (((long long)c.b * 2 * p.Hout + 2 * h) * (2 * p.Wout) + 2 * w) * p.out2x_pix_stride + c.n0;
+        const long long up_row_step = (long long)(2 * p.Wout) * p.out2x_pix_stride;
+        const int nvalid = min(p.BN, p.Cout - c.n0);
+        for (int c0 = 0; c0 < p.BN; c0 += 32) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)c0, r);
+          ptx::tmem_ld_wait();
+          if (valid && c0 < nvalid) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {  // 8 channels = one 16-byte store
+              const int cg = c0 + g * 8;
+              if (cg < nvalid) {
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[g * 8 + e]) + __ldg(p.bias + c.n0 + cg + e);
+                if (p.act) {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) v[e] = silu(v[e]);
+                }
+                if (rrow) {
+                  const uint4 rv = *reinterpret_cast<const uint4*>(rrow + cg);
+                  const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 f = __bfloat1622float2(rh[e]);
+                    v[2 * e] += f.x;
+                    v[2 * e + 1] += f.y;
+                  }
+                }
+                uint4 o;
+                o.x = pack_bf16(v[0], v[1]);
+                o.y = pack_bf16(v[2], v[3]);
+                o.z = pack_bf16(v[4], v[5]);
+                o.w = pack_bf16(v[6], v[7]);
+                *reinterpret_cast<uint4*>(orow + cg) = o;
+                if (urow) {
+                  *reinterpret_cast<uint4*>(urow + cg) = o;
+                  *reinterpret_cast<uint4*>(urow + p.out2x_pix_stride + cg) = o;
+                  *reinterpret_cast<uint4*>(urow + up_row_step + cg) = o;
+                  *reinterpret_cast<uint4*>(urow + up_row_step + p.out2x_pix_stride + cg) = o;
+                }
+              }
+            }
+          }
+        }
+      } else {
+        // Detect: N tile nt == anchor nt; columns [0, det_no) are that anchor's outputs.
+        // out row = b * rows_per_image + row_off + (a * H + h) * W + w   (models/yolo.py:65,81)
+        const int a = c.nt;
+        float* orow = p.det_out +
+                      ((long long)c.b * p.det_rows_per_image + p.det_row_off + ((long long)a * p.Hout + h) * p.Wout + w) *
+                          p.det_no;
+        const float aw = p.det_anchor[2 * a], ah = p.det_anchor[2 * a + 1];
+        for (int c0 = 0; c0 < p.BN; c0 += 32) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)c0, r);
+          ptx::tmem_ld_wait();
+          if (valid && c0 < p.det_no) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {  // 4 floats = one 16-byte store
+              const int cg = c0 + g * 4;
+              if (cg < p.det_no) {
+                float v[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[e] = __uint_as_float(r[g * 4 + e]) + __ldg(p.bias + c.n0 + cg + e);
+                if (p.det_decode) {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) v[e] = sigmoidf(v[e]);
+                  if (cg == 0) {  // xy, wh (models/yolo.py:73-74)
+                    v[0] = (v[0] * 2.0f - 0.5f + (float)w) * p.det_stride;
+                    v[1] = (v[1] * 2.0f - 0.5f + (float)h) * p.det_stride;
+                    v[2] = (v[2] * 2.0f) * (v[2] * 2.0f) * aw;
+                    v[3] = (v[3] * 2.0f) * (v[3] * 2.0f) * ah;
+                  }
+                }
+                *reinterpret_cast<float4*>(orow + cg) = make_float4(v[0], v[1], v[2], v[3]);
+              }
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_tmapEncodeTiled get_encode() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_tmapEncodeTiled>(p);
+  });
+  return fn;
+}
+
+CUtensorMapSwizzle swizzle_for(int bk) {
+  return bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+struct ConvObj {
+  ConvK k;
+  int grid;
+  size_t smem;
+  double flops;      // algorithmic 2*MACs
+  double hbm_bytes;  // algorithmic in + out (+ residual) bytes
+};
+
+}  // namespace
+}  // namespace y5obb
+
+using namespace y5obb;
+
+extern "C" {
+
+int y5obb_conv_tiling(int cin, int cout, int mode, int det_no, int* block_k, int* block_n, int* cin_pad,
+                      int* cout_pad, int* n_tiles_n) {
+  if (cin <= 0 || cout <= 0 || !block_k || !block_n || !cin_pad || !cout_pad || !n_tiles_n) return Y5OBB_EINVAL;
+  int bk = cin > 32 ? 64 : (cin > 16 ? 32 : 16);
+  int bn, nt;
+  if (mode == MODE_DETECT) {
+    if (det_no <= 0 || cout % det_no) return Y5OBB_EINVAL;
+    nt = cout / det_no;
+    bn = (det_no + 15) / 16 * 16;
+    if (bn > 256) return Y5OBB_EINVAL;
+  } else {
+    int best_nt = 0, best_bn = 0;
+    long best_cost = -1;
+    for (nt = (cout + 255) / 256; nt <= (cout + 255) / 256 + 3; ++nt) {
+      bn = ((cout + nt - 1) / nt + 15) / 16 * 16;
+      if (bn > 256) continue;
+      long cost = (long)bn * nt * 16 + nt;  // padded width first, then fewer tiles
+      if (best_cost < 0 || cost < best_cost) {
+        best_cost = cost;
+        best_nt = nt;
+        best_bn = bn;
+      }
+    }
+    nt = best_nt;
+    bn = best_bn;
+  }
+  *block_k = bk;
+  *block_n = bn;
+  *cin_pad = (cin + 7) / 8 * 8;
+  *cout_pad = bn * nt;
+  *n_tiles_n = nt;
+  return Y5OBB_OK;
+}
+
+int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
+  if (!d || !out) return Y5OBB_EINVAL;
+  if (!d->in || !d->w || !d->bias) return Y5OBB_EINVAL;
+  if (d->stride != 1 && d->stride != 2) return Y5OBB_EINVAL;
+  if (d->in_pix_stride % 8 || (reinterpret_cast<uintptr_t>(d->in) & 15)) return Y5OBB_EINVAL;
+  PFN_tmapEncodeTiled enc = get_encode();
+  if (!enc) return Y5OBB_ECUDA;
+
+  int bk, bn, cin_pad, cout_pad, nt;
+  int rc = y5obb_conv_tiling(d->Cin, d->Cout, d->mode, d->det_no, &bk, &bn, &cin_pad, &cout_pad, &nt);
+  if (rc) return rc;
+
+  ConvObj* o = new ConvObj();
+  ConvK& k = o->k;
+  memset(&k, 0, sizeof(k));
+  const int Hout = (d->Hin + 2 * d->pad - d->KH) / d->stride + 1;
+  const int Wout = (d->Win + 2 * d->pad - d->KW) / d->stride + 1;
+  k.B = d->B;
+  k.Hout = Hout;
+  k.Wout = Wout;
+  // tile: Wt x Ht = 128 pixels, Wt the power of two (<=128) that wastes the fewest edge pixels
+  int best_wt = 128;
+  double best_eff = -1;
+  for (int wt = 128; wt >= 8; wt >>= 1) {
+    int ht = BM / wt;
+    if (wt * d->stride > 256 || ht * d->stride > 256) continue;
+    double eff = (double)Wout * Hout / ((double)((Wout + wt - 1) / wt * wt) * ((Hout + ht - 1) / ht * ht));
+    if (eff > best_eff + 1e-9) {
+      best_eff = eff;
+      best_wt = wt;
+    }
+  }
+  k.Wt = best_wt;
+  k.Ht = BM / best_wt;
+  k.tiles_w = (Wout + k.Wt - 1) / k.Wt;
+  k.tiles_h = (Hout + k.Ht - 1) / k.Ht;
+  k.n_tiles_m = d->B * k.tiles_w * k.tiles_h;
+  k.n_tiles_n = nt;
+  k.BN = bn;
+  k.BK = bk;
+  k.Cout = d->Cout;
+  k.cout_pad = cout_pad;
+  k.kchunks = (d->Cin + bk - 1) / bk;
+  k.KH = d->KH;
+  k.KW = d->KW;
+  k.stride = d->stride;
+  k.pad = d->pad;
+  k.a_bytes = (uint32_t)BM * bk * 2;
+  k.b_bytes = (uint32_t)bn * bk * 2;
+  k.b_stage_bytes = (uint32_t)align_up(k.b_bytes, 1024);
+  k.stages = (int)std::min<size_t>(MAX_STAGES, SMEM_BUDGET / (k.a_bytes + k.b_stage_bytes));
+  if (k.stages < 2) {
+    delete o;
+    return Y5OBB_EINVAL;
+  }
+  k.idesc = ptx::make_idesc_bf16(BM, bn);
+  k.mode = d->mode;
+  k.act = d->act;
+  k.bias = d->bias;
+  k.out = static_cast<__nv_bfloat16*>(d->out);
+  k.out_pix_stride = d->out_pix_stride;
+  k.res = static_cast<const __nv_bfloat16*>(d->res);
+  k.res_pix_stride = d->res_pix_stride;
+  k.out2x = static_cast<__nv_bfloat16*>(d->out2x);
+  k.out2x_pix_stride = d->out2x_pix_stride;
+  k.det_out = d->det_out;
+  k.det_rows_per_image = d->det_rows_per_image;
+  k.det_row_off = d->det_row_off;
+  k.det_no = d->det_no;
+  k.det_decode = d->det_decode;
+  k.det_stride = d->det_stride;
+  for (int i = 0; i < 6; ++i) k.det_anchor[i] = d->det_anchor[i];
+  if (d->mode == MODE_CONV) {
+    if (!d->out || d->out_pix_stride % 8 || (reinterpret_cast<uintptr_t>(d->out) & 15) || d->Cout % 8) {
+      delete o;
+      return Y5OBB_EINVAL;
+    }
+  } else if (!d->det_out || d->det_no % 4) {
+    delete o;
+    return Y5OBB_EINVAL;
+  }
+
+  {  // activations: (C, W, H, B), element strides (1, s, s, 1)
+    cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->Win, (cuuint64_t)d->Hin, (cuuint64_t)d->B};
+    cuuint64_t strides[3] = {(cuuint64_t)d->in_pix_stride * 2, (cuuint64_t)d->in_pix_stride * 2 * d->Win,
+                             (cuuint64_t)d->in_pix_stride * 2 * d->Win * d->Hin};
+    cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)(k.Wt * d->stride), (cuuint32_t)(k.Ht * d->stride), 1};
+    cuuint32_t es[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
+    CUresult r = enc(&k.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->in), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(bk), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      g_last_cuda_error = (int)r;
+      delete o;
+      return Y5OBB_ECUDA;
+    }
+  }
+  {  // weights: (Cin, taps * Cout_pad)
+    cuuint64_t dims[2] = {(cuuint64_t)d->Cin, (cuuint64_t)d->KH * d->KW * cout_pad};
+    cuuint64_t strides[1] = {(cuuint64_t)cin_pad * 2};
+    cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)bn};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&k.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d->w), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(bk), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      g_last_cuda_error = (int)r;
+      delete o;
+      return Y5OBB_ECUDA;
+    }
+  }
+  const int total = k.n_tiles_m * k.n_tiles_n;
+  o->grid = std::min(total, sm_count());
+  // >= 116 KB so that two CTAs (each owning all 512 TMEM columns) can never share an SM
+  o->smem = std::max<size_t>((size_t)k.stages * (k.a_bytes + k.b_stage_bytes) + 1024, 116 * 1024);
+  o->flops = 2.0 * d->B * Hout * Wout * (double)d->Cout * d->Cin * d->KH * d->KW;
+  o->hbm_bytes = 2.0 * d->B * ((double)d->Hin * d->Win * d->Cin + (double)Hout * Wout * d->Cout * (d->res ? 2 : 1));
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + 2048);
+    if (e != cudaSuccess) {
+      delete o;
+      return cuda_fail(e);
+    }
+    attr_set = true;
+  }
+  *out = reinterpret_cast<y5obb_conv_t*>(o);
+  return Y5OBB_OK;
+}
+
+int y5obb_conv_run(const y5obb_conv_t* conv, void* stream) {
+  if (!conv) return Y5OBB_EINVAL;
+  const ConvObj* o = reinterpret_cast<const ConvObj*>(conv);
+  conv_tc_kernel<<<o->grid, NUM_THREADS, o->smem, (cudaStream_t)stream>>>(o->k);
+  Y5_LAUNCH_CHECK();
+  return Y5OBB_OK;
+}
+
+int y5obb_conv_info(const y5obb_conv_t* conv, double* flops, double* hbm_bytes, int* grid, int* block_n, int* block_k,
+                    int* stages) {
+  if (!conv) return Y5OBB_EINVAL;
+  const ConvObj* o = reinterpret_cast<const ConvObj*>(conv);
+  if (flops) *flops = o->flops;
+  if (hbm_bytes) *hbm_bytes = o->hbm_bytes;
+  if (grid) *grid = o->grid;
+  if (block_n) *block_n = o->k.BN;
+  if (block_k) *block_k = o->k.BK;
+  if (stages) *stages = o->k.stages;
+  return Y5OBB_OK;
+}
+
+void y5obb_conv_destroy(y5obb_conv_t* conv) { delete reinterpret_cast<ConvObj*>(conv); }
+
+}  // extern "C"
