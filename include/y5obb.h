@@ -111,6 +111,15 @@ int y5obb_conv_info(const y5obb_conv_t* conv, double* flops, double* hbm_bytes, 
                     int* block_k, int* stages);
 void y5obb_conv_destroy(y5obb_conv_t* conv);
 
+/* ---- HBM-bound helpers around the conv stack -------------------------------------------------
+ * y5obb_stem_s2d: NCHW fp32 image [B,3,H,W] -> 2x2 space-to-depth NHWC bf16 [B,H/2,W/2,16] (channel
+ * (dy*2+dx)*3 + c, 4 zero channels), so that the stem Conv(3, c, 6, 2, 2) of models/yolov5*.yaml (layer 0,
+ * models/common.py:37-49) becomes a 3x3/s1/p1 conv for the tensor-core kernel.
+ * y5obb_sppf_pool: SPPF's three chained MaxPool2d(5,1,2) (models/common.py:181-196) in one pass over
+ * channels [0,C) of an NHWC bf16 buffer, results at channel offsets C, 2C, 3C (replaces torch.cat). */
+int y5obb_stem_s2d(const float* x_nchw, void* out_nhwc16, int B, int H, int W, void* stream);
+int y5obb_sppf_pool(void* buf, int64_t pix_stride, int B, int H, int W, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

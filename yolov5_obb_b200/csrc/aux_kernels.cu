@@ -1,0 +1,122 @@
+// HBM-bound helpers around the conv stack (NHWC bf16):
+//   y5obb_stem_s2d     NCHW fp32 image -> 2x2 space-to-depth NHWC bf16 [B, H/2, W/2, 16] (12 real + 4 zero
+//                      channels), which turns the 6x6/s2/p2 stem conv (models/yolov5*.yaml layer 0,
+//                      models/common.py:37-49) into a 3x3/s1/p1 conv with K = 9 x 16 that the tcgen05
+//                      kernel runs with 32-byte swizzled tiles.
+//   y5obb_sppf_pool    the three chained 5x5/s1/p2 max-pools of SPPF (models/common.py:181-196) in one
+//                      pass: y1 = 5x5, y2 = 9x9, y3 = 13x13 windows of x (max-pool composition), written
+//                      at channel offsets C, 2C, 3C of the same buffer (the torch.cat disappears).
+// Algorithmic bytes: stem_s2d reads 12*H*W fp32 and writes H*W/4 * 32 B per image; sppf_pool reads
+// H*W*C*2 and writes 3x that.
+#include <cuda_bf16.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace y5obb {
+namespace {
+
+__global__ void k_stem_s2d(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int H, int W) {
+  const int Ho = H >> 1, Wo = W >> 1;
+  const long long total = (long long)B * Ho * Wo;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int wo = (int)(i % Wo);
+    const long long r = i / Wo;
+    const int ho = (int)(r % Ho);
+    const int b = (int)(r / Ho);
+    float v[16];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float* p = x + (((long long)b * 3 + c) * H + 2 * ho) * W + 2 * wo;
+      const float2 top = *reinterpret_cast<const float2*>(p);
+      const float2 bot = *reinterpret_cast<const float2*>(p + W);
+      v[0 * 3 + c] = top.x;  // (dy=0, dx=0)
+      v[1 * 3 + c] = top.y;  // (dy=0, dx=1)
+      v[2 * 3 + c] = bot.x;  // (dy=1, dx=0)
+      v[3 * 3 + c] = bot.y;  // (dy=1, dx=1)
+    }
+    v[12] = v[13] = v[14] = v[15] = 0.f;
+    uint4 o[2];
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(o);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) h[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+    uint4* dst = reinterpret_cast<uint4*>(out + i * 16);
+    dst[0] = o[0];
+    dst[1] = o[1];
+  }
+}
+
+__device__ __forceinline__ void vmax8(uint4& a, const uint4& b) {
+  __nv_bfloat162* x = reinterpret_cast<__nv_bfloat162*>(&a);
+  const __nv_bfloat162* y = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) x[i] = __hmax2(x[i], y[i]);
+}
+
+// one thread = one pixel x 8 channels; windows clipped at the border (max-pool pads with -inf)
+__global__ void k_sppf_pool(__nv_bfloat16* __restrict__ buf, long long pix_stride, int B, int H, int W, int C) {
+  const int vec = C >> 3;
+  const long long total = (long long)B * H * W * vec;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % vec);
+    long long r = i / vec;
+    const int w = (int)(r % W);
+    r /= W;
+    const int h = (int)(r % H);
+    const int b = (int)(r / H);
+    const uint4 ninf = make_uint4(0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u);
+    uint4 m5 = ninf, m9 = ninf, m13 = ninf;
+    for (int dy = -6; dy <= 6; ++dy) {
+      const int hh = h + dy;
+      if (hh < 0 || hh >= H) continue;
+      uint4 r5 = ninf, r9 = ninf, r13 = ninf;
+      const __nv_bfloat16* row = buf + (((long long)b * H + hh) * W) * pix_stride + cv * 8;
+      for (int dx = -6; dx <= 6; ++dx) {
+        const int ww = w + dx;
+        if (ww < 0 || ww >= W) continue;
+        const uint4 v = *reinterpret_cast<const uint4*>(row + (long long)ww * pix_stride);
+        vmax8(r13, v);
+        if (dx >= -4 && dx <= 4) vmax8(r9, v);
+        if (dx >= -2 && dx <= 2) vmax8(r5, v);
+      }
+      vmax8(m13, r13);
+      if (dy >= -4 && dy <= 4) vmax8(m9, r9);
+      if (dy >= -2 && dy <= 2) vmax8(m5, r5);
+    }
+    __nv_bfloat16* o = buf + (((long long)b * H + h) * W + w) * pix_stride + cv * 8;
+    *reinterpret_cast<uint4*>(o + C) = m5;
+    *reinterpret_cast<uint4*>(o + 2 * C) = m9;
+    *reinterpret_cast<uint4*>(o + 3 * C) = m13;
+  }
+}
+
+}  // namespace
+}  // namespace y5obb
+
+using namespace y5obb;
+
+extern "C" {
+
+int y5obb_stem_s2d(const float* x_nchw, void* out_nhwc16, int B, int H, int W, void* stream) {
+  if (!x_nchw || !out_nhwc16 || B <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1)) return Y5OBB_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(x_nchw) & 7) || (reinterpret_cast<uintptr_t>(out_nhwc16) & 15)) return Y5OBB_EINVAL;
+  const long long total = (long long)B * (H / 2) * (W / 2);
+  const int grid = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 16);
+  k_stem_s2d<<<grid, 256, 0, (cudaStream_t)stream>>>(x_nchw, static_cast<__nv_bfloat16*>(out_nhwc16), B, H, W);
+  Y5_LAUNCH_CHECK();
+  return Y5OBB_OK;
+}
+
+int y5obb_sppf_pool(void* buf, int64_t pix_stride, int B, int H, int W, int C, void* stream) {
+  if (!buf || B <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 7) || (pix_stride & 7) || pix_stride < 4 * (int64_t)C)
+    return Y5OBB_EINVAL;
+  if (reinterpret_cast<uintptr_t>(buf) & 15) return Y5OBB_EINVAL;
+  const long long total = (long long)B * H * W * (C / 8);
+  const int grid = (int)std::min<long long>((total + 127) / 128, (long long)sm_count() * 32);
+  k_sppf_pool<<<grid, 128, 0, (cudaStream_t)stream>>>(static_cast<__nv_bfloat16*>(buf), pix_stride, B, H, W, C);
+  Y5_LAUNCH_CHECK();
+  return Y5OBB_OK;
+}
+
+}  // extern "C"

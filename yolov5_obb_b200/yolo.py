@@ -1,0 +1,258 @@
+"""Host-side mirror of the reference model interface, executed by the sm_100a engine.
+
+Mirrors /root/reference/models/yolo.py (Model :95-268, Detect :33-92, parse_model :271-323) and the
+building blocks of /root/reference/models/common.py (Conv :37-49, Bottleneck :94-104, C3 :126-138,
+SPPF :181-196, Concat :267-274): same constructor arguments, same module/parameter names (so a
+reference state_dict loads unchanged), same forward() return values.  The modules here only HOLD
+parameters; all arithmetic runs in csrc/ through the C ABI (engine.py).  There is no PyTorch compute
+path in this package — the fp32 torch restatement used by the tests lives in oracle/model_ref.py.
+"""
+import math
+from copy import deepcopy
+from pathlib import Path
+
+import torch
+import torch.nn as nn
+
+# ---------------------------------------------------------------------------------------------
+# configuration (values of models/yolov5{n,s,m,l,x}.yaml, generated rather than stored)
+# ---------------------------------------------------------------------------------------------
+_SCALES = {"n": (0.33, 0.25), "s": (0.33, 0.50), "m": (0.67, 0.75), "l": (1.0, 1.0), "x": (1.33, 1.25)}
+_ANCHORS = [[10, 13, 16, 30, 33, 23], [30, 61, 62, 45, 59, 119], [116, 90, 156, 198, 373, 326]]  # P3/8, P4/16, P5/32
+
+
+def yolov5_cfg(size: str = "s", nc: int = 80) -> dict:
+    """The v6.0 CSPDarknet + PANet layout (models/yolov5s.yaml:13-48) for a given scale letter."""
+    gd, gw = _SCALES[size]
+    backbone = [[-1, 1, "Conv", [64, 6, 2, 2]]]                      # 0  P1/2
+    for width, depth in ((128, 3), (256, 6), (512, 9), (1024, 3)):   # 1-8: stride-2 conv + C3 per stage
+        backbone += [[-1, 1, "Conv", [width, 3, 2]], [-1, depth, "C3", [width]]]
+    backbone += [[-1, 1, "SPPF", [1024, 5]]]                          # 9
+    head = []
+    for width, skip in ((512, 6), (256, 4)):                          # top-down: 10-17
+        head += [[-1, 1, "Conv", [width, 1, 1]], [-1, 1, "nn.Upsample", [None, 2, "nearest"]],
+                 [[-1, skip], 1, "Concat", [1]], [-1, 3, "C3", [width, False]]]
+    for width, skip in ((256, 14), (512, 10)):                        # bottom-up: 18-23
+        head += [[-1, 1, "Conv", [width, 3, 2]], [[-1, skip], 1, "Concat", [1]], [-1, 3, "C3", [2 * width, False]]]
+    head += [[[17, 20, 23], 1, "Detect", ["nc", "anchors"]]]          # 24
+    return dict(nc=nc, depth_multiple=gd, width_multiple=gw, anchors=deepcopy(_ANCHORS), backbone=backbone, head=head)
+
+
+def make_divisible(x, divisor):
+    return math.ceil(x / divisor) * divisor
+
+
+def autopad(k, p=None):
+    return k // 2 if p is None else p
+
+
+# ---------------------------------------------------------------------------------------------
+# parameter containers (names match the reference modules)
+# ---------------------------------------------------------------------------------------------
+class _NoTorchPath(nn.Module):
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError(f"{type(self).__name__} holds parameters only; run the model through "
+                           "yolov5_obb_b200.yolo.Model.forward (sm_100a engine) — there is no PyTorch fallback")
+
+
+class Conv(_NoTorchPath):
+    def __init__(self, c1, c2, k=1, s=1, p=None, g=1, act=True):
+        super().__init__()
+        assert g == 1, "grouped convs are not used by yolov5{n,s,m,l,x}.yaml"
+        self.conv = nn.Conv2d(c1, c2, k, s, autopad(k, p), groups=g, bias=False)
+        self.bn = nn.BatchNorm2d(c2)
+        self.act = nn.SiLU() if act is True else nn.Identity()
+
+
+class Bottleneck(_NoTorchPath):
+    def __init__(self, c1, c2, shortcut=True, g=1, e=0.5):
+        super().__init__()
+        c_ = int(c2 * e)
+        self.cv1 = Conv(c1, c_, 1, 1)
+        self.cv2 = Conv(c_, c2, 3, 1, g=g)
+        self.add = shortcut and c1 == c2
+
+
+class C3(_NoTorchPath):
+    def __init__(self, c1, c2, n=1, shortcut=True, g=1, e=0.5):
+        super().__init__()
+        c_ = int(c2 * e)
+        self.cv1 = Conv(c1, c_, 1, 1)
+        self.cv2 = Conv(c1, c_, 1, 1)
+        self.cv3 = Conv(2 * c_, c2, 1)
+        self.m = nn.Sequential(*(Bottleneck(c_, c_, shortcut, g, e=1.0) for _ in range(n)))
+
+
+class SPPF(_NoTorchPath):
+    def __init__(self, c1, c2, k=5):
+        super().__init__()
+        assert k == 5
+        c_ = c1 // 2
+        self.cv1 = Conv(c1, c_, 1, 1)
+        self.cv2 = Conv(c_ * 4, c2, 1, 1)
+        self.k = k
+
+
+class Concat(_NoTorchPath):
+    def __init__(self, dimension=1):
+        super().__init__()
+        self.d = dimension
+
+
+class Upsample(_NoTorchPath):
+    """nn.Upsample(None, 2, 'nearest') placeholder (no parameters)."""
+
+    def __init__(self, size=None, scale_factor=2, mode="nearest"):
+        super().__init__()
+        assert size is None and scale_factor == 2 and mode == "nearest"
+        self.scale_factor, self.mode = scale_factor, mode
+
+
+class Detect(_NoTorchPath):
+    stride = None
+
+    def __init__(self, nc=80, anchors=(), ch=(), inplace=True):
+        super().__init__()
+        self.nc = nc
+        self.no = nc + 5 + 180  # models/yolo.py:40
+        self.nl = len(anchors)
+        self.na = len(anchors[0]) // 2
+        self.register_buffer("anchors", torch.tensor(anchors).float().view(self.nl, -1, 2))
+        self.m = nn.ModuleList(nn.Conv2d(x, self.no * self.na, 1) for x in ch)
+        self.inplace = inplace
+
+
+_MODULES = {"Conv": Conv, "C3": C3, "SPPF": SPPF, "Concat": Concat, "nn.Upsample": Upsample, "Detect": Detect}
+
+
+def parse_model(d: dict, ch: list):
+    """models/yolo.py:271-323 for the module types the shipped yamls use."""
+    anchors, nc, gd, gw = d["anchors"], d["nc"], d["depth_multiple"], d["width_multiple"]
+    na = (len(anchors[0]) // 2) if isinstance(anchors, list) else anchors
+    no = na * (nc + 185)
+    layers, save, c2 = [], [], ch[-1]
+    for i, (f, n, m, args) in enumerate(d["backbone"] + d["head"]):
+        name = m if isinstance(m, str) else m.__name__
+        if name not in _MODULES:
+            raise RuntimeError(f"module {name!r} is outside the hot path (only {sorted(_MODULES)} are built)")
+        cls = _MODULES[name]
+        args = [nc if a == "nc" else anchors if a == "anchors" else (None if a == "None" else a) for a in args]
+        n_ = max(round(n * gd), 1) if n > 1 else n
+        if cls in (Conv, C3, SPPF):
+            c1, c2 = ch[f], args[0]
+            if c2 != no:
+                c2 = make_divisible(c2 * gw, 8)
+            args = [c1, c2, *args[1:]]
+            if cls is C3:
+                args.insert(2, n_)
+                n_ = 1
+        elif cls is Concat:
+            c2 = sum(ch[x] for x in f)
+        elif cls is Detect:
+            args.append([ch[x] for x in f])
+            if isinstance(args[1], int):
+                args[1] = [list(range(args[1] * 2))] * len(f)
+        else:
+            c2 = ch[f]
+        assert n_ == 1, "repeated non-C3 modules do not occur in the shipped yamls"
+        m_ = cls(*args)
+        m_.i, m_.f, m_.type = i, f, name
+        m_.np = sum(x.numel() for x in m_.parameters())
+        save.extend(x % i for x in ([f] if isinstance(f, int) else f) if x != -1)
+        layers.append(m_)
+        if i == 0:
+            ch = []
+        ch.append(c2)
+    return nn.Sequential(*layers), sorted(save)
+
+
+class Model(nn.Module):
+    """Drop-in for models/yolo.py:95 Model: Model(cfg, ch=3, nc=None, anchors=None); forward(x[B,3,H,W] in [0,1])
+    -> eval: (pred[B, sum(3*H_i*W_i), nc+185] fp32, None); train: list of 3 [B,3,H_i,W_i,nc+185] logits."""
+
+    def __init__(self, cfg="yolov5s.yaml", ch=3, nc=None, anchors=None):
+        super().__init__()
+        if isinstance(cfg, dict):
+            self.yaml = deepcopy(cfg)
+        else:
+            p = Path(str(cfg))
+            if p.exists():  # a reference-style yaml file
+                import yaml
+                self.yaml_file = p.name
+                with open(p, encoding="ascii", errors="ignore") as f:
+                    self.yaml = yaml.safe_load(f)
+            else:  # "yolov5s.yaml" / "yolov5s" / "s"
+                key = p.stem.replace("yolov5", "")
+                if key not in _SCALES:
+                    raise FileNotFoundError(cfg)
+                self.yaml_file = f"yolov5{key}.yaml"
+                self.yaml = yolov5_cfg(key)
+        ch = self.yaml["ch"] = self.yaml.get("ch", ch)
+        if nc and nc != self.yaml["nc"]:
+            self.yaml["nc"] = nc
+        if anchors:
+            self.yaml["anchors"] = round(anchors)
+        self.model, self.save = parse_model(deepcopy(self.yaml), ch=[ch])
+        self.names = [str(i) for i in range(self.yaml["nc"])]
+        self.inplace = self.yaml.get("inplace", True)
+
+        m = self.model[-1]
+        assert isinstance(m, Detect)
+        m.inplace = self.inplace
+        m.stride = torch.tensor(self._strides())  # the reference probes a 256x256 forward (yolo.py:121-123)
+        m.anchors /= m.stride.view(-1, 1, 1)
+        self.stride = m.stride
+        self._initialize_biases()
+        for mod in self.modules():  # utils/torch_utils.py:154-166 initialize_weights
+            if isinstance(mod, nn.BatchNorm2d):
+                mod.eps = 1e-3
+                mod.momentum = 0.03
+        self._engines = {}
+        self._fused = False
+
+    def _strides(self):
+        s, out = [], {}
+        for m in self.model:
+            f = m.f if isinstance(m.f, int) else m.f[0]
+            src = (m.i - 1 if f == -1 else f)
+            cur = out.get(src, 1.0) if m.i > 0 else 1.0
+            if isinstance(m, Conv) and m.conv.stride[0] == 2:
+                cur *= 2
+            elif isinstance(m, Upsample):
+                cur /= 2
+            out[m.i] = cur
+        det = self.model[-1]
+        for j in det.f:
+            s.append(float(out[j]))
+        return s
+
+    def _initialize_biases(self, cf=None):  # models/yolo.py:223-232 (touches the 180 theta channels too)
+        m = self.model[-1]
+        for mi, s in zip(m.m, m.stride):
+            b = mi.bias.view(m.na, -1)
+            b.data[:, 4] += math.log(8 / (640 / s) ** 2)
+            b.data[:, 5:] += math.log(0.6 / (m.nc - 0.999999)) if cf is None else torch.log(cf / cf.sum())
+            mi.bias = torch.nn.Parameter(b.view(-1), requires_grad=True)
+
+    def fuse(self):
+        """models/yolo.py:246-254.  BN folding happens when an engine packs weights (engine.py uses
+        fuse_conv_and_bn arithmetic, utils/torch_utils.py:192-212); this only records the request."""
+        self._fused = True
+        return self
+
+    def invalidate(self):
+        """Call after changing parameters so that packed weights are rebuilt."""
+        self._engines.clear()
+
+    def forward(self, x, augment=False, profile=False, visualize=False):
+        if augment or profile or visualize:
+            raise RuntimeError("augment/profile/visualize are host tooling outside the hot path")
+        if self.training:
+            raise RuntimeError("training-mode forward (batch-stat BN + backward) is not built yet; "
+                               "call model.eval() — there is no PyTorch fallback")
+        from .engine import InferenceEngine
+        key = (tuple(x.shape), x.device.index)
+        eng = self._engines.get(key)
+        if eng is None:
+            eng = self._engines[key] = InferenceEngine(self, x.shape[0], x.shape[2], x.shape[3], x.device)
+        return eng.forward(x), None
