@@ -66,6 +66,19 @@ int y5obb_nms_rotated_batched_f32(const float* dets5, const float* scores, const
  * utils/nms_rotated/src/box_iou_rotated_utils.h:334-360 (single_box_iou_rotated<float>). */
 int y5obb_rbox_iou_pairs_f32(const float* a5, const float* b5, float* iou_out, int64_t n, void* stream);
 
+/* non_max_suppression_obb on the device (utils/general.py:772-862): conf filter, conf = obj*cls, theta =
+ * (argmax(180) - 90)/180*3.141592, multi-label expansion, optional class filter (class_mask bit j = class j
+ * allowed; ~0 = all), per-image top-max_nms clamp, class offset cls*max_wh on the centre, rotated NMS,
+ * max_det.  pred is the Detect eval output [batch, anchors, no] fp32.  Output: out7 [batch, max_det, 7] rows
+ * (cx, cy, l, s, theta, conf, cls) in descending-score order, counts [batch + 1] int64 = rows per image, then
+ * the total number of candidates found (if > max_candidates the result is incomplete: call again with a
+ * larger max_candidates; the Python shim does).  Nothing is synchronised or copied to the host. */
+size_t y5obb_nms_obb_workspace_bytes(int64_t batch, int64_t anchors, int64_t max_candidates, int64_t max_nms);
+int y5obb_nms_obb_f32(const float* pred, int64_t batch, int64_t anchors, int no, int nc, float conf_thres,
+                      float iou_thres, uint64_t class_mask, int agnostic, int multi_label, int max_det, int max_nms,
+                      float max_wh, int flags, int64_t max_candidates, float* out7, int64_t* counts,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
 
 /* ---- convolution (tcgen05 implicit GEMM) ---------------------------------------------------
  * Replaces the cuDNN/ATen calls behind models/common.py:37-49 (Conv.forward_fuse = conv + folded-BN

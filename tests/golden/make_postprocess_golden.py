@@ -1,0 +1,53 @@
+"""Golden vectors for non_max_suppression_obb produced by the REFERENCE function
+(utils/general.py:772, with the reference's own CPU nms_rotated extension) on seeded synthetic Detect
+outputs (tests/predgen.synth_pred) — only the function's OUTPUT is stored; the tests regenerate the input.
+Cases whose result could flip under the CPU(>=, no FMA) vs CUDA(>, FMA) difference are rejected by a margin
+check with the C++ oracle.  python tests/golden/make_postprocess_golden.py"""
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+HERE = Path(__file__).resolve().parent
+sys.path.insert(0, str(HERE))
+import ref_import  # noqa: E402
+
+ref_import.setup()
+sys.path.insert(0, str(HERE.parents[1]))
+from utils.general import non_max_suppression_obb  # noqa: E402
+from tests.predgen import synth_pred  # noqa: E402
+
+
+
+CFGS = {"multi": dict(conf_thres=0.25, iou_thres=0.45, multi_label=True, max_det=1500),
+        "best": dict(conf_thres=0.3, iou_thres=0.4, multi_label=False, max_det=1000),
+        "cls": dict(conf_thres=0.25, iou_thres=0.45, multi_label=True, classes=[1, 5, 9], max_det=50),
+        "agn": dict(conf_thres=0.28, iou_thres=0.2, multi_label=True, agnostic=True, max_det=1500),
+        "lowconf": dict(conf_thres=0.001, iou_thres=0.6, multi_label=True, max_det=300)}
+
+
+def main():
+    import oracle
+    from oracle.postprocess import non_max_suppression_obb as oracle_nms
+    out = {}
+    for name, kw in CFGS.items():
+        seed = 0
+        while True:
+            pred = torch.from_numpy(synth_pred(2, 3000, 15, seed))
+            res = non_max_suppression_obb(pred.clone(), **kw)
+            # margin: both oracle comparison rules must reproduce the reference result exactly
+            o0 = oracle_nms(pred, nms_mode=0, **kw)
+            o1 = oracle_nms(pred, nms_mode=1, **kw)
+            if all(torch.equal(a, b) and torch.equal(a, c) for a, b, c in zip(res, o0, o1)):
+                break
+            seed += 1
+        out[f"{name}/seed"] = np.int64(seed)
+        for b, r in enumerate(res):
+            out[f"{name}/{b}"] = r.numpy()
+        print(name, "seed", seed, [tuple(r.shape) for r in res])
+    np.savez_compressed(HERE / "postprocess_golden.npz", **out)
+
+
+if __name__ == "__main__":
+    main()

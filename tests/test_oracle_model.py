@@ -28,7 +28,7 @@ def test_mirror_init_and_oracle_forward_match_reference(size):
 
 def test_model_structure_mirrors_reference():
     from yolov5_obb_b200 import yolo as Y
-    for size, nparams in (("n", 2027752), ("s", 7545544), ("m", 21654696)):  # reference Model Summary lines
+    for size, nparams in (("n", 2027752), ("s", 7545544), ("m", 21655272), ("x", 87523240)):  # reference Model Summary lines
         m = Y.Model(f"yolov5{size}.yaml", ch=3, nc=15)
         assert sum(p.numel() for p in m.parameters()) == nparams
         assert m.stride.tolist() == [8.0, 16.0, 32.0]

@@ -28,6 +28,10 @@ PROTOTYPES = {
                                               c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                               c_void_p]),
     "y5obb_rbox_iou_pairs_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "y5obb_nms_obb_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64]),
+    "y5obb_nms_obb_f32": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_float, c_float, ctypes.c_uint64, c_int,
+                                  c_int, c_int, c_int, c_float, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_size_t,
+                                  c_void_p]),
     "y5obb_conv_tiling": (c_int, [c_int, c_int, c_int, c_int] + [ctypes.POINTER(c_int)] * 5),
     "y5obb_conv_create": (c_int, [c_void_p, ctypes.POINTER(c_void_p)]),
     "y5obb_conv_run": (c_int, [c_void_p, c_void_p]),

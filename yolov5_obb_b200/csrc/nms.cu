@@ -16,6 +16,7 @@
 // Algorithmic bytes per box: 24 in (5 floats + score) + 8 out per kept box; the bit-matrix is
 // internal traffic (8 bytes per 64x64 tile row, upper triangle only).
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "common.cuh"
 #include "rbox_iou.cuh"
@@ -65,9 +66,15 @@ __host__ __device__ inline long long units_for(long long nb) {
 
 __global__ void k_make_keys(const float* __restrict__ dets, const float* __restrict__ scores,
                             const int32_t* __restrict__ image_ids, int64_t n, int n_images, int flags,
-                            uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+                            const int64_t* __restrict__ n_valid_dev, uint64_t* __restrict__ keys,
+                            uint32_t* __restrict__ vals) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (n_valid_dev && i >= *n_valid_dev) {  // tail of an over-allocated candidate list
+    keys[i] = ((uint64_t)(uint32_t)n_images << 32) | 0xFFFFFFFFull;
+    vals[i] = (uint32_t)i;
+    return;
+  }
   int img = image_ids ? image_ids[i] : 0;
   if (img < 0 || img >= n_images) img = n_images;  // dump segment
   if (flags & Y5OBB_NMS_DROP_SMALL) {
@@ -88,13 +95,14 @@ __global__ void k_segments(const uint64_t* __restrict__ keys, int64_t n, int n_i
 }
 
 __global__ void k_plan(const int32_t* __restrict__ seg_start, int n_images, long long mask_capacity_words,
-                       NmsSeg* __restrict__ seg, NmsCtrl* ctrl) {
+                       int per_image_clamp, NmsSeg* __restrict__ seg, NmsCtrl* ctrl) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   long long units = 0, words = 0;
   for (int b = 0; b < n_images; ++b) {
     NmsSeg s;
     s.off = seg_start[b];
     s.n = seg_start[b + 1] - seg_start[b];
+    if (per_image_clamp > 0 && s.n > per_image_clamp) s.n = per_image_clamp;  // top-k by score (max_nms)
     s.nblk = (s.n + TB - 1) / TB;
     s.unit_off = units;
     s.mask_off = words;
@@ -367,7 +375,9 @@ NmsWs carve_nms(void* base, int64_t n, int64_t n_images, int64_t max_per_image) 
   w.cub_bytes = cub_sort_bytes(n);
   w.cub_tmp = c.take<char>(w.cub_bytes);
   long long nb = (max_per_image + TB - 1) / TB;
-  w.mask_words = (long long)n * nb;
+  long long mask_rows = n;
+  if ((long long)n_images * max_per_image < mask_rows) mask_rows = (long long)n_images * max_per_image;
+  w.mask_words = mask_rows * nb;
   w.mask = c.take<unsigned long long>((size_t)w.mask_words);
   w.total = c.used();
   return w;
@@ -375,7 +385,8 @@ NmsWs carve_nms(void* base, int64_t n, int64_t n_images, int64_t max_per_image) 
 
 int nms_impl(const float* dets, const float* scores, const int32_t* image_ids, int64_t n, int64_t n_images,
              int64_t max_per_image, float thr, int flags, int64_t max_keep, int64_t* keep_out, int64_t* n_keep_out,
-             int64_t* seg_off_out, void* workspace, size_t ws_bytes, cudaStream_t st) {
+             int64_t* seg_off_out, void* workspace, size_t ws_bytes, cudaStream_t st,
+             const int64_t* n_valid_dev = nullptr, int per_image_clamp = 0) {
   if (n < 0 || n_images < 1 || n_images > MAX_IMAGES || n > 0x7FFFFFF0ll) return Y5OBB_EINVAL;
   if (!keep_out || !n_keep_out || !seg_off_out) return Y5OBB_EINVAL;
   if (n == 0) {
@@ -389,7 +400,7 @@ int nms_impl(const float* dets, const float* scores, const int32_t* image_ids, i
   if (w.total > ws_bytes) return Y5OBB_EWORKSPACE;
 
   const unsigned g = (unsigned)((n + 255) / 256);
-  k_make_keys<<<g, 256, 0, st>>>(dets, scores, image_ids, n, (int)n_images, flags, w.keys_a, w.vals_a);
+  k_make_keys<<<g, 256, 0, st>>>(dets, scores, image_ids, n, (int)n_images, flags, n_valid_dev, w.keys_a, w.vals_a);
   Y5_LAUNCH_CHECK();
   int img_bits = 1;
   while ((1ll << img_bits) <= n_images) ++img_bits;
@@ -399,7 +410,7 @@ int nms_impl(const float* dets, const float* scores, const int32_t* image_ids, i
   Y5_CUDA(cudaMemsetAsync(w.rowflag, 0, (size_t)n, st));
   k_segments<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(w.keys_b, n, (int)n_images, w.seg_start);
   Y5_LAUNCH_CHECK();
-  k_plan<<<1, 32, 0, st>>>(w.seg_start, (int)n_images, w.mask_words, w.seg, w.ctrl);
+  k_plan<<<1, 32, 0, st>>>(w.seg_start, (int)n_images, w.mask_words, per_image_clamp, w.seg, w.ctrl);
   Y5_LAUNCH_CHECK();
   k_prep<<<g, 256, 0, st>>>(dets, w.vals_b, n, w.pre);
   Y5_LAUNCH_CHECK();
@@ -430,6 +441,227 @@ int nms_impl(const float* dets, const float* scores, const int32_t* image_ids, i
                                                             seg_off_out);
   Y5_LAUNCH_CHECK();
   return Y5OBB_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// non_max_suppression_obb on the device (/root/reference/utils/general.py:772-862)
+//   k_pp_count   one warp per anchor row: obj > conf (:781,:804), conf = cls * obj (:820), per-class
+//                candidates when multi_label (:826-828) or the best class (:830-832), class filter (:835)
+//   cub scan     deterministic candidate offsets in (image, anchor, class) order == the reference's order
+//   k_pp_emit    theta = (argmax(180) - 90) / 180 * 3.141592 (:822-823), class offset cls * 4096 on the
+//                centre (:849-851), un-offset 7-float row for the output
+//   nms_impl     batched NMS with the max_nms top-k clamp (:845-846) and max_det (:854-855)
+//   k_pp_gather  output rows [cx, cy, l, s, theta, conf, cls] in score order
+// ---------------------------------------------------------------------------------------------
+struct PPArgs {
+  const float* pred;
+  long long rows;  // B * A
+  int A, no, nc;
+  float conf;
+  int multi_label, agnostic;
+  unsigned long long class_mask;  // bit j set = class j allowed
+  float max_wh;
+};
+
+__global__ void k_pp_count(PPArgs a, int* __restrict__ cnt) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= a.rows) return;
+  const float* p = a.pred + row * a.no;
+  const float obj = p[4];
+  int n = 0;
+  if (obj > a.conf) {
+    if (a.multi_label) {
+      for (int j0 = 0; j0 < a.nc; j0 += 32) {
+        const int j = j0 + lane;
+        bool ok = false;
+        if (j < a.nc) ok = (__fmul_rn(p[5 + j], obj) > a.conf) && ((a.class_mask >> (j & 63)) & 1ull);
+        n += __popc(__ballot_sync(0xffffffffu, ok));
+      }
+    } else {
+      float bv = -INFINITY;
+      int bj = 0x7fffffff;
+      for (int j = lane; j < a.nc; j += 32) {
+        const float v = __fmul_rn(p[5 + j], obj);
+        if (v > bv) {
+          bv = v;
+          bj = j;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+        if (ov > bv || (ov == bv && oj < bj)) {
+          bv = ov;
+          bj = oj;
+        }
+      }
+      n = (bv > a.conf && bj < a.nc && ((a.class_mask >> (bj & 63)) & 1ull)) ? 1 : 0;
+    }
+  }
+  if (lane == 0) cnt[row] = n;
+}
+
+__global__ void k_pp_emit(PPArgs a, const int* __restrict__ cnt, const int* __restrict__ off, long long capacity,
+                          float* __restrict__ dets5, float* __restrict__ scores, int32_t* __restrict__ image_ids,
+                          float* __restrict__ out7, int64_t* __restrict__ n_valid) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= a.rows) return;
+  if (row == 0 && lane == 0) {
+    const long long total = (long long)off[a.rows - 1] + cnt[a.rows - 1];
+    n_valid[0] = total < capacity ? total : capacity;  // entries the NMS may look at
+    n_valid[1] = total;                                // what the host checks against capacity
+  }
+  if (cnt[row] == 0) return;
+  const float* p = a.pred + row * a.no;
+  const float obj = p[4];
+  // theta = first argmax over the 180 angle bins
+  float bv = -INFINITY;
+  int bk = 0x7fffffff;
+  const int cidx = 5 + a.nc;
+  for (int k = lane; k < 180; k += 32) {
+    const float v = p[cidx + k];
+    if (v > bv) {
+      bv = v;
+      bk = k;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+    if (ov > bv || (ov == bv && ok < bk)) {
+      bv = ov;
+      bk = ok;
+    }
+  }
+  if (bk > 179) bk = 0;  // all-NaN row: torch.max returns index 0
+  const float theta = __fmul_rn(__fdiv_rn((float)(bk - 90), 180.0f), 3.141592f);
+  const float cx = p[0], cy = p[1], w = p[2], h = p[3];
+  const int img = (int)(row / a.A);
+  long long base = off[row];
+
+  auto put = [&](long long slot, int cls, float sc) {
+    if (slot >= capacity) return;
+    const float c = a.agnostic ? 0.0f : __fmul_rn((float)cls, a.max_wh);
+    float* d = dets5 + slot * 5;
+    d[0] = __fadd_rn(cx, c);
+    d[1] = __fadd_rn(cy, c);
+    d[2] = w;
+    d[3] = h;
+    d[4] = theta;
+    scores[slot] = sc;
+    image_ids[slot] = img;
+    float* o = out7 + slot * 7;
+    o[0] = cx;
+    o[1] = cy;
+    o[2] = w;
+    o[3] = h;
+    o[4] = theta;
+    o[5] = sc;
+    o[6] = (float)cls;
+  };
+
+  if (a.multi_label) {
+    for (int j0 = 0; j0 < a.nc; j0 += 32) {
+      const int j = j0 + lane;
+      bool ok = false;
+      float sc = 0.f;
+      if (j < a.nc) {
+        sc = __fmul_rn(p[5 + j], obj);
+        ok = (sc > a.conf) && ((a.class_mask >> (j & 63)) & 1ull);
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, ok);
+      if (ok) put(base + __popc(bal & ((1u << lane) - 1u)), j, sc);
+      base += __popc(bal);
+    }
+  } else {
+    float cv = -INFINITY;
+    int cj = 0x7fffffff;
+    for (int j = lane; j < a.nc; j += 32) {
+      const float v = __fmul_rn(p[5 + j], obj);
+      if (v > cv) {
+        cv = v;
+        cj = j;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, cv, o);
+      const int oj = __shfl_xor_sync(0xffffffffu, cj, o);
+      if (ov > cv || (ov == cv && oj < cj)) {
+        cv = ov;
+        cj = oj;
+      }
+    }
+    if (lane == 0) put(base, cj, cv);
+  }
+}
+
+__global__ void k_pp_gather(const float* __restrict__ out7, const int64_t* __restrict__ keep,
+                            const int64_t* __restrict__ n_keep, const int64_t* __restrict__ seg_off, int n_images,
+                            int max_det, float* __restrict__ dst, int64_t* __restrict__ counts,
+                            const int64_t* __restrict__ n_valid) {
+  const int b = blockIdx.y;
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nk = n_keep[b];
+  if (k == 0) {
+    counts[b] = nk;
+    if (b == 0) counts[n_images] = n_valid[1];  // total candidates before the capacity clamp
+  }
+  if (k >= nk || k >= max_det) return;
+  const float* s = out7 + keep[seg_off[b] + k] * 7;
+  float* d = dst + ((long long)b * max_det + k) * 7;
+#pragma unroll
+  for (int e = 0; e < 7; ++e) d[e] = s[e];
+}
+
+struct PPWs {
+  int *cnt, *off;
+  void* scan_tmp;
+  size_t scan_bytes;
+  float *dets5, *scores, *out7;
+  int32_t* image_ids;
+  int64_t *n_valid, *keep, *n_keep, *seg_off;
+  void* nms_ws;
+  size_t nms_bytes;
+  size_t total;
+};
+
+size_t scan_bytes_for(long long rows) {
+  size_t bytes = 0;
+  cudaError_t e = cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const int*)nullptr, (int*)nullptr, (int)rows, 0);
+  if (e != cudaSuccess || bytes == 0) {
+    (void)cudaGetLastError();
+    bytes = (size_t)(1u << 20) + (size_t)rows / 64;
+  }
+  return bytes;
+}
+
+PPWs carve_pp(void* base, long long rows, int n_images, long long capacity, int max_nms) {
+  PPWs w;
+  Carver c(base);
+  w.cnt = c.take<int>(rows);
+  w.off = c.take<int>(rows);
+  w.scan_bytes = scan_bytes_for(rows);
+  w.scan_tmp = c.take<char>(w.scan_bytes);
+  w.dets5 = c.take<float>(capacity * 5);
+  w.scores = c.take<float>(capacity);
+  w.out7 = c.take<float>(capacity * 7);
+  w.image_ids = c.take<int32_t>(capacity);
+  w.n_valid = c.take<int64_t>(2);
+  w.keep = c.take<int64_t>(capacity);
+  w.n_keep = c.take<int64_t>(n_images);
+  w.seg_off = c.take<int64_t>(n_images + 1);
+  long long mpi = max_nms > 0 && max_nms < capacity ? max_nms : capacity;
+  NmsWs nw = carve_nms(nullptr, capacity, n_images, mpi);
+  w.nms_bytes = nw.total + 256;
+  w.nms_ws = c.take<char>(w.nms_bytes);
+  w.total = c.used();
+  return w;
 }
 
 }  // namespace
@@ -471,6 +703,53 @@ int y5obb_nms_rotated_batched_f32(const float* dets5, const float* scores, const
                                   void* workspace, size_t workspace_bytes, void* stream) {
   return nms_impl(dets5, scores, image_ids, n_total, n_images, max_per_image, iou_thr, flags, max_keep, keep_out,
                   n_keep_out, seg_off_out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+size_t y5obb_nms_obb_workspace_bytes(int64_t batch, int64_t anchors, int64_t max_candidates, int64_t max_nms) {
+  if (batch <= 0 || anchors <= 0 || max_candidates <= 0) return 256;
+  PPWs w = carve_pp(nullptr, batch * anchors, (int)batch, max_candidates, (int)max_nms);
+  return w.total + 256;
+}
+
+int y5obb_nms_obb_f32(const float* pred, int64_t batch, int64_t anchors, int no, int nc, float conf_thres,
+                      float iou_thres, uint64_t class_mask, int agnostic, int multi_label, int max_det, int max_nms,
+                      float max_wh, int flags, int64_t max_candidates, float* out7, int64_t* counts, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  if (!pred || !out7 || !counts || !workspace) return Y5OBB_EINVAL;
+  if (batch <= 0 || anchors <= 0 || nc <= 0 || nc > 64 || no != nc + 5 + 180 || max_det <= 0 || max_candidates <= 0)
+    return Y5OBB_EINVAL;
+  const long long rows = batch * anchors;
+  if (rows > 0x7FFFFFF0ll || max_candidates > 0x7FFFFFF0ll) return Y5OBB_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  PPWs w = carve_pp(workspace, rows, (int)batch, max_candidates, max_nms);
+  if (w.total > workspace_bytes) return Y5OBB_EWORKSPACE;
+  PPArgs a;
+  a.pred = pred;
+  a.rows = rows;
+  a.A = (int)anchors;
+  a.no = no;
+  a.nc = nc;
+  a.conf = conf_thres;
+  a.multi_label = (multi_label && nc > 1) ? 1 : 0;  // general.py:797
+  a.agnostic = agnostic;
+  a.class_mask = class_mask;
+  a.max_wh = max_wh;
+  const unsigned g = (unsigned)((rows * 32 + 255) / 256);
+  k_pp_count<<<g, 256, 0, st>>>(a, w.cnt);
+  Y5_LAUNCH_CHECK();
+  size_t sb = w.scan_bytes;
+  Y5_CUDA(cub::DeviceScan::ExclusiveSum(w.scan_tmp, sb, w.cnt, w.off, (int)rows, st));
+  k_pp_emit<<<g, 256, 0, st>>>(a, w.cnt, w.off, max_candidates, w.dets5, w.scores, w.image_ids, w.out7, w.n_valid);
+  Y5_LAUNCH_CHECK();
+  long long mpi = max_nms > 0 && max_nms < max_candidates ? max_nms : max_candidates;
+  int rc = nms_impl(w.dets5, w.scores, w.image_ids, max_candidates, batch, mpi, iou_thres,
+                    flags | Y5OBB_NMS_DROP_SMALL, max_det, w.keep, w.n_keep, w.seg_off, w.nms_ws, w.nms_bytes, st,
+                    w.n_valid, max_nms);
+  if (rc) return rc;
+  dim3 gg((unsigned)((max_det + 127) / 128), (unsigned)batch);
+  k_pp_gather<<<gg, 128, 0, st>>>(w.out7, w.keep, w.n_keep, w.seg_off, (int)batch, max_det, out7, counts, w.n_valid);
+  Y5_LAUNCH_CHECK();
+  return Y5OBB_OK;
 }
 
 int y5obb_rbox_iou_pairs_f32(const float* a5, const float* b5, float* iou_out, int64_t n, void* stream) {

@@ -1,0 +1,65 @@
+"""Host-side mirror of /root/reference/utils/general.py:772-862 (non_max_suppression_obb) — same signature
+and return value; the per-image Python loop, its >= 6 host syncs per image and the N^2/8-byte mask copy are
+replaced by one device pipeline (csrc/nms.cu: k_pp_* + batched rotated NMS) and ONE small D2H read of the
+per-image counts at the end."""
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+
+MAX_WH = 4096     # general.py:793
+MAX_NMS = 30000   # general.py:794
+
+
+def non_max_suppression_obb(prediction: torch.Tensor, conf_thres: float = 0.25, iou_thres: float = 0.45,
+                            classes: Optional[Sequence[int]] = None, agnostic: bool = False, multi_label: bool = False,
+                            labels=(), max_det: int = 1500) -> List[torch.Tensor]:
+    """Runs Non-Maximum Suppression (NMS) on inference results_obb.
+
+    Args:
+        prediction (tensor): (b, n_all_anchors, [cx cy l s obj num_cls theta_cls]) fp32 on a CUDA device
+    Returns:
+        list of detections, len=batch_size, on (n,7) tensor per image [xylsθ, conf, cls] θ ∈ [-pi/2, pi/2)
+    """
+    _lib.require_cuda(prediction, "prediction")
+    if prediction.dim() != 3:
+        raise RuntimeError("prediction must be [batch, anchors, nc+185]")
+    nc = prediction.shape[2] - 5 - 180
+    assert 0 <= conf_thres <= 1, f'Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0'
+    assert 0 <= iou_thres <= 1, f'Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0'
+    if labels:
+        raise RuntimeError("apriori `labels` (autolabelling) are not part of the hot path")
+    if nc < 1 or nc > 64:
+        raise RuntimeError(f"nc={nc} unsupported (1..64)")
+    B, A, no = prediction.shape
+    dev = prediction.device
+    if B == 0 or A == 0:
+        return [torch.zeros((0, 7), device=dev) for _ in range(B)]
+    pred = prediction.detach().float().contiguous()  # half inputs are widened (the arithmetic is defined in fp32)
+    mask = (1 << 64) - 1
+    if classes is not None:
+        mask = 0
+        for c in classes:
+            mask |= 1 << int(c)
+    L = _lib.lib()
+    out = torch.empty((B, max_det, 7), dtype=torch.float32, device=dev)
+    counts = torch.empty(B + 1, dtype=torch.int64, device=dev)
+    worst = B * A * (nc if (multi_label and nc > 1) else 1)
+    cap = min(worst, max(B * 4 * MAX_NMS, 1 << 18))
+    while True:
+        with torch.cuda.device(dev):
+            nbytes = L.y5obb_nms_obb_workspace_bytes(B, A, cap, MAX_NMS)
+            ws = _lib.workspace(nbytes, dev, "nms_obb")
+            rc = L.y5obb_nms_obb_f32(pred.data_ptr(), B, A, no, nc, float(conf_thres), float(iou_thres), mask,
+                                     int(bool(agnostic)), int(bool(multi_label)), int(max_det), MAX_NMS, float(MAX_WH),
+                                     _lib.NMS_STRICT_GT, cap, out.data_ptr(), counts.data_ptr(), ws.data_ptr(),
+                                     ws.numel(), _lib.stream_ptr(dev))
+        _lib.check(rc, "y5obb_nms_obb_f32")
+        c = counts.tolist()  # the one host read: rows per image (+ total candidates)
+        if c[B] <= cap:
+            break
+        cap = min(worst, max(c[B], cap * 4))  # rare: more candidates than the optimistic capacity
+    if any(k < 0 for k in c[:B]):
+        raise RuntimeError("y5obb_nms_obb_f32: internal capacity error")
+    return [out[b, :c[b]] for b in range(B)]
