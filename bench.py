@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric on its single-GPU configuration.
+
+Workload (config.workload): configs[1] = yolov5s-OBB inference, batch 16, 1024x1024 synthetic DOTA-shaped
+tiles, the three stages the reference's `val.py --task speed` times (val.py:183-207): pre-process
+(uint8 -> normalised), inference (Model.forward), NMS (non_max_suppression_obb, conf 0.25 / IoU 0.45,
+val.py:378-383).  Metric: images/s.
+
+  value      whole-job images/s with the uint8 batch already resident in HBM (device timing, CUDA events,
+             max over ranks)
+  e2e        the same step through the public API from PINNED HOST memory: H2D of the uint8 batch and D2H
+             of the detections inside the timed region
+  roofline   conv_tc_kernel (tcgen05 implicit GEMM), the dominant kernel: algorithmic conv FLOPs per launch
+             / mean launch duration measured with CUDA events around every launch in the timed steps,
+             against MEASURED_PEAKS.json's sustained bf16 figure
+  cpu_baseline   the oracle port (fp32 torch restatement of the reference's eager CPU path + the reference's
+             own CPU NMS kernel from oracle/_ref when present) on the host cores, bounded sample
+
+--impl reference runs that CPU arm alone (rank 0 only under torchrun).  N>1 = independent replicas, one
+b16 batch per GPU (the path shards by image batch, no data-path collective): weak scaling.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+MODEL, BATCH, IMG, NC = "s", 16, 1024, 15
+CONF, IOU, MAX_DET = 0.25, 0.45, 1500
+FWD_GFLOP_PER_IMG = 44.60  # BASELINE.md §2 (conv-only forward, yolov5s @1024, nc=15)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default=MODEL)
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(tflops=float(d.get("bf16_tflops_sustained", 1400.0)), hbm=float(d.get("hbm_gbs", 6650.0)),
+                    src="measured (MEASURED_PEAKS.json, sustained bf16)")
+    return dict(tflops=1400.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.p = [], None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            self.p.kill()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].startswith("Active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def synth_batch(batch, seed):
+    """uint8 DOTA-shaped synthetic tiles (tests/tilegen.py), on the host (pinned by the caller).  Four distinct
+    seeded tiles are tiled to the batch: generation is host-side Python and not part of any timed region."""
+    import torch
+    from tests.tilegen import synth_tiles
+    base = synth_tiles(min(batch, 4), IMG, seed)
+    reps = (batch + base.shape[0] - 1) // base.shape[0]
+    return base.repeat(reps, 1, 1, 1)[:batch].contiguous()
+
+
+def build_model(size, device=None):
+    """Seeded random-init yolov5-OBB (no checkpoints exist offline), calibrated identically on every arm so
+    that the NMS stage sees a DOTA-like few thousand candidates per tile (tests/modelgen.py)."""
+    from tests.modelgen import calibrated_bench_model
+    m = calibrated_bench_model(size, nc=NC, seed=0, conf=CONF)
+    return m.to(device) if device is not None else m
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's eager CPU path (+ the reference's own CPU NMS kernel)
+# ------------------------------------------------------------------------------------------------
+def cpu_arm(size, batch, steps, warmup, budget_s=25.0, use_ref_nms=False):
+    import torch
+    from oracle import model_ref
+    from oracle.postprocess import non_max_suppression_obb as cpu_nms
+    torch.set_grad_enabled(False)
+    m = build_model(size)
+    cores = torch.get_num_threads()
+    b = 1  # bounded sample: one tile per step of the same workload
+    x8 = synth_batch(b, 0)
+    kind = "port"
+    nms_note = "C++ oracle rotated NMS (1 thread)"
+    if use_ref_nms:  # the reference's own nms_rotated_cpu kernel, compiled from /root/reference into oracle/_ref
+        try:
+            import oracle.postprocess as pp
+            from oracle.build_ref import load_ref
+            ref = load_ref()
+
+            def ref_obb_nms(dets, scores, thr, mode=0):
+                import numpy as np
+                d, s_ = torch.from_numpy(np.ascontiguousarray(dets)), torch.from_numpy(np.ascontiguousarray(scores))
+                ok = ~(d[:, 2:4].min(1)[0] < 0.001)  # nms_rotated_wrapper.py:32-39
+                idx = torch.arange(d.shape[0])[ok]
+                return idx[ref.nms_rotated_cpu(d[ok], s_[ok], float(thr))].numpy()
+
+            pp._oracle_obb_nms = ref_obb_nms
+            nms_note = "the reference's own nms_rotated_cpu extension (oracle/_ref, 1 thread)"
+        except Exception as e:  # pragma: no cover
+            nms_note += f" [oracle/_ref unavailable: {type(e).__name__}]"
+
+    def step():
+        x = x8.float() / 255                      # pre-process (val.py:187-188)
+        pred, _ = model_ref.forward(m, x)         # inference
+        return cpu_nms(pred, CONF, IOU, multi_label=True, max_det=MAX_DET, nms_mode=0)  # NMS (CPU rule >=)
+
+    t0 = time.perf_counter()
+    for _ in range(max(1, min(warmup, 2))):
+        step()
+    per = (time.perf_counter() - t0) / max(1, min(warmup, 2))
+    n = max(1, min(steps, int(budget_s / max(per, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(n):
+        step()
+    dt = (time.perf_counter() - t0) / n
+    return dict(value=b / dt, unit="images/s", cores=cores, kind=kind, ms_per_step=dt * 1e3, steps=n,
+                sample=f"yolov5{size} fp32 eager-torch restatement of the reference CPU path + {nms_note}, "
+                       f"{n} steps of 1 tile 1024x1024 (of the b{batch} workload), torch {torch.__version__}, {cores} threads")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_arm(args.model, args.batch, args.steps, args.warmup, budget_s=60.0, use_ref_nms=True)
+    line = {
+        "impl": "reference", "metric": "images/s", "value": cb["value"], "unit": "images/s", "n_gpus": args.gpus,
+        "steps": cb["steps"], "warmup": min(args.warmup, 2), "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {"workload": f"yolov5{args.model}-OBB inference b{args.batch} 1024x1024 (BASELINE configs[1], val.py --task speed: "
+                        f"pre-process + Model.forward + non_max_suppression_obb conf {CONF} iou {IOU} multi_label)",
+            "batch_per_gpu": args.batch, "imgsz": IMG, "nc": NC, "parallelism": f"replicas x{args.gpus} (no collective)",
+            "l2": "per-step working set (activations > 3 GB) exceeds the 126 MB L2; no explicit flush"}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from yolov5_obb_b200 import _lib
+    from yolov5_obb_b200.general import non_max_suppression_obb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = args.batch
+    model = build_model(args.model, dev)
+    x_host = synth_batch(B, seed=rank).pin_memory()
+    x_dev = x_host.to(dev)
+    model(x_dev)  # builds the plan
+    eng = model._engines[(tuple(x_dev.shape), dev.index)]
+    conv_flops = [c.info()["flops"] for c in eng.convs]
+    n_conv = len(eng.convs)
+    st = _lib.stream_ptr(dev)
+    L = _lib.lib()
+    conv_handles = {c._h.value for c in eng.convs}
+
+    def step_device():
+        pred, _ = model(x_dev)
+        return non_max_suppression_obb(pred, CONF, IOU, multi_label=True, max_det=MAX_DET)
+
+    out_host = torch.empty((B, MAX_DET, 7), dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        xd = x_host.to(dev, non_blocking=True)                       # H2D, pinned
+        pred, _ = model(xd)
+        dets = non_max_suppression_obb(pred, CONF, IOU, multi_label=True, max_det=MAX_DET)
+        nb = 0
+        for b, d in enumerate(dets):                                  # D2H of the step's result
+            out_host[b, :d.shape[0]].copy_(d, non_blocking=True)
+            nb += d.numel() * 4
+        torch.cuda.current_stream().synchronize()
+        return nb
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = None
+        for _ in range(steps):
+            r = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, r
+
+    for _ in range(max(args.warmup, 3)):
+        dets = step_device()
+    cand_per_img = None
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_total, dets = timed(step_device, args.steps)
+    clocks = sampler.stop() if sampler else None
+    ms_step = ms_total / args.steps
+    value = world * B / (ms_step / 1e3)
+
+    for _ in range(3):
+        step_e2e()
+    ms_e2e, d2h = timed(step_e2e, args.steps)
+    e2e_value = world * B / (ms_e2e / args.steps / 1e3)
+
+    # roofline leg: CUDA events around every conv launch of the timed steps (same stream, after warm-up)
+    pk = peaks()
+    steps_r = min(args.steps, 5)
+    evs = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_conv)]
+           for _ in range(steps_r)]
+    x_f = x_dev
+    torch.cuda.synchronize()
+    for s in range(steps_r):
+        _lib.check(L.y5obb_stem_s2d_u8(x_f.data_ptr(), eng.x_s2d.data_ptr(), B, IMG, IMG, st), "s2d")
+        ci = 0
+        for op in eng.ops:
+            h = op.__defaults__[0] if op.__defaults__ else None
+            is_conv = isinstance(h, type(eng.convs[0]._h)) and h.value in conv_handles
+            if is_conv:
+                evs[s][ci][0].record()
+            op(st)
+            if is_conv:
+                evs[s][ci][1].record()
+                ci += 1
+    torch.cuda.synchronize()
+    conv_ms = [sum(evs[s][i][0].elapsed_time(evs[s][i][1]) for s in range(steps_r)) / steps_r for i in range(n_conv)]
+    tot_conv_ms = sum(conv_ms)
+    ach_tflops = sum(conv_flops) / (tot_conv_ms / 1e3) / 1e12
+    roof = {"bound": "tensor", "kernel": "conv_tc_kernel", "achieved": ach_tflops, "peak": pk["tflops"],
+            "unit": "TFLOP/s", "frac": ach_tflops / pk["tflops"], "traffic": None, "peak_source": pk["src"],
+            "launches_per_step": n_conv, "flops_per_launch": sum(conv_flops) / n_conv,
+            "mean_launch_us": tot_conv_ms / n_conv * 1e3, "conv_share_of_step": tot_conv_ms / ms_step,
+            "hbm_view": {"algorithmic_GB_per_step": eng.hbm_bytes / 1e9,
+                         "achieved_GBps": eng.hbm_bytes / (tot_conv_ms / 1e3) / 1e9, "peak_GBps": pk["hbm"]}}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    line = {
+        "metric": "images/s", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic (seeded DOTA-shaped uint8 tiles, seeded random-init weights with calibrated BN/Detect statistics)",
+        "config": workload_config(args),
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(x_host.numel()),
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": (1 + len(eng.ops) + 10) * args.steps,
+        "detections_per_image": float(sum(d.shape[0] for d in dets)) / B,
+        "clocks": clocks, "roofline": roof,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        cb = cpu_arm(args.model, B, args.steps, args.warmup)
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -131,6 +131,8 @@ void y5obb_conv_destroy(y5obb_conv_t* conv);
  * y5obb_sppf_pool: SPPF's three chained MaxPool2d(5,1,2) (models/common.py:181-196) in one pass over
  * channels [0,C) of an NHWC bf16 buffer, results at channel offsets C, 2C, 3C (replaces torch.cat). */
 int y5obb_stem_s2d(const float* x_nchw, void* out_nhwc16, int B, int H, int W, void* stream);
+/* same for a uint8 image, with the caller-side `/ 255` (train.py:299, val.py:187-188) folded in */
+int y5obb_stem_s2d_u8(const uint8_t* x_nchw, void* out_nhwc16, int B, int H, int W, void* stream);
 int y5obb_sppf_pool(void* buf, int64_t pix_stride, int B, int H, int W, int C, void* stream);
 
 #ifdef __cplusplus

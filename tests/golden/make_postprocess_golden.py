@@ -20,11 +20,7 @@ from tests.predgen import synth_pred  # noqa: E402
 
 
 
-CFGS = {"multi": dict(conf_thres=0.25, iou_thres=0.45, multi_label=True, max_det=1500),
-        "best": dict(conf_thres=0.3, iou_thres=0.4, multi_label=False, max_det=1000),
-        "cls": dict(conf_thres=0.25, iou_thres=0.45, multi_label=True, classes=[1, 5, 9], max_det=50),
-        "agn": dict(conf_thres=0.28, iou_thres=0.2, multi_label=True, agnostic=True, max_det=1500),
-        "lowconf": dict(conf_thres=0.001, iou_thres=0.6, multi_label=True, max_det=300)}
+from tests.golden_cfgs import PP_CFGS as CFGS, PP_ANCHORS as ANCHORS  # noqa: E402
 
 
 def main():
@@ -34,7 +30,7 @@ def main():
     for name, kw in CFGS.items():
         seed = 0
         while True:
-            pred = torch.from_numpy(synth_pred(2, 3000, 15, seed))
+            pred = torch.from_numpy(synth_pred(2, ANCHORS.get(name, 3000), 15, seed))
             res = non_max_suppression_obb(pred.clone(), **kw)
             # margin: both oracle comparison rules must reproduce the reference result exactly
             o0 = oracle_nms(pred, nms_mode=0, **kw)
@@ -43,6 +39,7 @@ def main():
                 break
             seed += 1
         out[f"{name}/seed"] = np.int64(seed)
+        out[f"{name}/anchors"] = np.int64(ANCHORS.get(name, 3000))
         for b, r in enumerate(res):
             out[f"{name}/{b}"] = r.numpy()
         print(name, "seed", seed, [tuple(r.shape) for r in res])

@@ -47,6 +47,38 @@ __global__ void k_stem_s2d(const float* __restrict__ x, __nv_bfloat16* __restric
   }
 }
 
+// uint8 NCHW image: the caller-side `imgs.float() / 255` (train.py:299, val.py:187-188, detect.py:108-109)
+// folded into the same pass
+__global__ void k_stem_s2d_u8(const uint8_t* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int H, int W) {
+  const int Ho = H >> 1, Wo = W >> 1;
+  const long long total = (long long)B * Ho * Wo;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int wo = (int)(i % Wo);
+    const long long r = i / Wo;
+    const int ho = (int)(r % Ho);
+    const int b = (int)(r / Ho);
+    float v[16];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const uint8_t* p = x + (((long long)b * 3 + c) * H + 2 * ho) * W + 2 * wo;
+      const uchar2 top = *reinterpret_cast<const uchar2*>(p);
+      const uchar2 bot = *reinterpret_cast<const uchar2*>(p + W);
+      v[0 * 3 + c] = (float)top.x / 255.0f;
+      v[1 * 3 + c] = (float)top.y / 255.0f;
+      v[2 * 3 + c] = (float)bot.x / 255.0f;
+      v[3 * 3 + c] = (float)bot.y / 255.0f;
+    }
+    v[12] = v[13] = v[14] = v[15] = 0.f;
+    uint4 o[2];
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(o);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) h[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+    uint4* dst = reinterpret_cast<uint4*>(out + i * 16);
+    dst[0] = o[0];
+    dst[1] = o[1];
+  }
+}
+
 __device__ __forceinline__ void vmax8(uint4& a, const uint4& b) {
   __nv_bfloat162* x = reinterpret_cast<__nv_bfloat162*>(&a);
   const __nv_bfloat162* y = reinterpret_cast<const __nv_bfloat162*>(&b);
@@ -104,6 +136,16 @@ int y5obb_stem_s2d(const float* x_nchw, void* out_nhwc16, int B, int H, int W, v
   const long long total = (long long)B * (H / 2) * (W / 2);
   const int grid = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 16);
   k_stem_s2d<<<grid, 256, 0, (cudaStream_t)stream>>>(x_nchw, static_cast<__nv_bfloat16*>(out_nhwc16), B, H, W);
+  Y5_LAUNCH_CHECK();
+  return Y5OBB_OK;
+}
+
+int y5obb_stem_s2d_u8(const uint8_t* x_nchw, void* out_nhwc16, int B, int H, int W, void* stream) {
+  if (!x_nchw || !out_nhwc16 || B <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1)) return Y5OBB_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(x_nchw) & 1) || (reinterpret_cast<uintptr_t>(out_nhwc16) & 15)) return Y5OBB_EINVAL;
+  const long long total = (long long)B * (H / 2) * (W / 2);
+  const int grid = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 16);
+  k_stem_s2d_u8<<<grid, 256, 0, (cudaStream_t)stream>>>(x_nchw, static_cast<__nv_bfloat16*>(out_nhwc16), B, H, W);
   Y5_LAUNCH_CHECK();
   return Y5OBB_OK;
 }

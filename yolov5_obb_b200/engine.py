@@ -203,15 +203,22 @@ class InferenceEngine:
         self.n_launches = len(self.ops) + 1
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        """x: [B,3,H,W] fp32 in [0,1] on this engine's device -> pred [B, A, no] fp32 (engine-owned buffer)."""
+        """x: [B,3,H,W] fp32 in [0,1] (or uint8 0..255) on this engine's device -> pred [B, A, no] fp32
+        (engine-owned buffer, overwritten by the next call)."""
         _lib.require_cuda(x, "x")
         if tuple(x.shape) != (self.B, 3, self.H, self.W):
             raise RuntimeError(f"engine was planned for {(self.B, 3, self.H, self.W)}, got {tuple(x.shape)}")
-        x = x.contiguous().float()
         st = _lib.stream_ptr(self.device)
         L = _lib.lib()
         with torch.cuda.device(self.device):
-            _lib.check(L.y5obb_stem_s2d(x.data_ptr(), self.x_s2d.data_ptr(), self.B, self.H, self.W, st), "y5obb_stem_s2d")
+            if x.dtype == torch.uint8:  # raw image: the caller-side `/ 255` is folded into the layout pass
+                x = x.contiguous()
+                _lib.check(L.y5obb_stem_s2d_u8(x.data_ptr(), self.x_s2d.data_ptr(), self.B, self.H, self.W, st),
+                           "y5obb_stem_s2d_u8")
+            else:
+                x = x.contiguous().float()
+                _lib.check(L.y5obb_stem_s2d(x.data_ptr(), self.x_s2d.data_ptr(), self.B, self.H, self.W, st),
+                           "y5obb_stem_s2d")
             for op in self.ops:
                 rc = op(st)
                 if rc:
