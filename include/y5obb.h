@@ -86,7 +86,8 @@ int y5obb_nms_obb_f32(const float* pred, int64_t batch, int64_t anchors, int no,
  * nn.Upsample(2x nearest) (models/yolov5*.yaml head) and models/yolo.py:49-81 (Detect).
  * Activations are NHWC bf16; a tensor argument is a channel SLICE of a wider buffer: `ptr` points at
  * the slice's first channel of pixel 0 and `*_pix_stride` is the element distance between pixels.
- * Weights are bf16 packed [KH*KW][cout_pad][cin_pad] (K-major), bias fp32 [cout_pad]; the paddings and
+ * Weights are bf16 packed [KH*KW][cout_pad][cin_pad] (K-major), bias fp32 [cout_pad + 32]
+ * (the epilogue reads it in 32-wide chunks); the paddings and
  * the tile shape come from y5obb_conv_tiling so that host packing and kernel agree. */
 typedef struct y5obb_conv y5obb_conv_t;
 

@@ -80,14 +80,14 @@ def tiling(cin: int, cout: int, mode: int = MODE_CONV, det_no: int = 0):
 
 
 def pack_weights(w: torch.Tensor, bias: Optional[torch.Tensor], mode: int = MODE_CONV, det_no: int = 0):
-    """[Cout, Cin, KH, KW] fp32 (+ bias [Cout]) -> bf16 [KH*KW, cout_pad, cin_pad] K-major, fp32 bias [cout_pad].
+    """[Cout, Cin, KH, KW] fp32 (+ bias [Cout]) -> bf16 [KH*KW, cout_pad, cin_pad] K-major, fp32 bias [cout_pad + 32].
 
     Detect mode places anchor a's det_no rows at [a*block_n, a*block_n + det_no) so one N tile == one anchor.
     """
     cout, cin, kh, kw = w.shape
     bk, bn, cin_pad, cout_pad, nt = tiling(cin, cout, mode, det_no)
     wp = torch.zeros((kh * kw, cout_pad, cin_pad), dtype=torch.float32, device=w.device)
-    bp = torch.zeros((cout_pad,), dtype=torch.float32, device=w.device)
+    bp = torch.zeros((cout_pad + 32,), dtype=torch.float32, device=w.device)  # epilogue reads bias in 32-wide chunks
     wt = w.detach().float().permute(2, 3, 0, 1).reshape(kh * kw, cout, cin)
     if mode == MODE_DETECT:
         for a in range(nt):

@@ -34,14 +34,17 @@ namespace {
 
 constexpr int BM = 128;  // output pixels per tile == TMEM lanes
 constexpr int MAX_STAGES = 8;
-constexpr int NUM_THREADS = 192;
-constexpr int SMEM_BUDGET = 200 * 1024;
+constexpr int NUM_THREADS = 320;          // TMA producer, MMA issuer, 8 epilogue warps
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_STAGE_BYTES = 32 * 64;  // 32 pixels x 32 bf16 channels, 64-byte swizzled
+constexpr int SMEM_BUDGET = 190 * 1024;   // operand ring; + 32 KB epilogue staging + alignment slack < 227 KB
 
 enum Mode : int { MODE_CONV = 0, MODE_DETECT = 1 };
 
 struct ConvK {
   CUtensorMap tmA;
   CUtensorMap tmB;
+  CUtensorMap tmO;  // output slice, box {32 ch, min(Wt,32), 32/min(Wt,32), 1}, 64-byte swizzle (MODE_CONV)
   // geometry
   int B, Hout, Wout;
   int Wt, Ht, tiles_w, tiles_h;
@@ -87,8 +90,17 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvK& p, int t) {
   return c;
 }
 
-__device__ __forceinline__ float silu(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
-__device__ __forceinline__ float sigmoidf(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
+// x * sigmoid(x) = h + h * tanh(h), h = x / 2: one MUFU op (tanh.approx, rel. error ~2^-11) instead of ex2 + rcp
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float silu(float v) {
+  const float h = 0.5f * v;
+  return fmaf(h, tanh_fast(h), h);
+}
+__device__ __forceinline__ float sigmoid_fast(float v) { return fmaf(0.5f, tanh_fast(0.5f * v), 0.5f); }
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -115,13 +127,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&p.tmA);
     ptx::prefetch_tmap(&p.tmB);
+    if (p.mode == MODE_CONV) ptx::prefetch_tmap(&p.tmO);
     for (int s = 0; s < p.stages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full[a], 1);
-      ptx::mbar_init(&tmem_empty[a], 128);
+      ptx::mbar_init(&tmem_empty[a], EPI_WARPS * 32);
     }
     ptx::fence_mbar_init();
   }
@@ -196,11 +209,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =====================
+    // ===================== epilogue: 8 warps =====================
+    // warp e = warp - 2; TMEM lane quarter q = warp & 3 (hardware rule: a warp reads lanes 32*(warp%4)..+31);
+    // the two warps sharing a quarter split the columns: 32-column chunks with (chunk & 1) == half.
+    const int e = warp - 2;
     const int q = warp & 3;
+    const int half = e >> 2;
     const int row = q * 32 + lane;
     const int hl = row / p.Wt;
     const int wl = row - hl * p.Wt;
+    // this warp's 32 pixels as a TMA box: {32 ch, bw, 32 / bw, 1}
+    const int bw = min(p.Wt, 32);
+    const int box_h0 = (q * 32) / p.Wt, box_w0 = (q * 32) % p.Wt;
+    uint8_t* stage = smem + (size_t)p.stages * stage_bytes + (size_t)e * (2 * EPI_STAGE_BYTES);
+    int sbuf = 0;
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const TileCoord c = decode_tile(p, t);
@@ -215,53 +237,69 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       const uint32_t taddr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(q * 32) << 16);
 
       if (p.mode == MODE_CONV) {
-        __nv_bfloat16* orow = p.out + pix * p.out_pix_stride + c.n0;
         const __nv_bfloat16* rrow = p.res ? p.res + pix * p.res_pix_stride + c.n0 : nullptr;
         __nv_bfloat16* urow = nullptr;
         if (p.out2x) urow = p.out2x + (((long long)c.b * 2 * p.Hout + 2 * h) * (2 * p.Wout) + 2 * w) * p.out2x_pix_stride + c.n0;
         const long long up_row_step = (long long)(2 * p.Wout) * p.out2x_pix_stride;
         const int nvalid = min(p.BN, p.Cout - c.n0);
-        for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        for (int c0 = half * 32; c0 < nvalid; c0 += 64) {
           uint32_t r[32];
           ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)c0, r);
           ptx::tmem_ld_wait();
-          if (valid && c0 < nvalid) {
+          // the staging buffer about to be overwritten must have been read by its TMA store
+          if (lane == 0) ptx::tma_store_wait_read<1>();
+          __syncwarp();
+          uint8_t* sb = stage + sbuf * EPI_STAGE_BYTES;
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + c.n0 + c0);
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {  // 8 channels = one 16-byte store
-              const int cg = c0 + g * 8;
-              if (cg < nvalid) {
-                float v[8];
+          for (int g = 0; g < 4; ++g) {  // 8 channels = one 16-byte chunk
+            const int cg = c0 + g * 8;
+            float v[8];
+            const float4 ba = __ldg(b4 + 2 * g), bb = __ldg(b4 + 2 * g + 1);
+            v[0] = __uint_as_float(r[g * 8 + 0]) + ba.x;
+            v[1] = __uint_as_float(r[g * 8 + 1]) + ba.y;
+            v[2] = __uint_as_float(r[g * 8 + 2]) + ba.z;
+            v[3] = __uint_as_float(r[g * 8 + 3]) + ba.w;
+            v[4] = __uint_as_float(r[g * 8 + 4]) + bb.x;
+            v[5] = __uint_as_float(r[g * 8 + 5]) + bb.y;
+            v[6] = __uint_as_float(r[g * 8 + 6]) + bb.z;
+            v[7] = __uint_as_float(r[g * 8 + 7]) + bb.w;
+            if (p.act) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[g * 8 + e]) + __ldg(p.bias + c.n0 + cg + e);
-                if (p.act) {
+              for (int k = 0; k < 8; ++k) v[k] = silu(v[k]);
+            }
+            if (rrow && valid && cg < nvalid) {
+              const uint4 rv = *reinterpret_cast<const uint4*>(rrow + cg);
+              const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
-                  for (int e = 0; e < 8; ++e) v[e] = silu(v[e]);
-                }
-                if (rrow) {
-                  const uint4 rv = *reinterpret_cast<const uint4*>(rrow + cg);
-                  const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rv);
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const float2 f = __bfloat1622float2(rh[e]);
-                    v[2 * e] += f.x;
-                    v[2 * e + 1] += f.y;
-                  }
-                }
-                uint4 o;
-                o.x = pack_bf16(v[0], v[1]);
-                o.y = pack_bf16(v[2], v[3]);
-                o.z = pack_bf16(v[4], v[5]);
-                o.w = pack_bf16(v[6], v[7]);
-                *reinterpret_cast<uint4*>(orow + cg) = o;
-                if (urow) {
-                  *reinterpret_cast<uint4*>(urow + cg) = o;
-                  *reinterpret_cast<uint4*>(urow + p.out2x_pix_stride + cg) = o;
-                  *reinterpret_cast<uint4*>(urow + up_row_step + cg) = o;
-                  *reinterpret_cast<uint4*>(urow + up_row_step + p.out2x_pix_stride + cg) = o;
-                }
+              for (int k = 0; k < 4; ++k) {
+                const float2 f = __bfloat1622float2(rh[k]);
+                v[2 * k] += f.x;
+                v[2 * k + 1] += f.y;
               }
             }
+            uint4 o;
+            o.x = pack_bf16(v[0], v[1]);
+            o.y = pack_bf16(v[2], v[3]);
+            o.z = pack_bf16(v[4], v[5]);
+            o.w = pack_bf16(v[6], v[7]);
+            // 64-byte swizzle (Swizzle<2,4,3>): 16-byte chunk index ^= (row >> 1) & 3
+            *reinterpret_cast<uint4*>(sb + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) = o;
+            if (urow && valid && cg < nvalid) {
+              *reinterpret_cast<uint4*>(urow + cg) = o;
+              *reinterpret_cast<uint4*>(urow + p.out2x_pix_stride + cg) = o;
+              *reinterpret_cast<uint4*>(urow + up_row_step + cg) = o;
+              *reinterpret_cast<uint4*>(urow + up_row_step + p.out2x_pix_stride + cg) = o;
+            }
           }
+          ptx::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            // rows beyond the image and channels beyond Cout are clipped by the tensor map
+            ptx::tma_store_4d(&p.tmO, sb, c.n0 + c0, c.w0 + box_w0, c.h0 + box_h0, c.b);
+            ptx::tma_store_commit();
+          }
+          sbuf ^= 1;
         }
       } else {
         // Detect: N tile nt == anchor nt; columns [0, det_no) are that anchor's outputs.
@@ -271,21 +309,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                       ((long long)c.b * p.det_rows_per_image + p.det_row_off + ((long long)a * p.Hout + h) * p.Wout + w) *
                           p.det_no;
         const float aw = p.det_anchor[2 * a], ah = p.det_anchor[2 * a + 1];
-        for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        for (int c0 = half * 32; c0 < p.det_no; c0 += 64) {
           uint32_t r[32];
           ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)c0, r);
           ptx::tmem_ld_wait();
-          if (valid && c0 < p.det_no) {
+          if (valid) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + c.n0 + c0);
 #pragma unroll
             for (int g = 0; g < 8; ++g) {  // 4 floats = one 16-byte store
               const int cg = c0 + g * 4;
               if (cg < p.det_no) {
+                const float4 bv = __ldg(b4 + g);
                 float v[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) v[e] = __uint_as_float(r[g * 4 + e]) + __ldg(p.bias + c.n0 + cg + e);
+                v[0] = __uint_as_float(r[g * 4 + 0]) + bv.x;
+                v[1] = __uint_as_float(r[g * 4 + 1]) + bv.y;
+                v[2] = __uint_as_float(r[g * 4 + 2]) + bv.z;
+                v[3] = __uint_as_float(r[g * 4 + 3]) + bv.w;
                 if (p.det_decode) {
 #pragma unroll
-                  for (int e = 0; e < 4; ++e) v[e] = sigmoidf(v[e]);
+                  for (int k = 0; k < 4; ++k) v[k] = sigmoid_fast(v[k]);
                   if (cg == 0) {  // xy, wh (models/yolo.py:73-74)
                     v[0] = (v[0] * 2.0f - 0.5f + (float)w) * p.det_stride;
                     v[1] = (v[1] * 2.0f - 0.5f + (float)h) * p.det_stride;
@@ -293,7 +335,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     v[3] = (v[3] * 2.0f) * (v[3] * 2.0f) * ah;
                   }
                 }
-                *reinterpret_cast<float4*>(orow + cg) = make_float4(v[0], v[1], v[2], v[3]);
+                __stcs(reinterpret_cast<float4*>(orow + cg), make_float4(v[0], v[1], v[2], v[3]));
               }
             }
           }
@@ -302,6 +344,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tmem_empty[acc]);
     }
+    if (lane == 0) ptx::tma_store_wait_all();
   }
 
   ptx::tc_fence_before();
@@ -496,15 +539,32 @@ int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
       return Y5OBB_ECUDA;
     }
   }
+  if (d->mode == MODE_CONV) {  // output: (C, W, H, B); each epilogue warp stores its 32 pixels x 32 channels
+    const int bw = std::min(k.Wt, 32);
+    cuuint64_t dims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)Wout, (cuuint64_t)Hout, (cuuint64_t)d->B};
+    cuuint64_t strides[3] = {(cuuint64_t)d->out_pix_stride * 2, (cuuint64_t)d->out_pix_stride * 2 * Wout,
+                             (cuuint64_t)d->out_pix_stride * 2 * Wout * Hout};
+    cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)(32 / bw), 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&k.tmO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, d->out, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      g_last_cuda_error = (int)r;
+      delete o;
+      return Y5OBB_ECUDA;
+    }
+  }
   const int total = k.n_tiles_m * k.n_tiles_n;
   o->grid = std::min(total, sm_count());
   // >= 116 KB so that two CTAs (each owning all 512 TMEM columns) can never share an SM
-  o->smem = std::max<size_t>((size_t)k.stages * (k.a_bytes + k.b_stage_bytes) + 1024, 116 * 1024);
+  o->smem = std::max<size_t>((size_t)k.stages * (k.a_bytes + k.b_stage_bytes) + EPI_WARPS * 2 * EPI_STAGE_BYTES + 1024,
+                             116 * 1024);
   o->flops = 2.0 * d->B * Hout * Wout * (double)d->Cout * d->Cin * d->KH * d->KW;
   o->hbm_bytes = 2.0 * d->B * ((double)d->Hin * d->Win * d->Cin + (double)Hout * Wout * d->Cout * (d->res ? 2 : 1));
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + 2048);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + EPI_WARPS * 2 * EPI_STAGE_BYTES + 2048);
     if (e != cudaSuccess) {
       delete o;
       return cuda_fail(e);
