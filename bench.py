@@ -275,7 +275,7 @@ def run_ours(args):
     x_f = x_dev
     torch.cuda.synchronize()
     for s in range(steps_r):
-        _lib.check(L.y5obb_stem_s2d_u8(x_f.data_ptr(), eng.x_s2d.data_ptr(), B, IMG, IMG, st), "s2d")
+        _lib.check(L.y5obb_stem_s2d_u8(x_f.data_ptr(), eng.x_s2d.data_ptr(), B, IMG, IMG, 1, st), "s2d")
         ci = 0
         for op in eng.ops:
             h = op.__defaults__[0] if op.__defaults__ else None

@@ -94,14 +94,21 @@ typedef struct y5obb_conv y5obb_conv_t;
 #define Y5OBB_CONV_MODE_CONV 0    /* bf16 NHWC output (+ optional residual / 2x up-sampled copy) */
 #define Y5OBB_CONV_MODE_DETECT 1  /* Detect head: fp32 [B, rows, no] output, optional sigmoid+decode */
 
+#define Y5OBB_CONV_NO_ROWSHIFT 1   /* flags: force one TMA load per tap (debug / A-B comparison) */
+#define Y5OBB_CONV_NO_RESIDENT 2   /* flags: always stream the weight tiles */
+
 typedef struct {
   const void* in;            /* bf16 NHWC slice */
-  int64_t in_pix_stride;
-  int B, Hin, Win, Cin;
+  int64_t in_pix_stride;     /* elements between horizontally adjacent input pixels */
+  int64_t in_row_stride;     /* elements between image rows (0 = Win * in_pix_stride) */
+  int64_t in_img_stride;     /* elements between images     (0 = Hin * in_row_stride) */
+  int B, Hin, Win, Cin;      /* Cin may exceed in_pix_stride: overlapping windows (the stem's merged-kw view) */
+  int hbm_cin;               /* channels really read per pixel, for the byte accounting (0 = Cin) */
   const void* w;             /* packed weights */
   const float* bias;
-  int Cout, KH, KW, stride, pad;
+  int Cout, KH, KW, stride, pad_h, pad_w;
   int mode, act;             /* act: 0 = identity, 1 = SiLU */
+  int flags;
   void* out;                 /* bf16 NHWC slice (MODE_CONV) */
   int64_t out_pix_stride;
   const void* res;           /* optional residual slice added after the activation (Bottleneck.add) */
@@ -127,13 +134,13 @@ void y5obb_conv_destroy(y5obb_conv_t* conv);
 
 /* ---- HBM-bound helpers around the conv stack -------------------------------------------------
  * y5obb_stem_s2d: NCHW fp32 image [B,3,H,W] -> 2x2 space-to-depth NHWC bf16 [B,H/2,W/2,16] (channel
- * (dy*2+dx)*3 + c, 4 zero channels), so that the stem Conv(3, c, 6, 2, 2) of models/yolov5*.yaml (layer 0,
+ * (dy*2+dx)*3 + c, 4 zero channels; rows hold pad_cols untouched (zero) pixels on each side), so that the stem Conv(3, c, 6, 2, 2) of models/yolov5*.yaml (layer 0,
  * models/common.py:37-49) becomes a 3x3/s1/p1 conv for the tensor-core kernel.
  * y5obb_sppf_pool: SPPF's three chained MaxPool2d(5,1,2) (models/common.py:181-196) in one pass over
  * channels [0,C) of an NHWC bf16 buffer, results at channel offsets C, 2C, 3C (replaces torch.cat). */
-int y5obb_stem_s2d(const float* x_nchw, void* out_nhwc16, int B, int H, int W, void* stream);
+int y5obb_stem_s2d(const float* x_nchw, void* out_nhwc16, int B, int H, int W, int pad_cols, void* stream);
 /* same for a uint8 image, with the caller-side `/ 255` (train.py:299, val.py:187-188) folded in */
-int y5obb_stem_s2d_u8(const uint8_t* x_nchw, void* out_nhwc16, int B, int H, int W, void* stream);
+int y5obb_stem_s2d_u8(const uint8_t* x_nchw, void* out_nhwc16, int B, int H, int W, int pad_cols, void* stream);
 int y5obb_sppf_pool(void* buf, int64_t pix_stride, int B, int H, int W, int C, void* stream);
 
 #ifdef __cplusplus

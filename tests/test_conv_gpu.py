@@ -73,6 +73,22 @@ def test_conv_matches_torch_fp32(B, H, W, Cin, Cout, k, s, act):
     assert info["flops"] == 2.0 * B * Ho * Wo * Cout * Cin * k * k
 
 
+@pytest.mark.parametrize("flags", [1, 2, 3])  # NO_ROWSHIFT, NO_RESIDENT, both: the classic one-load-per-tap path
+@pytest.mark.parametrize("Cin,Cout", [(32, 32), (128, 128), (80, 320)])
+def test_conv_3x3_streamed_and_classic_paths(flags, Cin, Cout):
+    from yolov5_obb_b200.conv import Conv, Slice, pack_weights
+    B, H, W = 2, 24, 40
+    g = torch.Generator(device="cpu").manual_seed(Cin + flags)
+    x = _mk(B, H, W, Cin, 4)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5).to(DEV)
+    b = (torch.randn(Cout, generator=g) * 0.1).to(DEV)
+    out = torch.full((B, H, W, Cout), float("nan"), dtype=torch.bfloat16, device=DEV)
+    wp, bp = pack_weights(w, b)
+    Conv(Slice.full(x), wp, bp, Cout, 3, 1, 1, True, out=Slice.full(out), flags=flags).run()
+    torch.cuda.synchronize()
+    _check(out, _ref_conv(x, w, b, 1, 1, True), f"3x3 {Cin}->{Cout} flags={flags}")
+
+
 def test_conv_slices_residual_and_upsample():
     """Concat-offset store, strided input slice, Bottleneck residual (in place) and the 2x up-sampled copy."""
     from yolov5_obb_b200.conv import Conv, Slice, pack_weights

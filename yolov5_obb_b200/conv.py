@@ -18,11 +18,11 @@ MODE_CONV, MODE_DETECT = 0, 1
 class ConvDesc(ctypes.Structure):
     """Mirror of y5obb_conv_desc in include/y5obb.h."""
     _fields_ = [
-        ("in_", c_void_p), ("in_pix_stride", c_int64),
-        ("B", c_int), ("Hin", c_int), ("Win", c_int), ("Cin", c_int),
+        ("in_", c_void_p), ("in_pix_stride", c_int64), ("in_row_stride", c_int64), ("in_img_stride", c_int64),
+        ("B", c_int), ("Hin", c_int), ("Win", c_int), ("Cin", c_int), ("hbm_cin", c_int),
         ("w", c_void_p), ("bias", c_void_p),
-        ("Cout", c_int), ("KH", c_int), ("KW", c_int), ("stride", c_int), ("pad", c_int),
-        ("mode", c_int), ("act", c_int),
+        ("Cout", c_int), ("KH", c_int), ("KW", c_int), ("stride", c_int), ("pad_h", c_int), ("pad_w", c_int),
+        ("mode", c_int), ("act", c_int), ("flags", c_int),
         ("out", c_void_p), ("out_pix_stride", c_int64),
         ("res", c_void_p), ("res_pix_stride", c_int64),
         ("out2x", c_void_p), ("out2x_pix_stride", c_int64),
@@ -101,19 +101,42 @@ def pack_weights(w: torch.Tensor, bias: Optional[torch.Tensor], mode: int = MODE
     return wp.to(torch.bfloat16).contiguous(), bp.contiguous()
 
 
+@dataclass
+class WindowView:
+    """An input described by explicit strides: `C` channels per position may exceed `pix_stride` (overlapping
+    horizontal windows — how the stem's three kw taps become one contiguous K range)."""
+    buf: torch.Tensor
+    ptr: int
+    pix_stride: int
+    row_stride: int
+    img_stride: int
+    B: int
+    H: int
+    W: int
+    C: int
+    hbm_c: int = 0
+
+
+NO_ROWSHIFT, NO_RESIDENT = 1, 2
+
+
 class Conv:
     """One convolution bound to fixed buffers (TMA descriptors are baked at creation)."""
 
-    def __init__(self, x: Slice, w_packed: torch.Tensor, bias_pad: torch.Tensor, cout: int, k: int, stride: int,
-                 pad: int, act: bool, out: Optional[Slice] = None, res: Optional[Slice] = None,
-                 out2x: Optional[Slice] = None, det: Optional[dict] = None):
+    def __init__(self, x, w_packed: torch.Tensor, bias_pad: torch.Tensor, cout: int, k, stride: int,
+                 pad, act: bool, out: Optional[Slice] = None, res: Optional[Slice] = None,
+                 out2x: Optional[Slice] = None, det: Optional[dict] = None, flags: int = 0):
         _lib.require_cuda(x.buf, "conv input")
+        kh, kw = (k, k) if isinstance(k, int) else k
+        ph, pw = (pad, pad) if isinstance(pad, int) else pad
         d = ConvDesc()
         d.in_, d.in_pix_stride = x.ptr, x.pix_stride
+        if isinstance(x, WindowView):
+            d.in_row_stride, d.in_img_stride, d.hbm_cin = x.row_stride, x.img_stride, x.hbm_c
         d.B, d.Hin, d.Win, d.Cin = x.B, x.H, x.W, x.C
         d.w, d.bias = w_packed.data_ptr(), bias_pad.data_ptr()
-        d.Cout, d.KH, d.KW, d.stride, d.pad = cout, k, k, stride, pad
-        d.mode, d.act = (MODE_DETECT if det else MODE_CONV), int(bool(act))
+        d.Cout, d.KH, d.KW, d.stride, d.pad_h, d.pad_w = cout, kh, kw, stride, ph, pw
+        d.mode, d.act, d.flags = (MODE_DETECT if det else MODE_CONV), int(bool(act)), flags
         if out is not None:
             d.out, d.out_pix_stride = out.ptr, out.pix_stride
         if res is not None:

@@ -17,7 +17,8 @@
 namespace y5obb {
 namespace {
 
-__global__ void k_stem_s2d(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int H, int W) {
+__global__ void k_stem_s2d(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int H, int W,
+                           int pad_cols) {
   const int Ho = H >> 1, Wo = W >> 1;
   const long long total = (long long)B * Ho * Wo;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -41,7 +42,8 @@ __global__ void k_stem_s2d(const float* __restrict__ x, __nv_bfloat16* __restric
     __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(o);
 #pragma unroll
     for (int e = 0; e < 8; ++e) h[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-    uint4* dst = reinterpret_cast<uint4*>(out + i * 16);
+    // destination rows carry pad_cols zero pixels on each side (written once at allocation, never here)
+    uint4* dst = reinterpret_cast<uint4*>(out + ((r * (Wo + 2 * pad_cols)) + wo + pad_cols) * 16);
     dst[0] = o[0];
     dst[1] = o[1];
   }
@@ -49,7 +51,8 @@ __global__ void k_stem_s2d(const float* __restrict__ x, __nv_bfloat16* __restric
 
 // uint8 NCHW image: the caller-side `imgs.float() / 255` (train.py:299, val.py:187-188, detect.py:108-109)
 // folded into the same pass
-__global__ void k_stem_s2d_u8(const uint8_t* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int H, int W) {
+__global__ void k_stem_s2d_u8(const uint8_t* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int H, int W,
+                              int pad_cols) {
   const int Ho = H >> 1, Wo = W >> 1;
   const long long total = (long long)B * Ho * Wo;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -73,7 +76,8 @@ __global__ void k_stem_s2d_u8(const uint8_t* __restrict__ x, __nv_bfloat16* __re
     __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(o);
 #pragma unroll
     for (int e = 0; e < 8; ++e) h[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-    uint4* dst = reinterpret_cast<uint4*>(out + i * 16);
+    // destination rows carry pad_cols zero pixels on each side (written once at allocation, never here)
+    uint4* dst = reinterpret_cast<uint4*>(out + ((r * (Wo + 2 * pad_cols)) + wo + pad_cols) * 16);
     dst[0] = o[0];
     dst[1] = o[1];
   }
@@ -130,22 +134,22 @@ using namespace y5obb;
 
 extern "C" {
 
-int y5obb_stem_s2d(const float* x_nchw, void* out_nhwc16, int B, int H, int W, void* stream) {
-  if (!x_nchw || !out_nhwc16 || B <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1)) return Y5OBB_EINVAL;
+int y5obb_stem_s2d(const float* x_nchw, void* out_nhwc16, int B, int H, int W, int pad_cols, void* stream) {
+  if (!x_nchw || !out_nhwc16 || B <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1) || pad_cols < 0) return Y5OBB_EINVAL;
   if ((reinterpret_cast<uintptr_t>(x_nchw) & 7) || (reinterpret_cast<uintptr_t>(out_nhwc16) & 15)) return Y5OBB_EINVAL;
   const long long total = (long long)B * (H / 2) * (W / 2);
   const int grid = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 16);
-  k_stem_s2d<<<grid, 256, 0, (cudaStream_t)stream>>>(x_nchw, static_cast<__nv_bfloat16*>(out_nhwc16), B, H, W);
+  k_stem_s2d<<<grid, 256, 0, (cudaStream_t)stream>>>(x_nchw, static_cast<__nv_bfloat16*>(out_nhwc16), B, H, W, pad_cols);
   Y5_LAUNCH_CHECK();
   return Y5OBB_OK;
 }
 
-int y5obb_stem_s2d_u8(const uint8_t* x_nchw, void* out_nhwc16, int B, int H, int W, void* stream) {
-  if (!x_nchw || !out_nhwc16 || B <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1)) return Y5OBB_EINVAL;
+int y5obb_stem_s2d_u8(const uint8_t* x_nchw, void* out_nhwc16, int B, int H, int W, int pad_cols, void* stream) {
+  if (!x_nchw || !out_nhwc16 || B <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1) || pad_cols < 0) return Y5OBB_EINVAL;
   if ((reinterpret_cast<uintptr_t>(x_nchw) & 1) || (reinterpret_cast<uintptr_t>(out_nhwc16) & 15)) return Y5OBB_EINVAL;
   const long long total = (long long)B * (H / 2) * (W / 2);
   const int grid = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 16);
-  k_stem_s2d_u8<<<grid, 256, 0, (cudaStream_t)stream>>>(x_nchw, static_cast<__nv_bfloat16*>(out_nhwc16), B, H, W);
+  k_stem_s2d_u8<<<grid, 256, 0, (cudaStream_t)stream>>>(x_nchw, static_cast<__nv_bfloat16*>(out_nhwc16), B, H, W, pad_cols);
   Y5_LAUNCH_CHECK();
   return Y5OBB_OK;
 }

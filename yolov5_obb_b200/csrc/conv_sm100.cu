@@ -51,9 +51,12 @@ struct ConvK {
   int n_tiles_m, n_tiles_n;
   int BN, BK;
   int Cout, cout_pad;
-  int kchunks, KH, KW, stride, pad;
+  int Cin, kchunks, KH, KW, stride, pad_h, pad_w;
   int stages;
-  uint32_t a_bytes, b_bytes, b_stage_bytes;
+  int rowshift;    // 1: one A stage holds Ht + KH - 1 image rows; the KH taps of a column read it at row offsets
+  int b_resident;  // 1: every weight tile stays in shared memory for the whole kernel (loaded once)
+  int b_per_stage; // weight tiles streamed with each A stage (0 when resident)
+  uint32_t a_bytes, a_tx_bytes, b_bytes, b_stage_bytes, b_res_bytes, row_shift_bytes;
   uint32_t idesc;
   // epilogue
   int mode, act;
@@ -113,16 +116,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
   __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
   __shared__ __align__(8) uint64_t tmem_full[2];
   __shared__ __align__(8) uint64_t tmem_empty[2];
+  __shared__ __align__(8) uint64_t wres_bar;
   __shared__ uint32_t tmem_base_smem;
 
-  // 1024-byte aligned operand ring (the swizzle pattern repeats every 8 rows = up to 1024 bytes)
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const uint32_t stage_bytes = p.a_bytes + p.b_stage_bytes;
+  // 1024-byte aligned: [resident weights][operand ring][epilogue staging] (swizzle patterns repeat every 8 rows)
+  uint8_t* smem_res = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_res + p.b_res_bytes;
+  const uint32_t stage_bytes = p.a_bytes + (uint32_t)p.b_per_stage * p.b_stage_bytes;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.n_tiles_m * p.n_tiles_n;
-  const int k_iters = p.KH * p.KW * p.kchunks;
+  const int outer_iters = (p.rowshift ? p.KW : p.KH * p.KW) * p.kchunks;  // A stages per tile
+  const int ksub = p.rowshift ? p.KH : 1;                                  // taps served by one A stage
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&p.tmA);
@@ -136,6 +142,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       ptx::mbar_init(&tmem_full[a], 1);
       ptx::mbar_init(&tmem_empty[a], EPI_WARPS * 32);
     }
+    ptx::mbar_init(&wres_bar, 1);
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -150,22 +157,34 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      if (p.b_resident) {  // all weight tiles, once: tile (tap, kc) at smem_res + (tap * kchunks + kc) * b_stage_bytes
+        const int ntile = p.KH * p.KW * p.kchunks;
+        ptx::mbar_expect_tx(&wres_bar, (uint32_t)ntile * p.b_bytes);
+        for (int tap = 0; tap < p.KH * p.KW; ++tap)
+          for (int kc = 0; kc < p.kchunks; ++kc)
+            ptx::tma_load_2d(smem_res + (size_t)(tap * p.kchunks + kc) * p.b_stage_bytes, &p.tmB, &wres_bar, kc * p.BK,
+                             tap * p.cout_pad);
+      }
       int s = 0;
       uint32_t ph = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const TileCoord c = decode_tile(p, t);
-        for (int kh = 0; kh < p.KH; ++kh)
+        const int kh_n = p.rowshift ? 1 : p.KH;
+        for (int kh = 0; kh < kh_n; ++kh)
           for (int kw = 0; kw < p.KW; ++kw) {
-            const int tap = kh * p.KW + kw;
-            const int wi = c.w0 * p.stride + kw - p.pad;
-            const int hi = c.h0 * p.stride + kh - p.pad;
+            const int wi = c.w0 * p.stride + kw - p.pad_w;
+            const int hi = c.h0 * p.stride + kh - p.pad_h;
             for (int kc = 0; kc < p.kchunks; ++kc) {
               ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
               uint8_t* sa = smem + (size_t)s * stage_bytes;
               uint8_t* sb = sa + p.a_bytes;
-              ptx::mbar_expect_tx(&full_bar[s], p.a_bytes + p.b_bytes);
+              ptx::mbar_expect_tx(&full_bar[s], p.a_tx_bytes + (uint32_t)p.b_per_stage * p.b_bytes);
               ptx::tma_load_4d(sa, &p.tmA, &full_bar[s], kc * p.BK, wi, hi, c.b);
-              ptx::tma_load_2d(sb, &p.tmB, &full_bar[s], kc * p.BK, tap * p.cout_pad + c.n0);
+              for (int j = 0; j < p.b_per_stage; ++j) {
+                const int tap = (p.rowshift ? j : kh) * p.KW + kw;
+                ptx::tma_load_2d(sb + (size_t)j * p.b_stage_bytes, &p.tmB, &full_bar[s], kc * p.BK,
+                                 tap * p.cout_pad + c.n0);
+              }
               if (++s == p.stages) {
                 s = 0;
                 ph ^= 1u;
@@ -181,23 +200,38 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       uint32_t ph = 0;
       int it = 0;
       const uint32_t row_bytes = (uint32_t)p.BK * 2u;
+      if (p.b_resident) {
+        ptx::mbar_wait(&wres_bar, 0u);
+        ptx::tc_fence_after();
+      }
+      const uint32_t sres = ptx::smem_u32(smem_res);
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
         const int acc = it & 1;
         const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
         ptx::mbar_wait(&tmem_empty[acc], acc_ph ^ 1u);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
-        for (int k = 0; k < k_iters; ++k) {
+        uint32_t accumulate = 0u;
+        for (int k = 0; k < outer_iters; ++k) {
+          const int kc = k % p.kchunks;
+          const int tap_outer = k / p.kchunks;  // rowshift: kw ; classic: kh * KW + kw
+          // K sub-blocks of 16 that hold real channels (the zero-filled tail of a ragged chunk is skipped)
+          const int nk = (min(p.BK, p.Cin - kc * p.BK) + 15) >> 4;
           ptx::mbar_wait(&full_bar[s], ph);
           ptx::tc_fence_after();
           const uint32_t sa = ptx::smem_u32(smem + (size_t)s * stage_bytes);
           const uint32_t sb = sa + p.a_bytes;
-          const uint64_t da = ptx::make_kmajor_desc(sa, row_bytes);
-          const uint64_t db = ptx::make_kmajor_desc(sb, row_bytes);
-          const int nk = p.BK >> 4;
-          for (int j = 0; j < nk; ++j) {
-            // advance 16 K-elements = 32 bytes inside the swizzle span: +2 in the (addr >> 4) field
-            ptx::umma_bf16(d_tmem, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), p.idesc, (k | j) ? 1u : 0u);
+          for (int u = 0; u < ksub; ++u) {
+            const int tap = p.rowshift ? u * p.KW + tap_outer : tap_outer;
+            const uint64_t da = ptx::make_kmajor_desc(sa + (uint32_t)u * p.row_shift_bytes, row_bytes);
+            const uint32_t baddr = p.b_resident ? sres + (uint32_t)(tap * p.kchunks + kc) * p.b_stage_bytes
+                                                : sb + (uint32_t)(p.rowshift ? u : 0) * p.b_stage_bytes;
+            const uint64_t db = ptx::make_kmajor_desc(baddr, row_bytes);
+            for (int j = 0; j < nk; ++j) {
+              // advance 16 K-elements = 32 bytes inside the swizzle span: +2 in the (addr >> 4) field
+              ptx::umma_bf16(d_tmem, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), p.idesc, accumulate);
+              accumulate = 1u;
+            }
           }
           ptx::umma_commit(&empty_bar[s]);
           if (++s == p.stages) {
@@ -433,6 +467,10 @@ int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
   if (!d->in || !d->w || !d->bias) return Y5OBB_EINVAL;
   if (d->stride != 1 && d->stride != 2) return Y5OBB_EINVAL;
   if (d->in_pix_stride % 8 || (reinterpret_cast<uintptr_t>(d->in) & 15)) return Y5OBB_EINVAL;
+  if (d->KH < 1 || d->KW < 1 || d->pad_h < 0 || d->pad_w < 0) return Y5OBB_EINVAL;
+  const int64_t in_row_stride = d->in_row_stride ? d->in_row_stride : d->in_pix_stride * d->Win;
+  const int64_t in_img_stride = d->in_img_stride ? d->in_img_stride : in_row_stride * d->Hin;
+  if (in_row_stride % 8 || in_img_stride % 8) return Y5OBB_EINVAL;
   PFN_tmapEncodeTiled enc = get_encode();
   if (!enc) return Y5OBB_ECUDA;
 
@@ -443,8 +481,8 @@ int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
   ConvObj* o = new ConvObj();
   ConvK& k = o->k;
   memset(&k, 0, sizeof(k));
-  const int Hout = (d->Hin + 2 * d->pad - d->KH) / d->stride + 1;
-  const int Wout = (d->Win + 2 * d->pad - d->KW) / d->stride + 1;
+  const int Hout = (d->Hin + 2 * d->pad_h - d->KH) / d->stride + 1;
+  const int Wout = (d->Win + 2 * d->pad_w - d->KW) / d->stride + 1;
   k.B = d->B;
   k.Hout = Hout;
   k.Wout = Wout;
@@ -460,6 +498,11 @@ int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
       best_wt = wt;
     }
   }
+  // Row-shift mode (stride-1 convs with KH > 1): an 8 x 16 pixel tile whose A stage holds Ht + KH - 1 image
+  // rows; the KH vertical taps read the same stage at row offsets that are whole 8-row swizzle groups, so each
+  // input row crosses L2 -> shared memory (Ht + KH - 1) / Ht times per kw instead of KH times.
+  const bool rowshift = d->stride == 1 && d->KH > 1 && Wout >= 8 && !(d->flags & Y5OBB_CONV_NO_ROWSHIFT);
+  if (rowshift) best_wt = 8;
   k.Wt = best_wt;
   k.Ht = BM / best_wt;
   k.tiles_w = (Wout + k.Wt - 1) / k.Wt;
@@ -470,15 +513,30 @@ int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
   k.BK = bk;
   k.Cout = d->Cout;
   k.cout_pad = cout_pad;
+  k.Cin = d->Cin;
   k.kchunks = (d->Cin + bk - 1) / bk;
   k.KH = d->KH;
   k.KW = d->KW;
   k.stride = d->stride;
-  k.pad = d->pad;
-  k.a_bytes = (uint32_t)BM * bk * 2;
+  k.pad_h = d->pad_h;
+  k.pad_w = d->pad_w;
+  k.rowshift = rowshift ? 1 : 0;
+  const int a_rows = rowshift ? k.Ht + d->KH - 1 : k.Ht;  // image rows per A stage
+  k.a_bytes = (uint32_t)a_rows * k.Wt * bk * 2;
+  k.row_shift_bytes = (uint32_t)k.Wt * bk * 2;
   k.b_bytes = (uint32_t)bn * bk * 2;
   k.b_stage_bytes = (uint32_t)align_up(k.b_bytes, 1024);
-  k.stages = (int)std::min<size_t>(MAX_STAGES, SMEM_BUDGET / (k.a_bytes + k.b_stage_bytes));
+  const size_t a_stage = align_up(k.a_bytes, 1024);
+  const size_t b_all = (size_t)d->KH * d->KW * k.kchunks * k.b_stage_bytes;
+  // weights stay resident when every tile uses the same ones (one N tile) and they leave room for >= 3 A stages
+  k.b_resident = (nt == 1 && b_all <= (size_t)SMEM_BUDGET - 3 * a_stage && !(d->flags & Y5OBB_CONV_NO_RESIDENT)) ? 1 : 0;
+  k.b_res_bytes = k.b_resident ? (uint32_t)b_all : 0u;
+  k.b_per_stage = k.b_resident ? 0 : (rowshift ? d->KH : 1);
+  k.a_bytes = (uint32_t)a_stage;  // ring slots are 1024-aligned; the TMA box fills the first a_rows*Wt rows
+  const uint32_t a_tx = (uint32_t)a_rows * k.Wt * bk * 2;
+  k.a_tx_bytes = a_tx;
+  const size_t stage_bytes = a_stage + (size_t)k.b_per_stage * k.b_stage_bytes;
+  k.stages = (int)std::min<size_t>(MAX_STAGES, ((size_t)SMEM_BUDGET - k.b_res_bytes) / stage_bytes);
   if (k.stages < 2) {
     delete o;
     return Y5OBB_EINVAL;
@@ -512,9 +570,9 @@ int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
 
   {  // activations: (C, W, H, B), element strides (1, s, s, 1)
     cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->Win, (cuuint64_t)d->Hin, (cuuint64_t)d->B};
-    cuuint64_t strides[3] = {(cuuint64_t)d->in_pix_stride * 2, (cuuint64_t)d->in_pix_stride * 2 * d->Win,
-                             (cuuint64_t)d->in_pix_stride * 2 * d->Win * d->Hin};
-    cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)(k.Wt * d->stride), (cuuint32_t)(k.Ht * d->stride), 1};
+    cuuint64_t strides[3] = {(cuuint64_t)d->in_pix_stride * 2, (cuuint64_t)in_row_stride * 2,
+                             (cuuint64_t)in_img_stride * 2};
+    cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)(k.Wt * d->stride), (cuuint32_t)(a_rows * d->stride), 1};
     cuuint32_t es[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
     CUresult r = enc(&k.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->in), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(bk), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -558,10 +616,10 @@ int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
   const int total = k.n_tiles_m * k.n_tiles_n;
   o->grid = std::min(total, sm_count());
   // >= 116 KB so that two CTAs (each owning all 512 TMEM columns) can never share an SM
-  o->smem = std::max<size_t>((size_t)k.stages * (k.a_bytes + k.b_stage_bytes) + EPI_WARPS * 2 * EPI_STAGE_BYTES + 1024,
+  o->smem = std::max<size_t>(k.b_res_bytes + (size_t)k.stages * stage_bytes + EPI_WARPS * 2 * EPI_STAGE_BYTES + 1024,
                              116 * 1024);
   o->flops = 2.0 * d->B * Hout * Wout * (double)d->Cout * d->Cin * d->KH * d->KW;
-  o->hbm_bytes = 2.0 * d->B * ((double)d->Hin * d->Win * d->Cin + (double)Hout * Wout * d->Cout * (d->res ? 2 : 1));
+  o->hbm_bytes = 2.0 * d->B * ((double)d->Hin * d->Win * (d->hbm_cin ? d->hbm_cin : d->Cin) + (double)Hout * Wout * d->Cout * (d->res ? 2 : 1));
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + EPI_WARPS * 2 * EPI_STAGE_BYTES + 2048);

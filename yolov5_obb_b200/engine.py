@@ -20,7 +20,7 @@ from typing import List, Optional
 import torch
 
 from . import _lib
-from .conv import Conv as ConvOp, Slice, pack_weights, MODE_DETECT
+from .conv import Conv as ConvOp, Slice, WindowView, pack_weights, MODE_DETECT
 from . import yolo as Y
 
 
@@ -39,7 +39,7 @@ def _conv_params(m: "Y.Conv"):
 
 
 class InferenceEngine:
-    def __init__(self, model: "Y.Model", B: int, H: int, W: int, device):
+    def __init__(self, model: "Y.Model", B: int, H: int, W: int, device, conv_flags: int = 0):
         device = torch.device(device)
         if device.type != "cuda":
             raise RuntimeError("InferenceEngine needs a CUDA device (sm_100a); there is no CPU path")
@@ -123,9 +123,10 @@ class InferenceEngine:
             else:
                 out[i] = Slice.full(new(hw[i][0], hw[i][1], ch[i]))
 
-        def add_conv(x: Slice, w, b, k, s, p, act, dst: Optional[Slice] = None, res=None, out2x=None, detd=None):
+        def add_conv(x, w, b, k, s, p, act, dst: Optional[Slice] = None, res=None, out2x=None, detd=None):
             wp, bp = pack_weights(w, b, MODE_DETECT if detd else 0, detd["no"] if detd else 0)
-            op = ConvOp(x, wp, bp, w.shape[0], k, s, p, act, out=dst, res=res, out2x=out2x, det=detd)
+            op = ConvOp(x, wp, bp, w.shape[0], k, s, p, act, out=dst, res=res, out2x=out2x, det=detd,
+                        flags=conv_flags)
             self.convs.append(op)
             info = op.info()
             self.flops += info["flops"]
@@ -134,7 +135,10 @@ class InferenceEngine:
             self.ops.append(lambda st, h=h: L.y5obb_conv_run(h, st))
 
         # ---- pass 3: emit ops
-        self.x_s2d = new(H // 2, W // 2, 16)
+        # space-to-depth image with one zero pixel of padding left and right of every row: the stem's three
+        # horizontal taps are then 48 CONTIGUOUS channels of an overlapping-window view (pixel stride 16)
+        self.x_s2d = torch.zeros((B, H // 2, W // 2 + 2, 16), dtype=torch.bfloat16, device=device)
+        self.keep.append(self.x_s2d)
         for m in layers:
             i = m.i
             if isinstance(m, Y.Detect):
@@ -147,12 +151,17 @@ class InferenceEngine:
                 if i == 0:
                     if (k, s, p, w.shape[1]) != (6, 2, 2, 3):
                         raise RuntimeError("layer 0 must be the v6.0 stem Conv(3, c, 6, 2, 2)")
-                    # w2[co, (dy*2+dx)*3 + c, ty, tx] = w[co, c, 2*ty+dy, 2*tx+dx]
+                    # w2[co, (dy*2+dx)*3 + c, ty, tx] = w[co, c, 2*ty+dy, 2*tx+dx]   (3x3/s1/p1 over the s2d image)
                     w2 = torch.zeros((w.shape[0], 16, 3, 3), device=w.device)
                     for dy in range(2):
                         for dx in range(2):
                             w2[:, (dy * 2 + dx) * 3:(dy * 2 + dx) * 3 + 3] = w[:, :, dy::2, dx::2]
-                    add_conv(Slice.full(self.x_s2d), w2, b, 3, 1, 1, act, out[i])
+                    # w3[co, tx*16 + ch, ty, 0] = w2[co, ch, ty, tx]   (3x1 over 48-channel windows)
+                    w3 = w2.permute(0, 3, 1, 2).reshape(w.shape[0], 48, 3, 1).contiguous()
+                    Wp = W // 2 + 2
+                    win = WindowView(buf=self.x_s2d, ptr=self.x_s2d.data_ptr(), pix_stride=16, row_stride=Wp * 16,
+                                     img_stride=(H // 2) * Wp * 16, B=B, H=H // 2, W=W // 2, C=48, hbm_c=16)
+                    add_conv(win, w3, b, (3, 1), 1, (1, 0), act, out[i])
                 else:
                     add_conv(out[fs[0]], w, b, k, s, p, act, out[i], out2x=up_of.get(i))
             elif isinstance(m, Y.C3):
@@ -213,11 +222,11 @@ class InferenceEngine:
         with torch.cuda.device(self.device):
             if x.dtype == torch.uint8:  # raw image: the caller-side `/ 255` is folded into the layout pass
                 x = x.contiguous()
-                _lib.check(L.y5obb_stem_s2d_u8(x.data_ptr(), self.x_s2d.data_ptr(), self.B, self.H, self.W, st),
+                _lib.check(L.y5obb_stem_s2d_u8(x.data_ptr(), self.x_s2d.data_ptr(), self.B, self.H, self.W, 1, st),
                            "y5obb_stem_s2d_u8")
             else:
                 x = x.contiguous().float()
-                _lib.check(L.y5obb_stem_s2d(x.data_ptr(), self.x_s2d.data_ptr(), self.B, self.H, self.W, st),
+                _lib.check(L.y5obb_stem_s2d(x.data_ptr(), self.x_s2d.data_ptr(), self.B, self.H, self.W, 1, st),
                            "y5obb_stem_s2d")
             for op in self.ops:
                 rc = op(st)
