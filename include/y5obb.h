@@ -143,6 +143,35 @@ int y5obb_stem_s2d(const float* x_nchw, void* out_nhwc16, int B, int H, int W, i
 int y5obb_stem_s2d_u8(const uint8_t* x_nchw, void* out_nhwc16, int B, int H, int W, int pad_cols, void* stream);
 int y5obb_sppf_pool(void* buf, int64_t pix_stride, int B, int H, int W, int C, void* stream);
 
+/* ---- loss ------------------------------------------------------------------------------------
+ * Replaces utils/loss.py:122-192 (ComputeLoss.__call__), :194-275 (build_targets) and utils/metrics.py:201-236
+ * (bbox_iou, CIoU).  p[i]: Detect training outputs [B, na, H_i, W_i, no] fp32 (models/yolo.py:65);
+ * targets [nt, tcols] fp32 rows (img, cls, cx, cy, l, s, theta, csl[180]) in pixels (utils/datasets.py:643-659).
+ * loss1[0] = (lbox + lobj + lcls + ltheta) * B, items4 = (lbox, lobj, lcls, ltheta) after the hyp gains
+ * (loss.py:185-192).  backward writes dLoss/dp[i] * grad_loss[0] into grad[i] (dense, same shape as p[i]); it
+ * must be given the workspace its forward filled.  Duplicate (b,a,gj,gi) cells: the highest source row wins
+ * tobj, as sequential CPU index assignment does (loss.py:159). */
+typedef struct {
+  const float* p[3];
+  float* grad[3];            /* backward only */
+  int H[3], W[3];
+  float stride[3];
+  float anchors[18];         /* Detect.anchors: [nl][na][2] in grid units */
+  float balance[3];          /* {4.0, 1.0, 0.4} (loss.py:114) */
+  int nl, B, na, no, nc;
+  const float* targets;
+  int nt, tcols;
+  float anchor_t, cp, cn;    /* hyp['anchor_t']; smooth_BCE targets (loss.py:107) */
+  float hyp_box, hyp_obj, hyp_cls, hyp_theta;  /* already rescaled as train.py:249-252 does */
+  float cls_pw, obj_pw, theta_pw;              /* BCEWithLogitsLoss pos_weight (loss.py:99-101) */
+} y5obb_loss_desc;
+
+size_t y5obb_loss_workspace_bytes(const y5obb_loss_desc* desc);
+int y5obb_loss_forward(const y5obb_loss_desc* desc, float* loss1, float* items4, void* workspace,
+                       size_t workspace_bytes, void* stream);
+int y5obb_loss_backward(const y5obb_loss_desc* desc, const float* grad_loss, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

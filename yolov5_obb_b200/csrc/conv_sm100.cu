@@ -486,28 +486,6 @@ int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
   k.B = d->B;
   k.Hout = Hout;
   k.Wout = Wout;
-  // tile: Wt x Ht = 128 pixels, Wt the power of two (<=128) that wastes the fewest edge pixels
-  int best_wt = 128;
-  double best_eff = -1;
-  for (int wt = 128; wt >= 8; wt >>= 1) {
-    int ht = BM / wt;
-    if (wt * d->stride > 256 || ht * d->stride > 256) continue;
-    double eff = (double)Wout * Hout / ((double)((Wout + wt - 1) / wt * wt) * ((Hout + ht - 1) / ht * ht));
-    if (eff > best_eff + 1e-9) {
-      best_eff = eff;
-      best_wt = wt;
-    }
-  }
-  // Row-shift mode (stride-1 convs with KH > 1): an 8 x 16 pixel tile whose A stage holds Ht + KH - 1 image
-  // rows; the KH vertical taps read the same stage at row offsets that are whole 8-row swizzle groups, so each
-  // input row crosses L2 -> shared memory (Ht + KH - 1) / Ht times per kw instead of KH times.
-  const bool rowshift = d->stride == 1 && d->KH > 1 && Wout >= 8 && !(d->flags & Y5OBB_CONV_NO_ROWSHIFT);
-  if (rowshift) best_wt = 8;
-  k.Wt = best_wt;
-  k.Ht = BM / best_wt;
-  k.tiles_w = (Wout + k.Wt - 1) / k.Wt;
-  k.tiles_h = (Hout + k.Ht - 1) / k.Ht;
-  k.n_tiles_m = d->B * k.tiles_w * k.tiles_h;
   k.n_tiles_n = nt;
   k.BN = bn;
   k.BK = bk;
@@ -520,24 +498,53 @@ int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
   k.stride = d->stride;
   k.pad_h = d->pad_h;
   k.pad_w = d->pad_w;
-  k.rowshift = rowshift ? 1 : 0;
-  const int a_rows = rowshift ? k.Ht + d->KH - 1 : k.Ht;  // image rows per A stage
-  k.a_bytes = (uint32_t)a_rows * k.Wt * bk * 2;
-  k.row_shift_bytes = (uint32_t)k.Wt * bk * 2;
   k.b_bytes = (uint32_t)bn * bk * 2;
   k.b_stage_bytes = (uint32_t)align_up(k.b_bytes, 1024);
-  const size_t a_stage = align_up(k.a_bytes, 1024);
-  const size_t b_all = (size_t)d->KH * d->KW * k.kchunks * k.b_stage_bytes;
-  // weights stay resident when every tile uses the same ones (one N tile) and they leave room for >= 3 A stages
-  k.b_resident = (nt == 1 && b_all <= (size_t)SMEM_BUDGET - 3 * a_stage && !(d->flags & Y5OBB_CONV_NO_RESIDENT)) ? 1 : 0;
-  k.b_res_bytes = k.b_resident ? (uint32_t)b_all : 0u;
-  k.b_per_stage = k.b_resident ? 0 : (rowshift ? d->KH : 1);
-  k.a_bytes = (uint32_t)a_stage;  // ring slots are 1024-aligned; the TMA box fills the first a_rows*Wt rows
-  const uint32_t a_tx = (uint32_t)a_rows * k.Wt * bk * 2;
-  k.a_tx_bytes = a_tx;
-  const size_t stage_bytes = a_stage + (size_t)k.b_per_stage * k.b_stage_bytes;
-  k.stages = (int)std::min<size_t>(MAX_STAGES, ((size_t)SMEM_BUDGET - k.b_res_bytes) / stage_bytes);
-  if (k.stages < 2) {
+  int a_rows = 0;
+  size_t stage_bytes = 0;
+  // Row-shift mode (stride-1 convs with KH > 1): an 8 x 16 pixel tile whose A stage holds Ht + KH - 1 image
+  // rows; the KH vertical taps read the same stage at row offsets that are whole 8-row swizzle groups, so each
+  // input row crosses L2 -> shared memory (Ht + KH - 1) / Ht times per kw instead of KH times.  Taken when the
+  // weights are resident or at least 3 pipeline stages still fit; otherwise one load per tap (classic).
+  auto plan = [&](bool rowshift) -> bool {
+    int best_wt = 128;
+    if (rowshift) {
+      best_wt = 8;
+    } else {  // Wt x Ht = 128 pixels, Wt the power of two (<=128) that wastes the fewest edge pixels
+      double best_eff = -1;
+      for (int wt = 128; wt >= 8; wt >>= 1) {
+        int ht = BM / wt;
+        if (wt * d->stride > 256 || ht * d->stride > 256) continue;
+        double eff = (double)Wout * Hout / ((double)((Wout + wt - 1) / wt * wt) * ((Hout + ht - 1) / ht * ht));
+        if (eff > best_eff + 1e-9) {
+          best_eff = eff;
+          best_wt = wt;
+        }
+      }
+    }
+    k.Wt = best_wt;
+    k.Ht = BM / best_wt;
+    k.tiles_w = (Wout + k.Wt - 1) / k.Wt;
+    k.tiles_h = (Hout + k.Ht - 1) / k.Ht;
+    k.n_tiles_m = d->B * k.tiles_w * k.tiles_h;
+    k.rowshift = rowshift ? 1 : 0;
+    a_rows = rowshift ? k.Ht + d->KH - 1 : k.Ht;  // image rows per A stage
+    k.a_tx_bytes = (uint32_t)a_rows * k.Wt * bk * 2;
+    k.row_shift_bytes = (uint32_t)k.Wt * bk * 2;
+    const size_t a_stage = align_up(k.a_tx_bytes, 1024);
+    k.a_bytes = (uint32_t)a_stage;  // ring slots are 1024-aligned; the TMA box fills the first a_rows * Wt rows
+    const size_t b_all = (size_t)d->KH * d->KW * k.kchunks * k.b_stage_bytes;
+    // weights stay resident when every tile uses the same ones (one N tile) and they leave room for >= 3 A stages
+    k.b_resident =
+        (nt == 1 && b_all + 3 * a_stage <= (size_t)SMEM_BUDGET && !(d->flags & Y5OBB_CONV_NO_RESIDENT)) ? 1 : 0;
+    k.b_res_bytes = k.b_resident ? (uint32_t)b_all : 0u;
+    k.b_per_stage = k.b_resident ? 0 : (rowshift ? d->KH : 1);
+    stage_bytes = a_stage + (size_t)k.b_per_stage * k.b_stage_bytes;
+    k.stages = (int)std::min<size_t>(MAX_STAGES, ((size_t)SMEM_BUDGET - k.b_res_bytes) / stage_bytes);
+    return k.stages >= (rowshift ? 3 : 2);
+  };
+  const bool want_rowshift = d->stride == 1 && d->KH > 1 && Wout >= 8 && !(d->flags & Y5OBB_CONV_NO_ROWSHIFT);
+  if (!(want_rowshift && plan(true)) && !plan(false)) {
     delete o;
     return Y5OBB_EINVAL;
   }
