@@ -36,8 +36,9 @@ constexpr int BM = 128;  // output pixels per tile == TMEM lanes
 constexpr int MAX_STAGES = 8;
 constexpr int NUM_THREADS = 320;          // TMA producer, MMA issuer, 8 epilogue warps
 constexpr int EPI_WARPS = 8;
-constexpr int EPI_STAGE_BYTES = 32 * 64;  // 32 pixels x 32 bf16 channels, 64-byte swizzled
-constexpr int SMEM_BUDGET = 190 * 1024;   // operand ring; + 32 KB epilogue staging + alignment slack < 227 KB
+constexpr int EPI_STAGE_CONV = 32 * 64;    // 32 pixels x 32 bf16 channels, 64-byte swizzled
+constexpr int EPI_STAGE_DET = 32 * 128;    // 32 pixels x 32 fp32 outputs, 128-byte swizzled
+constexpr int SMEM_TOTAL = 224 * 1024;    // dynamic shared memory we ask for at most (227 KB is the hardware cap)
 
 enum Mode : int { MODE_CONV = 0, MODE_DETECT = 1 };
 
@@ -56,7 +57,7 @@ struct ConvK {
   int rowshift;    // 1: one A stage holds Ht + KH - 1 image rows; the KH taps of a column read it at row offsets
   int b_resident;  // 1: every weight tile stays in shared memory for the whole kernel (loaded once)
   int b_per_stage; // weight tiles streamed with each A stage (0 when resident)
-  uint32_t a_bytes, a_tx_bytes, b_bytes, b_stage_bytes, b_res_bytes, row_shift_bytes;
+  uint32_t a_bytes, a_tx_bytes, b_bytes, b_stage_bytes, b_res_bytes, row_shift_bytes, epi_stage_bytes;
   uint32_t idesc;
   // epilogue
   int mode, act;
@@ -133,7 +134,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&p.tmA);
     ptx::prefetch_tmap(&p.tmB);
-    if (p.mode == MODE_CONV) ptx::prefetch_tmap(&p.tmO);
+    ptx::prefetch_tmap(&p.tmO);
     for (int s = 0; s < p.stages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     // this warp's 32 pixels as a TMA box: {32 ch, bw, 32 / bw, 1}
     const int bw = min(p.Wt, 32);
     const int box_h0 = (q * 32) / p.Wt, box_w0 = (q * 32) % p.Wt;
-    uint8_t* stage = smem + (size_t)p.stages * stage_bytes + (size_t)e * (2 * EPI_STAGE_BYTES);
+    uint8_t* stage = smem + (size_t)p.stages * stage_bytes + (size_t)e * (2 * p.epi_stage_bytes);
     int sbuf = 0;
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
@@ -283,7 +284,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
           // the staging buffer about to be overwritten must have been read by its TMA store
           if (lane == 0) ptx::tma_store_wait_read<1>();
           __syncwarp();
-          uint8_t* sb = stage + sbuf * EPI_STAGE_BYTES;
+          uint8_t* sb = stage + sbuf * p.epi_stage_bytes;
           const float4* b4 = reinterpret_cast<const float4*>(p.bias + c.n0 + c0);
 #pragma unroll
           for (int g = 0; g < 4; ++g) {  // 8 channels = one 16-byte chunk
@@ -337,42 +338,46 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         }
       } else {
         // Detect: N tile nt == anchor nt; columns [0, det_no) are that anchor's outputs.
-        // out row = b * rows_per_image + row_off + (a * H + h) * W + w   (models/yolo.py:65,81)
+        // out row = b * rows_per_image + row_off + (a * H + h) * W + w   (models/yolo.py:65,81): the tensor map
+        // views the output as (no, W, H, anchor, image), so the permute is the store's addressing.
         const int a = c.nt;
-        float* orow = p.det_out +
-                      ((long long)c.b * p.det_rows_per_image + p.det_row_off + ((long long)a * p.Hout + h) * p.Wout + w) *
-                          p.det_no;
         const float aw = p.det_anchor[2 * a], ah = p.det_anchor[2 * a + 1];
         for (int c0 = half * 32; c0 < p.det_no; c0 += 64) {
           uint32_t r[32];
           ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)c0, r);
           ptx::tmem_ld_wait();
-          if (valid) {
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + c.n0 + c0);
+          if (lane == 0) ptx::tma_store_wait_read<1>();
+          __syncwarp();
+          uint8_t* sb = stage + sbuf * p.epi_stage_bytes;
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + c.n0 + c0);
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {  // 4 floats = one 16-byte store
-              const int cg = c0 + g * 4;
-              if (cg < p.det_no) {
-                const float4 bv = __ldg(b4 + g);
-                float v[4];
-                v[0] = __uint_as_float(r[g * 4 + 0]) + bv.x;
-                v[1] = __uint_as_float(r[g * 4 + 1]) + bv.y;
-                v[2] = __uint_as_float(r[g * 4 + 2]) + bv.z;
-                v[3] = __uint_as_float(r[g * 4 + 3]) + bv.w;
-                if (p.det_decode) {
+          for (int g = 0; g < 8; ++g) {  // 4 floats = one 16-byte chunk
+            const float4 bv = __ldg(b4 + g);
+            float v[4];
+            v[0] = __uint_as_float(r[g * 4 + 0]) + bv.x;
+            v[1] = __uint_as_float(r[g * 4 + 1]) + bv.y;
+            v[2] = __uint_as_float(r[g * 4 + 2]) + bv.z;
+            v[3] = __uint_as_float(r[g * 4 + 3]) + bv.w;
+            if (p.det_decode) {
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) v[k] = sigmoid_fast(v[k]);
-                  if (cg == 0) {  // xy, wh (models/yolo.py:73-74)
-                    v[0] = (v[0] * 2.0f - 0.5f + (float)w) * p.det_stride;
-                    v[1] = (v[1] * 2.0f - 0.5f + (float)h) * p.det_stride;
-                    v[2] = (v[2] * 2.0f) * (v[2] * 2.0f) * aw;
-                    v[3] = (v[3] * 2.0f) * (v[3] * 2.0f) * ah;
-                  }
-                }
-                __stcs(reinterpret_cast<float4*>(orow + cg), make_float4(v[0], v[1], v[2], v[3]));
+              for (int k = 0; k < 4; ++k) v[k] = sigmoid_fast(v[k]);
+              if (c0 == 0 && g == 0) {  // xy, wh (models/yolo.py:73-74)
+                v[0] = (v[0] * 2.0f - 0.5f + (float)w) * p.det_stride;
+                v[1] = (v[1] * 2.0f - 0.5f + (float)h) * p.det_stride;
+                v[2] = (v[2] * 2.0f) * (v[2] * 2.0f) * aw;
+                v[3] = (v[3] * 2.0f) * (v[3] * 2.0f) * ah;
               }
             }
+            // 128-byte swizzle (Swizzle<3,4,3>): 16-byte chunk index ^= row & 7
+            *reinterpret_cast<float4*>(sb + lane * 128 + ((g ^ (lane & 7)) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
           }
+          ptx::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_5d(&p.tmO, sb, c0, c.w0 + box_w0, c.h0 + box_h0, a, c.b);
+            ptx::tma_store_commit();
+          }
+          sbuf ^= 1;
         }
       }
       ptx::tc_fence_before();
@@ -502,6 +507,8 @@ int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
   k.b_stage_bytes = (uint32_t)align_up(k.b_bytes, 1024);
   int a_rows = 0;
   size_t stage_bytes = 0;
+  k.epi_stage_bytes = d->mode == MODE_DETECT ? EPI_STAGE_DET : EPI_STAGE_CONV;
+  const size_t SMEM_BUDGET = (size_t)SMEM_TOTAL - 1024 - (size_t)EPI_WARPS * 2 * k.epi_stage_bytes;  // operand ring (+ resident weights)
   // Row-shift mode (stride-1 convs with KH > 1): an 8 x 16 pixel tile whose A stage holds Ht + KH - 1 image
   // rows; the KH vertical taps read the same stage at row offsets that are whole 8-row swizzle groups, so each
   // input row crosses L2 -> shared memory (Ht + KH - 1) / Ht times per kw instead of KH times.  Taken when the
@@ -536,11 +543,11 @@ int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
     const size_t b_all = (size_t)d->KH * d->KW * k.kchunks * k.b_stage_bytes;
     // weights stay resident when every tile uses the same ones (one N tile) and they leave room for >= 3 A stages
     k.b_resident =
-        (nt == 1 && b_all + 3 * a_stage <= (size_t)SMEM_BUDGET && !(d->flags & Y5OBB_CONV_NO_RESIDENT)) ? 1 : 0;
+        (nt == 1 && b_all + 3 * a_stage <= SMEM_BUDGET && !(d->flags & Y5OBB_CONV_NO_RESIDENT)) ? 1 : 0;
     k.b_res_bytes = k.b_resident ? (uint32_t)b_all : 0u;
     k.b_per_stage = k.b_resident ? 0 : (rowshift ? d->KH : 1);
     stage_bytes = a_stage + (size_t)k.b_per_stage * k.b_stage_bytes;
-    k.stages = (int)std::min<size_t>(MAX_STAGES, ((size_t)SMEM_BUDGET - k.b_res_bytes) / stage_bytes);
+    k.stages = (int)std::min<size_t>(MAX_STAGES, (SMEM_BUDGET - k.b_res_bytes) / stage_bytes);
     return k.stages >= (rowshift ? 3 : 2);
   };
   const bool want_rowshift = d->stride == 1 && d->KH > 1 && Wout >= 8 && !(d->flags & Y5OBB_CONV_NO_ROWSHIFT);
@@ -620,16 +627,37 @@ int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
       return Y5OBB_ECUDA;
     }
   }
+  if (d->mode == MODE_DETECT) {  // output rows as (no, W, H, anchor, image) fp32; each warp stores 32 pixels x 32 floats
+    const int bw = std::min(k.Wt, 32);
+    cuuint64_t dims[5] = {(cuuint64_t)d->det_no, (cuuint64_t)Wout, (cuuint64_t)Hout, (cuuint64_t)nt, (cuuint64_t)d->B};
+    const cuuint64_t rowb = (cuuint64_t)d->det_no * 4;
+    cuuint64_t strides[4] = {rowb, rowb * Wout, rowb * Wout * Hout, rowb * (cuuint64_t)d->det_rows_per_image};
+    cuuint32_t box[5] = {32, (cuuint32_t)bw, (cuuint32_t)(32 / bw), 1, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    float* base = d->det_out + (size_t)d->det_row_off * d->det_no;
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (rowb & 15)) {
+      delete o;
+      return Y5OBB_EINVAL;
+    }
+    CUresult r = enc(&k.tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, base, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      g_last_cuda_error = (int)r;
+      delete o;
+      return Y5OBB_ECUDA;
+    }
+  }
   const int total = k.n_tiles_m * k.n_tiles_n;
   o->grid = std::min(total, sm_count());
   // >= 116 KB so that two CTAs (each owning all 512 TMEM columns) can never share an SM
-  o->smem = std::max<size_t>(k.b_res_bytes + (size_t)k.stages * stage_bytes + EPI_WARPS * 2 * EPI_STAGE_BYTES + 1024,
+  o->smem = std::max<size_t>(k.b_res_bytes + (size_t)k.stages * stage_bytes + EPI_WARPS * 2 * k.epi_stage_bytes + 1024,
                              116 * 1024);
   o->flops = 2.0 * d->B * Hout * Wout * (double)d->Cout * d->Cin * d->KH * d->KW;
   o->hbm_bytes = 2.0 * d->B * ((double)d->Hin * d->Win * (d->hbm_cin ? d->hbm_cin : d->Cin) + (double)Hout * Wout * d->Cout * (d->res ? 2 : 1));
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + EPI_WARPS * 2 * EPI_STAGE_BYTES + 2048);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
     if (e != cudaSuccess) {
       delete o;
       return cuda_fail(e);

@@ -145,13 +145,15 @@ __device__ __forceinline__ void load_prebox(PreBox* dst, const PreBox* src) {
   d[1] = s[1];
 }
 
+constexpr int CAND_CAP = 8192;  // candidate pairs buffered per work unit before the IoU phase runs
+
 __global__ void __launch_bounds__(TILE_THREADS)
 k_tiles(const PreBox* __restrict__ pre, const NmsSeg* __restrict__ seg, int n_images, NmsCtrl* ctrl,
         unsigned long long* __restrict__ mask, uint8_t* __restrict__ rowflag, float thr, int strict) {
   __shared__ __align__(16) PreBox s_row[TB];
   __shared__ __align__(16) PreBox s_col[TB];
-  __shared__ unsigned long long s_mask[TB];
-  __shared__ unsigned short s_cand[TB * TB];
+  __shared__ unsigned long long s_mask[TB * CHUNK];  // [row][col block of the unit]
+  __shared__ unsigned short s_cand[CAND_CAP];        // row (6 bits) | col block in unit (3) | col (6)
   __shared__ int s_ncand;
   __shared__ long long s_unit;
 
@@ -187,19 +189,37 @@ k_tiles(const PreBox* __restrict__ pre, const NmsSeg* __restrict__ seg, int n_im
     const int nrow = min(TB, S.n - rb * TB);
 
     if (tid < nrow) load_prebox(&s_row[tid], &pre[S.off + rb * TB + tid]);
+    for (int i = tid; i < TB * CHUNK; i += TILE_THREADS) s_mask[i] = 0ull;
+    if (tid == 0) s_ncand = 0;
+
+    // phase 2 (all lanes busy): evaluate the buffered candidates with the bit-faithful IoU
+    auto drain = [&]() {
+      __syncthreads();
+      const int nc = s_ncand;
+      for (int c = tid; c < nc; c += TILE_THREADS) {
+        const int pr = s_cand[c];
+        const int r = pr >> 9, cbl = (pr >> 6) & 7, j = pr & 63;
+        PreBox cbx;
+        load_prebox(&cbx, &pre[S.off + (cb0 + cbl) * TB + j]);
+        const float v = rbox_iou(s_row[r], cbx);
+        const bool sup = strict ? (v > thr) : (v >= thr);
+        if (sup) atomicOr(&s_mask[r * CHUNK + cbl], 1ull << j);
+      }
+      __syncthreads();
+      if (tid == 0) s_ncand = 0;
+    };
 
     for (int cb = cb0; cb < cb1; ++cb) {
       const int ncol = min(TB, S.n - cb * TB);
+      __syncthreads();  // s_col free (previous phase 1 done), s_row / s_ncand visible
       if (tid >= TB && tid - TB < ncol) load_prebox(&s_col[tid - TB], &pre[S.off + cb * TB + (tid - TB)]);
-      if (tid < TB) s_mask[tid] = 0ull;
-      if (tid == 0) s_ncand = 0;
       __syncthreads();
-
       {  // phase 1: exact reject of pairs whose circumscribed circles do not touch
         const int r = tid & (TB - 1);
         const int half = tid >> 6;
         const bool rvalid = r < nrow;
         const float rx = s_row[r].cx, ry = s_row[r].cy, rr = s_row[r].rad;
+        const int tag = (r << 9) | ((cb - cb0) << 6);
 #pragma unroll 4
         for (int jj = 0; jj < TB / 2; ++jj) {
           const int j = half * (TB / 2) + jj;
@@ -214,31 +234,24 @@ k_tiles(const PreBox* __restrict__ pre, const NmsSeg* __restrict__ seg, int n_im
             int base = 0;
             if (lane == 0) base = atomicAdd(&s_ncand, __popc(bal));
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (c) s_cand[base + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)((r << 6) | j);
+            if (c) s_cand[base + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)(tag | j);
           }
         }
       }
       __syncthreads();
-
-      {  // phase 2: every lane takes candidates off the list
-        const int nc = s_ncand;
-        for (int c = tid; c < nc; c += TILE_THREADS) {
-          const int pr = s_cand[c];
-          const int r = pr >> 6, j = pr & 63;
-          const float v = rbox_iou(s_row[r], s_col[j]);
-          const bool sup = strict ? (v > thr) : (v >= thr);
-          if (sup) atomicOr(&s_mask[r], 1ull << j);
-        }
-      }
-      __syncthreads();
-
-      if (tid < nrow) {
-        const unsigned long long w = s_mask[tid];
-        mask[S.mask_off + (long long)(rb * TB + tid) * S.nblk + cb] = w;
-        if (w) rowflag[S.off + rb * TB + tid] = 1;
-      }
-      __syncthreads();
+      if (s_ncand > CAND_CAP - TB * TB) drain();  // the next tile could add up to 4096 pairs
     }
+    drain();
+
+    // phase 3: the unit's mask words, contiguous along the column blocks of a row
+    const int ncb = cb1 - cb0;
+    for (int i = tid; i < nrow * ncb; i += TILE_THREADS) {
+      const int r = i / ncb, cbl = i - r * ncb;
+      const unsigned long long w = s_mask[r * CHUNK + cbl];
+      mask[S.mask_off + (long long)(rb * TB + r) * S.nblk + cb0 + cbl] = w;
+      if (w) rowflag[S.off + rb * TB + r] = 1;
+    }
+    __syncthreads();
   }
 }
 
