@@ -172,6 +172,18 @@ int y5obb_loss_forward(const y5obb_loss_desc* desc, float* loss1, float* items4,
 int y5obb_loss_backward(const y5obb_loss_desc* desc, const float* grad_loss, void* workspace,
                         size_t workspace_bytes, void* stream);
 
+/* ---- post-NMS geometry and CSL targets (one thread per box, fp32, separately rounded ops) -------
+ * rbox2poly: utils/rboxs_utils.py:106-126 — [n,5] (cx,cy,l,s,theta) -> [n,8] corner coordinates.
+ * poly2hbb:  utils/rboxs_utils.py:147-165 — [n,8] -> [n,4] (xc, yc, w, h) of the axis-aligned hull.
+ * scale_polys: utils/general.py:636-650 — in place: x -= pad_x, y -= pad_y, all /= gain (un-letterbox).
+ * gaussian_label: utils/rboxs_utils.py:9-26 — Circular-Smooth-Label rows [n, num_class] from angles in degrees
+ *   (fp64, as numpy evaluates them); peak at bin num_class/2 - trunc(num_class/2 - angle). */
+int y5obb_rbox2poly_f32(const float* rboxes5, float* polys8, int64_t n, void* stream);
+int y5obb_poly2hbb_f32(const float* polys8, float* hbb4, int64_t n, void* stream);
+int y5obb_scale_polys_f32(float* polys8, int64_t n, float pad_x, float pad_y, float gain, void* stream);
+int y5obb_gaussian_label(const double* angle_deg, float* csl_out, int64_t n, int num_class, double sigma,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif
