@@ -34,8 +34,18 @@ def fold_bn(conv: torch.nn.Conv2d, bn: Optional[torch.nn.BatchNorm2d]):
     return w * scale.view(-1, 1, 1, 1), (b - bn.running_mean.detach().float()) * scale + bn.bias.detach().float()
 
 
-def _conv_params(m: "Y.Conv"):
+def _conv_params(m):
     return fold_bn(m.conv, getattr(m, "bn", None))
+
+
+def _kind(m) -> str:
+    """Module kind by class NAME, so that the reference's own modules (models/common.py, models/yolo.py,
+    torch.nn.Upsample) are accepted as well as the mirrors of yolo.py."""
+    return type(m).__name__
+
+
+def _is(m, name: str) -> bool:
+    return _kind(m) == name
 
 
 class InferenceEngine:
@@ -43,7 +53,7 @@ class InferenceEngine:
         device = torch.device(device)
         if device.type != "cuda":
             raise RuntimeError("InferenceEngine needs a CUDA device (sm_100a); there is no CPU path")
-        det: Y.Detect = model.model[-1]
+        det = model.model[-1]
         smax = int(max(model.stride))
         if H % smax or W % smax:
             raise RuntimeError(f"image size {H}x{W} must be a multiple of the max stride {smax}")
@@ -64,21 +74,21 @@ class InferenceEngine:
         ch, hw = [0] * n, [(0, 0)] * n
         for m in layers:
             i = m.i
-            if isinstance(m, Y.Detect):
+            if _is(m, "Detect"):
                 continue
             fs = [src_of(i, f) for f in ([m.f] if isinstance(m.f, int) else m.f)]
             in_hw = (H, W) if i == 0 else hw[fs[0]]
-            if isinstance(m, Y.Conv):
+            if _is(m, "Conv"):
                 s, k, p = m.conv.stride[0], m.conv.kernel_size[0], m.conv.padding[0]
                 ch[i] = m.conv.out_channels
                 hw[i] = ((in_hw[0] + 2 * p - k) // s + 1, (in_hw[1] + 2 * p - k) // s + 1)
-            elif isinstance(m, Y.C3):
+            elif _is(m, "C3"):
                 ch[i], hw[i] = m.cv3.conv.out_channels, in_hw
-            elif isinstance(m, Y.SPPF):
+            elif _is(m, "SPPF"):
                 ch[i], hw[i] = m.cv2.conv.out_channels, in_hw
-            elif isinstance(m, Y.Upsample):
+            elif _is(m, "Upsample"):
                 ch[i], hw[i] = ch[fs[0]], (in_hw[0] * 2, in_hw[1] * 2)
-            elif isinstance(m, Y.Concat):
+            elif _is(m, "Concat"):
                 ch[i], hw[i] = sum(ch[f] for f in fs), in_hw
                 assert all(hw[f] == in_hw for f in fs)
 
@@ -91,7 +101,7 @@ class InferenceEngine:
         feeds = {}
         cat_buf = {}
         for m in layers:
-            if isinstance(m, Y.Concat):
+            if _is(m, "Concat"):
                 cat_buf[m.i] = new(hw[m.i][0], hw[m.i][1], ch[m.i])
                 off = 0
                 for f in m.f:
@@ -104,16 +114,16 @@ class InferenceEngine:
         up_of = {}  # producer conv index -> Slice receiving the up-sampled copy
         for m in layers:
             i = m.i
-            if isinstance(m, Y.Detect):
+            if _is(m, "Detect"):
                 continue
-            if isinstance(m, Y.Concat):
+            if _is(m, "Concat"):
                 out[i] = Slice.full(cat_buf[i])
-            elif isinstance(m, Y.Upsample):
+            elif _is(m, "Upsample"):
                 if i not in feeds:
                     raise RuntimeError("nn.Upsample must feed a Concat (v6.0 head pattern)")
                 j, off = feeds[i]
                 src = src_of(i, m.f)
-                if not isinstance(layers[src], Y.Conv):
+                if not _is(layers[src], "Conv"):
                     raise RuntimeError("nn.Upsample must follow a Conv (v6.0 head pattern)")
                 up_of[src] = Slice(cat_buf[j], off, ch[i])
                 out[i] = up_of[src]
@@ -141,10 +151,10 @@ class InferenceEngine:
         self.keep.append(self.x_s2d)
         for m in layers:
             i = m.i
-            if isinstance(m, Y.Detect):
+            if _is(m, "Detect"):
                 break
             fs = [src_of(i, f) for f in ([m.f] if isinstance(m.f, int) else m.f)]
-            if isinstance(m, Y.Conv):
+            if _is(m, "Conv"):
                 w, b = _conv_params(m)
                 k, s, p = m.conv.kernel_size[0], m.conv.stride[0], m.conv.padding[0]
                 act = isinstance(m.act, torch.nn.SiLU)
@@ -164,7 +174,7 @@ class InferenceEngine:
                     add_conv(win, w3, b, (3, 1), 1, (1, 0), act, out[i])
                 else:
                     add_conv(out[fs[0]], w, b, k, s, p, act, out[i], out2x=up_of.get(i))
-            elif isinstance(m, Y.C3):
+            elif _is(m, "C3"):
                 x = out[fs[0]]
                 c_ = m.cv1.conv.out_channels
                 cat = Slice.full(new(hw[i][0], hw[i][1], 2 * c_))
@@ -180,7 +190,7 @@ class InferenceEngine:
                     add_conv(tmp, wb, bb, 3, 1, 1, True, chain, res=chain if bt.add else None)
                 w3, b3 = _conv_params(m.cv3)
                 add_conv(cat, w3, b3, 1, 1, 0, True, out[i])
-            elif isinstance(m, Y.SPPF):
+            elif _is(m, "SPPF"):
                 x = out[fs[0]]
                 c_ = m.cv1.conv.out_channels
                 cat4 = new(hw[i][0], hw[i][1], 4 * c_)
