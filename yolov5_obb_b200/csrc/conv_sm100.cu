@@ -33,7 +33,7 @@ namespace y5obb {
 namespace {
 
 constexpr int BM = 128;  // output pixels per tile == TMEM lanes
-constexpr int MAX_STAGES = 8;
+constexpr int MAX_STAGES = 16;
 constexpr int NUM_THREADS = 320;          // TMA producer, MMA issuer, 8 epilogue warps
 constexpr int EPI_WARPS = 8;
 constexpr int EPI_STAGE_CONV = 32 * 64;    // 32 pixels x 32 bf16 channels, 64-byte swizzled
@@ -54,6 +54,8 @@ struct ConvK {
   int Cout, cout_pad;
   int Cin, kchunks, KH, KW, stride, pad_h, pad_w;
   int stages;
+  int epi_tile_split;  // 1: epilogue warp group g handles the tiles whose accumulator is g (all columns); 0: both
+                       // groups work on every tile and split its columns (few tiles per CTA)
   int rowshift;    // 1: one A stage holds Ht + KH - 1 image rows; the KH taps of a column read it at row offsets
   int b_resident;  // 1: every weight tile stays in shared memory for the whole kernel (loaded once)
   int b_per_stage; // weight tiles streamed with each A stage (0 when resident)
@@ -141,7 +143,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full[a], 1);
-      ptx::mbar_init(&tmem_empty[a], EPI_WARPS * 32);
+      ptx::mbar_init(&tmem_empty[a], p.epi_tile_split ? 128 : EPI_WARPS * 32);
     }
     ptx::mbar_init(&wres_bar, 1);
     ptx::fence_mbar_init();
@@ -259,9 +261,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     uint8_t* stage = smem + (size_t)p.stages * stage_bytes + (size_t)e * (2 * p.epi_stage_bytes);
     int sbuf = 0;
     int it = 0;
+    const int col_first = p.epi_tile_split ? 0 : half * 32;  // first 32-column chunk of this warp
+    const int col_step = p.epi_tile_split ? 32 : 64;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-      const TileCoord c = decode_tile(p, t);
       const int acc = it & 1;
+      if (p.epi_tile_split && acc != half) continue;  // the other warp group owns this tile
+      const TileCoord c = decode_tile(p, t);
       const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
       const int h = c.h0 + hl, w = c.w0 + wl;
       const bool valid = (h < p.Hout) && (w < p.Wout);
@@ -277,9 +282,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         if (p.out2x) urow = p.out2x + (((long long)c.b * 2 * p.Hout + 2 * h) * (2 * p.Wout) + 2 * w) * p.out2x_pix_stride + c.n0;
         const long long up_row_step = (long long)(2 * p.Wout) * p.out2x_pix_stride;
         const int nvalid = min(p.BN, p.Cout - c.n0);
-        for (int c0 = half * 32; c0 < nvalid; c0 += 64) {
+        for (int c0 = col_first; c0 < nvalid; c0 += col_step) {
           uint32_t r[32];
           ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)c0, r);
+          // residual: all four 16-byte loads of this chunk are in flight before anything waits on them
+          uint4 rv[4];
+          const bool has_res = rrow && valid;
+          if (has_res) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              rv[g] = (c0 + g * 8 < nvalid) ? *reinterpret_cast<const uint4*>(rrow + c0 + g * 8) : make_uint4(0, 0, 0, 0);
+          }
           ptx::tmem_ld_wait();
           // the staging buffer about to be overwritten must have been read by its TMA store
           if (lane == 0) ptx::tma_store_wait_read<1>();
@@ -303,9 +316,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
 #pragma unroll
               for (int k = 0; k < 8; ++k) v[k] = silu(v[k]);
             }
-            if (rrow && valid && cg < nvalid) {
-              const uint4 rv = *reinterpret_cast<const uint4*>(rrow + cg);
-              const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rv);
+            if (has_res) {
+              const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rv[g]);
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const float2 f = __bfloat1622float2(rh[k]);
@@ -342,7 +354,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         // views the output as (no, W, H, anchor, image), so the permute is the store's addressing.
         const int a = c.nt;
         const float aw = p.det_anchor[2 * a], ah = p.det_anchor[2 * a + 1];
-        for (int c0 = half * 32; c0 < p.det_no; c0 += 64) {
+        for (int c0 = col_first; c0 < p.det_no; c0 += col_step) {
           uint32_t r[32];
           ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)c0, r);
           ptx::tmem_ld_wait();
@@ -650,6 +662,9 @@ int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
   }
   const int total = k.n_tiles_m * k.n_tiles_n;
   o->grid = std::min(total, sm_count());
+  // many tiles per CTA: the two epilogue groups alternate tiles (two epilogues in flight, any BN);
+  // few tiles per CTA: they split the columns of each tile (shortest single-tile latency)
+  k.epi_tile_split = (total >= 4 * o->grid) ? 1 : 0;
   // >= 116 KB so that two CTAs (each owning all 512 TMEM columns) can never share an SM
   o->smem = std::max<size_t>(k.b_res_bytes + (size_t)k.stages * stage_bytes + EPI_WARPS * 2 * k.epi_stage_bytes + 1024,
                              116 * 1024);
