@@ -89,6 +89,21 @@ def test_conv_3x3_streamed_and_classic_paths(flags, Cin, Cout):
     _check(out, _ref_conv(x, w, b, 1, 1, True), f"3x3 {Cin}->{Cout} flags={flags}")
 
 
+@pytest.mark.parametrize("flags", [0, 4])  # pixel-pair view vs TMA element strides along W
+def test_conv_stride2_slice_paths(flags):
+    from yolov5_obb_b200.conv import Conv, Slice, pack_weights
+    B, H, W = 2, 32, 48
+    buf = _mk(B, H, W, 160, 8)            # input = channels [32, 112): ragged against BK = 64
+    g = torch.Generator(device="cpu").manual_seed(21)
+    w = (torch.randn(96, 80, 3, 3, generator=g) / (80 * 9) ** 0.5).to(DEV)
+    b = (torch.randn(96, generator=g) * 0.1).to(DEV)
+    out = torch.full((B, H // 2, W // 2, 96), float("nan"), dtype=torch.bfloat16, device=DEV)
+    wp, bp = pack_weights(w, b)
+    Conv(Slice(buf, 32, 80), wp, bp, 96, 3, 2, 1, True, out=Slice.full(out), flags=flags).run()
+    torch.cuda.synchronize()
+    _check(out, _ref_conv(buf[..., 32:112], w, b, 2, 1, True), f"3x3 s2 slice flags={flags}")
+
+
 def test_conv_slices_residual_and_upsample():
     """Concat-offset store, strided input slice, Bottleneck residual (in place) and the 2x up-sampled copy."""
     from yolov5_obb_b200.conv import Conv, Slice, pack_weights

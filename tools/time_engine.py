@@ -11,7 +11,8 @@ from yolov5_obb_b200.engine import InferenceEngine
 
 size, B, S = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
 m = build_mirror(size, nc=15, seed=0).cuda()
-eng = InferenceEngine(m, B, S, S, torch.device("cuda:0"))
+import os
+eng = InferenceEngine(m, B, S, S, torch.device("cuda:0"), conv_flags=int(os.environ.get("Y5OBB_CONV_FLAGS", "0")))
 x = torch.rand(B, 3, S, S, device="cuda")
 for _ in range(3):
     eng.forward(x)

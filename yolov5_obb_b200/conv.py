@@ -117,7 +117,7 @@ class WindowView:
     hbm_c: int = 0
 
 
-NO_ROWSHIFT, NO_RESIDENT = 1, 2
+NO_ROWSHIFT, NO_RESIDENT, NO_PAIRW, BIAS_HALVED = 1, 2, 4, 8
 
 
 class Conv:
@@ -134,6 +134,10 @@ class Conv:
         if isinstance(x, WindowView):
             d.in_row_stride, d.in_img_stride, d.hbm_cin = x.row_stride, x.img_stride, x.hbm_c
         d.B, d.Hin, d.Win, d.Cin = x.B, x.H, x.W, x.C
+        if act and not det:
+            # the SiLU epilogue evaluates h + h*tanh(h) with h = 0.5*acc + 0.5*bias: hand it 0.5*bias
+            bias_pad = (bias_pad * 0.5).contiguous()
+            flags |= BIAS_HALVED
         d.w, d.bias = w_packed.data_ptr(), bias_pad.data_ptr()
         d.Cout, d.KH, d.KW, d.stride, d.pad_h, d.pad_w = cout, kh, kw, stride, ph, pw
         d.mode, d.act, d.flags = (MODE_DETECT if det else MODE_CONV), int(bool(act)), flags

@@ -54,6 +54,9 @@ struct ConvK {
   int Cout, cout_pad;
   int Cin, kchunks, KH, KW, stride, pad_h, pad_w;
   int stages;
+  int pairw;           // 1: stride-2 conv whose input is viewed as horizontal pixel PAIRS (2*pix_stride channels per
+                       // position): the column phase of a tap is a channel offset, so TMA reads contiguous rows
+  int in_pix_stride;
   int epi_tile_split;  // 1: epilogue warp group g handles the tiles whose accumulator is g (all columns); 0: both
                        // groups work on every tile and split its columns (few tiles per CTA)
   int rowshift;    // 1: one A stage holds Ht + KH - 1 image rows; the KH taps of a column read it at row offsets
@@ -102,15 +105,101 @@ __device__ __forceinline__ float tanh_fast(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float silu(float v) {
-  const float h = 0.5f * v;
-  return fmaf(h, tanh_fast(h), h);
-}
 __device__ __forceinline__ float sigmoid_fast(float v) { return fmaf(0.5f, tanh_fast(0.5f * v), 0.5f); }
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+
+
+// ---- epilogue of one MODE_CONV tile for one warp -----------------------------------------------------
+struct EpiTile {
+  uint32_t taddr;     // TMEM address of this warp's lane quarter, column 0 of the accumulator
+  uint8_t* stage;     // two swizzled staging buffers of this warp
+  uint32_t stage_bytes;
+  uint32_t swz;       // (lane >> 1) & 3
+  int lane;
+  const float* bias;  // + n0; holds 0.5 * bias when the layer has SiLU (Y5OBB_CONV_BIAS_HALVED)
+  const __nv_bfloat16* rrow;  // residual row of this thread's pixel (+ n0) or null
+  __nv_bfloat16* urow;        // up-sampled destination of this thread's pixel (+ n0) or null
+  long long up_pix, up_row;
+  int nvalid, col_first, col_step;
+  const CUtensorMap* tm;
+  int cn0, cw, chh, cb;
+};
+
+template <bool ACT, bool RES, bool UP>
+__device__ __forceinline__ void conv_epi_tile(const EpiTile& e, int& sbuf) {
+  for (int c0 = e.col_first; c0 < e.nvalid; c0 += e.col_step) {
+    uint32_t r[32];
+    ptx::tmem_ld_32x32b_x32(e.taddr + (uint32_t)c0, r);
+    uint4 rv[4];
+    if (RES) {  // all four 16-byte residual loads are in flight before anything waits on them
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        rv[g] = (e.rrow && c0 + g * 8 < e.nvalid) ? *reinterpret_cast<const uint4*>(e.rrow + c0 + g * 8)
+                                                   : make_uint4(0, 0, 0, 0);
+    }
+    const float4* b4 = reinterpret_cast<const float4*>(e.bias + c0);
+    float4 bv[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) bv[g] = __ldg(b4 + g);
+    ptx::tmem_ld_wait();
+    // the staging buffer about to be overwritten must have been read by its TMA store
+    if (e.lane == 0) ptx::tma_store_wait_read<1>();
+    __syncwarp();
+    uint8_t* sb = e.stage + sbuf * e.stage_bytes + e.lane * 64;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {  // 8 channels = one 16-byte chunk
+      float v[8];
+      const float bb[8] = {bv[2 * g].x, bv[2 * g].y, bv[2 * g].z, bv[2 * g].w,
+                           bv[2 * g + 1].x, bv[2 * g + 1].y, bv[2 * g + 1].z, bv[2 * g + 1].w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float acc = __uint_as_float(r[g * 8 + k]);
+        if (ACT) {  // SiLU(x) = h + h * tanh(h), h = x / 2 = 0.5 * acc + (0.5 * bias)
+          const float hh = fmaf(acc, 0.5f, bb[k]);
+          v[k] = fmaf(hh, tanh_fast(hh), hh);
+        } else {
+          v[k] = acc + bb[k];
+        }
+      }
+      if (RES) {
+        const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rv[g]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __bfloat1622float2(rh[k]);
+          v[2 * k] += f.x;
+          v[2 * k + 1] += f.y;
+        }
+      }
+      uint4 o;
+      o.x = pack_bf16(v[0], v[1]);
+      o.y = pack_bf16(v[2], v[3]);
+      o.z = pack_bf16(v[4], v[5]);
+      o.w = pack_bf16(v[6], v[7]);
+      // 64-byte swizzle (Swizzle<2,4,3>): 16-byte chunk index ^= (row >> 1) & 3
+      *reinterpret_cast<uint4*>(sb + (((uint32_t)g ^ e.swz) << 4)) = o;
+      if (UP) {
+        const int cg = c0 + g * 8;
+        if (e.urow && cg < e.nvalid) {
+          *reinterpret_cast<uint4*>(e.urow + cg) = o;
+          *reinterpret_cast<uint4*>(e.urow + e.up_pix + cg) = o;
+          *reinterpret_cast<uint4*>(e.urow + e.up_row + cg) = o;
+          *reinterpret_cast<uint4*>(e.urow + e.up_row + e.up_pix + cg) = o;
+        }
+      }
+    }
+    ptx::fence_proxy_async();
+    __syncwarp();
+    if (e.lane == 0) {
+      // rows beyond the image and channels beyond Cout are clipped by the tensor map
+      ptx::tma_store_4d(e.tm, e.stage + sbuf * e.stage_bytes, e.cn0 + c0, e.cw, e.chh, e.cb);
+      ptx::tma_store_commit();
+    }
+    sbuf ^= 1;
+  }
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvK p) {
@@ -175,14 +264,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         const int kh_n = p.rowshift ? 1 : p.KH;
         for (int kh = 0; kh < kh_n; ++kh)
           for (int kw = 0; kw < p.KW; ++kw) {
-            const int wi = c.w0 * p.stride + kw - p.pad_w;
+            int wi = c.w0 * p.stride + kw - p.pad_w;
             const int hi = c.h0 * p.stride + kh - p.pad_h;
+            int cbase = 0;
+            if (p.pairw) {  // input column 2*wo + (kw - pad): pair index wo + floor(off / 2), phase off & 1
+              const int off = kw - p.pad_w;
+              const int phase = off & 1;
+              wi = c.w0 + ((off - phase) >> 1);
+              cbase = phase * p.in_pix_stride;
+            }
             for (int kc = 0; kc < p.kchunks; ++kc) {
               ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
               uint8_t* sa = smem + (size_t)s * stage_bytes;
               uint8_t* sb = sa + p.a_bytes;
               ptx::mbar_expect_tx(&full_bar[s], p.a_tx_bytes + (uint32_t)p.b_per_stage * p.b_bytes);
-              ptx::tma_load_4d(sa, &p.tmA, &full_bar[s], kc * p.BK, wi, hi, c.b);
+              ptx::tma_load_4d(sa, &p.tmA, &full_bar[s], cbase + kc * p.BK, wi, hi, c.b);
               for (int j = 0; j < p.b_per_stage; ++j) {
                 const int tap = (p.rowshift ? j : kh) * p.KW + kw;
                 ptx::tma_load_2d(sb + (size_t)j * p.b_stage_bytes, &p.tmB, &full_bar[s], kc * p.BK,
@@ -280,73 +376,37 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         const __nv_bfloat16* rrow = p.res ? p.res + pix * p.res_pix_stride + c.n0 : nullptr;
         __nv_bfloat16* urow = nullptr;
         if (p.out2x) urow = p.out2x + (((long long)c.b * 2 * p.Hout + 2 * h) * (2 * p.Wout) + 2 * w) * p.out2x_pix_stride + c.n0;
-        const long long up_row_step = (long long)(2 * p.Wout) * p.out2x_pix_stride;
         const int nvalid = min(p.BN, p.Cout - c.n0);
-        for (int c0 = col_first; c0 < nvalid; c0 += col_step) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)c0, r);
-          // residual: all four 16-byte loads of this chunk are in flight before anything waits on them
-          uint4 rv[4];
-          const bool has_res = rrow && valid;
-          if (has_res) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-              rv[g] = (c0 + g * 8 < nvalid) ? *reinterpret_cast<const uint4*>(rrow + c0 + g * 8) : make_uint4(0, 0, 0, 0);
-          }
-          ptx::tmem_ld_wait();
-          // the staging buffer about to be overwritten must have been read by its TMA store
-          if (lane == 0) ptx::tma_store_wait_read<1>();
-          __syncwarp();
-          uint8_t* sb = stage + sbuf * p.epi_stage_bytes;
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + c.n0 + c0);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {  // 8 channels = one 16-byte chunk
-            const int cg = c0 + g * 8;
-            float v[8];
-            const float4 ba = __ldg(b4 + 2 * g), bb = __ldg(b4 + 2 * g + 1);
-            v[0] = __uint_as_float(r[g * 8 + 0]) + ba.x;
-            v[1] = __uint_as_float(r[g * 8 + 1]) + ba.y;
-            v[2] = __uint_as_float(r[g * 8 + 2]) + ba.z;
-            v[3] = __uint_as_float(r[g * 8 + 3]) + ba.w;
-            v[4] = __uint_as_float(r[g * 8 + 4]) + bb.x;
-            v[5] = __uint_as_float(r[g * 8 + 5]) + bb.y;
-            v[6] = __uint_as_float(r[g * 8 + 6]) + bb.z;
-            v[7] = __uint_as_float(r[g * 8 + 7]) + bb.w;
-            if (p.act) {
-#pragma unroll
-              for (int k = 0; k < 8; ++k) v[k] = silu(v[k]);
-            }
-            if (has_res) {
-              const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rv[g]);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const float2 f = __bfloat1622float2(rh[k]);
-                v[2 * k] += f.x;
-                v[2 * k + 1] += f.y;
-              }
-            }
-            uint4 o;
-            o.x = pack_bf16(v[0], v[1]);
-            o.y = pack_bf16(v[2], v[3]);
-            o.z = pack_bf16(v[4], v[5]);
-            o.w = pack_bf16(v[6], v[7]);
-            // 64-byte swizzle (Swizzle<2,4,3>): 16-byte chunk index ^= (row >> 1) & 3
-            *reinterpret_cast<uint4*>(sb + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) = o;
-            if (urow && valid && cg < nvalid) {
-              *reinterpret_cast<uint4*>(urow + cg) = o;
-              *reinterpret_cast<uint4*>(urow + p.out2x_pix_stride + cg) = o;
-              *reinterpret_cast<uint4*>(urow + up_row_step + cg) = o;
-              *reinterpret_cast<uint4*>(urow + up_row_step + p.out2x_pix_stride + cg) = o;
-            }
-          }
-          ptx::fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            // rows beyond the image and channels beyond Cout are clipped by the tensor map
-            ptx::tma_store_4d(&p.tmO, sb, c.n0 + c0, c.w0 + box_w0, c.h0 + box_h0, c.b);
-            ptx::tma_store_commit();
-          }
-          sbuf ^= 1;
+        EpiTile et;
+        et.taddr = taddr;
+        et.stage = stage;
+        et.stage_bytes = p.epi_stage_bytes;
+        et.swz = (uint32_t)((lane >> 1) & 3);
+        et.lane = lane;
+        et.bias = p.bias + c.n0;
+        et.rrow = valid ? rrow : nullptr;
+        et.urow = valid ? urow : nullptr;
+        et.up_pix = p.out2x_pix_stride;
+        et.up_row = (long long)(2 * p.Wout) * p.out2x_pix_stride;
+        et.nvalid = nvalid;
+        et.col_first = col_first;
+        et.col_step = col_step;
+        et.tm = &p.tmO;
+        et.cn0 = c.n0;
+        et.cw = c.w0 + box_w0;
+        et.chh = c.h0 + box_h0;
+        et.cb = c.b;
+        // one specialised instantiation per layer flavour: nothing of the unused paths is issued
+        const int flavour = (p.act ? 1 : 0) | (p.res ? 2 : 0) | (p.out2x ? 4 : 0);
+        switch (flavour) {
+          case 0: conv_epi_tile<false, false, false>(et, sbuf); break;
+          case 1: conv_epi_tile<true, false, false>(et, sbuf); break;
+          case 2: conv_epi_tile<false, true, false>(et, sbuf); break;
+          case 3: conv_epi_tile<true, true, false>(et, sbuf); break;
+          case 5: conv_epi_tile<true, false, true>(et, sbuf); break;
+          case 4:
+          case 6: conv_epi_tile<false, true, true>(et, sbuf); break;  // generic paths tolerate null rrow / urow
+          default: conv_epi_tile<true, true, true>(et, sbuf); break;
         }
       } else {
         // Detect: N tile nt == anchor nt; columns [0, det_no) are that anchor's outputs.
@@ -485,6 +545,7 @@ int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
   if (d->stride != 1 && d->stride != 2) return Y5OBB_EINVAL;
   if (d->in_pix_stride % 8 || (reinterpret_cast<uintptr_t>(d->in) & 15)) return Y5OBB_EINVAL;
   if (d->KH < 1 || d->KW < 1 || d->pad_h < 0 || d->pad_w < 0) return Y5OBB_EINVAL;
+  if (d->mode == MODE_CONV && d->act && !(d->flags & Y5OBB_CONV_BIAS_HALVED)) return Y5OBB_EINVAL;
   const int64_t in_row_stride = d->in_row_stride ? d->in_row_stride : d->in_pix_stride * d->Win;
   const int64_t in_img_stride = d->in_img_stride ? d->in_img_stride : in_row_stride * d->Hin;
   if (in_row_stride % 8 || in_img_stride % 8) return Y5OBB_EINVAL;
@@ -594,12 +655,24 @@ int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
     return Y5OBB_EINVAL;
   }
 
+  // stride-2 convs over dense rows: view the input as horizontal pixel pairs so that no element stride is needed
+  // along W (channels beyond the slice are finite activations of the same buffer and meet zero weights)
+  k.pairw = (d->stride == 2 && !(d->Win & 1) && in_row_stride == d->in_pix_stride * d->Win &&
+             !(d->flags & Y5OBB_CONV_NO_PAIRW)) ? 1 : 0;
+  k.in_pix_stride = (int)d->in_pix_stride;
   {  // activations: (C, W, H, B), element strides (1, s, s, 1)
     cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->Win, (cuuint64_t)d->Hin, (cuuint64_t)d->B};
     cuuint64_t strides[3] = {(cuuint64_t)d->in_pix_stride * 2, (cuuint64_t)in_row_stride * 2,
                              (cuuint64_t)in_img_stride * 2};
     cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)(k.Wt * d->stride), (cuuint32_t)(a_rows * d->stride), 1};
     cuuint32_t es[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
+    if (k.pairw) {
+      dims[0] = (cuuint64_t)d->in_pix_stride + d->Cin;
+      dims[1] = (cuuint64_t)d->Win / 2;
+      strides[0] = (cuuint64_t)d->in_pix_stride * 4;
+      box[1] = (cuuint32_t)k.Wt;
+      es[1] = 1;
+    }
     CUresult r = enc(&k.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->in), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(bk), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -93,7 +93,9 @@ class InferenceEngine:
                 assert all(hw[f] == in_hw for f in fs)
 
         def new(h, w, c):
-            t = torch.empty((B, h, w, c), dtype=torch.bfloat16, device=device)
+            # zeros, once: the pixel-pair view of stride-2 convs may read channels of a buffer before their
+            # producer ran (they meet zero weights, but must be finite)
+            t = torch.zeros((B, h, w, c), dtype=torch.bfloat16, device=device)
             self.keep.append(t)
             return t
 
@@ -133,7 +135,12 @@ class InferenceEngine:
             else:
                 out[i] = Slice.full(new(hw[i][0], hw[i][1], ch[i]))
 
+        import os
+        dbg_no_res = os.environ.get("Y5OBB_DEBUG_NO_RES") == "1"  # timing experiments only (wrong results)
+
         def add_conv(x, w, b, k, s, p, act, dst: Optional[Slice] = None, res=None, out2x=None, detd=None):
+            if dbg_no_res:
+                res = None
             wp, bp = pack_weights(w, b, MODE_DETECT if detd else 0, detd["no"] if detd else 0)
             op = ConvOp(x, wp, bp, w.shape[0], k, s, p, act, out=dst, res=res, out2x=out2x, det=detd,
                         flags=conv_flags)
