@@ -42,6 +42,21 @@ constexpr int SMEM_TOTAL = 224 * 1024;    // dynamic shared memory we ask for at
 
 enum Mode : int { MODE_CONV = 0, MODE_DETECT = 1 };
 
+// division by a launch-time constant without the ~100-cycle integer divide (x < 2^31): q = (umulhi(x, m) + x) >> s
+struct FastDiv {
+  uint32_t d, m, s;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d;
+  uint32_t s = 0;
+  while ((1u << s) < d) ++s;
+  f.s = s;
+  f.m = (uint32_t)((((uint64_t)1 << 32) * (((uint64_t)1 << s) - d)) / d + 1);
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t x, const FastDiv& f) { return (__umulhi(x, f.m) + x) >> f.s; }
+
 struct ConvK {
   CUtensorMap tmA;
   CUtensorMap tmB;
@@ -50,6 +65,7 @@ struct ConvK {
   int B, Hout, Wout;
   int Wt, Ht, tiles_w, tiles_h;
   int n_tiles_m, n_tiles_n;
+  FastDiv fd_ntn, fd_per_img, fd_tiles_w, fd_wt;
   int BN, BK;
   int Cout, cout_pad;
   int Cin, kchunks, KH, KW, stride, pad_h, pad_w;
@@ -87,12 +103,12 @@ struct TileCoord {
 
 __device__ __forceinline__ TileCoord decode_tile(const ConvK& p, int t) {
   TileCoord c;
-  c.nt = t % p.n_tiles_n;
-  int mt = t / p.n_tiles_n;
-  int per_img = p.tiles_h * p.tiles_w;
-  c.b = mt / per_img;
-  int r = mt - c.b * per_img;
-  int th = r / p.tiles_w;
+  const int mt = (int)fdiv((uint32_t)t, p.fd_ntn);
+  c.nt = t - mt * p.n_tiles_n;
+  const int per_img = p.tiles_h * p.tiles_w;
+  c.b = (int)fdiv((uint32_t)mt, p.fd_per_img);
+  const int r = mt - c.b * per_img;
+  const int th = (int)fdiv((uint32_t)r, p.fd_tiles_w);
   c.h0 = th * p.Ht;
   c.w0 = (r - th * p.tiles_w) * p.Wt;
   c.n0 = c.nt * p.BN;
@@ -219,7 +235,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.n_tiles_m * p.n_tiles_n;
-  const int outer_iters = (p.rowshift ? p.KW : p.KH * p.KW) * p.kchunks;  // A stages per tile
   const int ksub = p.rowshift ? p.KH : 1;                                  // taps served by one A stage
 
   if (warp == 0 && lane == 0) {
@@ -304,6 +319,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         ptx::tc_fence_after();
       }
       const uint32_t sres = ptx::smem_u32(smem_res);
+      const uint32_t ring_u32 = ptx::smem_u32(smem);
+      const uint64_t desc_hi = ptx::make_kmajor_desc(0u, row_bytes);
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
         const int acc = it & 1;
         const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
@@ -311,33 +328,33 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
         uint32_t accumulate = 0u;
-        for (int k = 0; k < outer_iters; ++k) {
-          const int kc = k % p.kchunks;
-          const int tap_outer = k / p.kchunks;  // rowshift: kw ; classic: kh * KW + kw
-          // K sub-blocks of 16 that hold real channels (the zero-filled tail of a ragged chunk is skipped)
-          const int nk = (min(p.BK, p.Cin - kc * p.BK) + 15) >> 4;
-          ptx::mbar_wait(&full_bar[s], ph);
-          ptx::tc_fence_after();
-          const uint32_t sa = ptx::smem_u32(smem + (size_t)s * stage_bytes);
-          const uint32_t sb = sa + p.a_bytes;
-          for (int u = 0; u < ksub; ++u) {
-            const int tap = p.rowshift ? u * p.KW + tap_outer : tap_outer;
-            const uint64_t da = ptx::make_kmajor_desc(sa + (uint32_t)u * p.row_shift_bytes, row_bytes);
-            const uint32_t baddr = p.b_resident ? sres + (uint32_t)(tap * p.kchunks + kc) * p.b_stage_bytes
-                                                : sb + (uint32_t)(p.rowshift ? u : 0) * p.b_stage_bytes;
-            const uint64_t db = ptx::make_kmajor_desc(baddr, row_bytes);
-            for (int j = 0; j < nk; ++j) {
-              // advance 16 K-elements = 32 bytes inside the swizzle span: +2 in the (addr >> 4) field
-              ptx::umma_bf16(d_tmem, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), p.idesc, accumulate);
-              accumulate = 1u;
+        const int n_outer_taps = p.rowshift ? p.KW : p.KH * p.KW;
+        for (int tap_outer = 0; tap_outer < n_outer_taps; ++tap_outer)  // rowshift: kw ; classic: kh * KW + kw
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            // K sub-blocks of 16 that hold real channels (the zero-filled tail of a ragged chunk is skipped)
+            const int nk = (min(p.BK, p.Cin - kc * p.BK) + 15) >> 4;
+            ptx::mbar_wait(&full_bar[s], ph);
+            ptx::tc_fence_after();
+            const uint32_t sa = ring_u32 + (uint32_t)s * stage_bytes;
+            const uint32_t sb = sa + p.a_bytes;
+            for (int u = 0; u < ksub; ++u) {
+              const int tap = p.rowshift ? u * p.KW + tap_outer : tap_outer;
+              const uint32_t baddr = p.b_resident ? sres + (uint32_t)(tap * p.kchunks + kc) * p.b_stage_bytes
+                                                  : sb + (uint32_t)(p.rowshift ? u : 0) * p.b_stage_bytes;
+              // descriptors differ only in the 14-bit (address >> 4) field; +2 there = 32 bytes = 16 K-elements
+              const uint64_t da = desc_hi | (uint64_t)(((sa + (uint32_t)u * p.row_shift_bytes) & 0x3FFFFu) >> 4);
+              const uint64_t db = desc_hi | (uint64_t)((baddr & 0x3FFFFu) >> 4);
+              for (int j = 0; j < nk; ++j) {
+                ptx::umma_bf16(d_tmem, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), p.idesc, accumulate);
+                accumulate = 1u;
+              }
+            }
+            ptx::umma_commit(&empty_bar[s]);
+            if (++s == p.stages) {
+              s = 0;
+              ph ^= 1u;
             }
           }
-          ptx::umma_commit(&empty_bar[s]);
-          if (++s == p.stages) {
-            s = 0;
-            ph ^= 1u;
-          }
-        }
         ptx::umma_commit(&tmem_full[acc]);
       }
     }
@@ -349,7 +366,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     const int q = warp & 3;
     const int half = e >> 2;
     const int row = q * 32 + lane;
-    const int hl = row / p.Wt;
+    const int hl = (int)fdiv((uint32_t)row, p.fd_wt);
     const int wl = row - hl * p.Wt;
     // this warp's 32 pixels as a TMA box: {32 ch, bw, 32 / bw, 1}
     const int bw = min(p.Wt, 32);
@@ -628,6 +645,10 @@ int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
     delete o;
     return Y5OBB_EINVAL;
   }
+  k.fd_ntn = make_fastdiv((uint32_t)k.n_tiles_n);
+  k.fd_per_img = make_fastdiv((uint32_t)(k.tiles_h * k.tiles_w));
+  k.fd_tiles_w = make_fastdiv((uint32_t)k.tiles_w);
+  k.fd_wt = make_fastdiv((uint32_t)k.Wt);
   k.idesc = ptx::make_idesc_bf16(BM, bn);
   k.mode = d->mode;
   k.act = d->act;
