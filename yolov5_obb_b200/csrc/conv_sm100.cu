@@ -70,6 +70,7 @@ struct ConvK {
   int Cout, cout_pad;
   int Cin, kchunks, KH, KW, stride, pad_h, pad_w;
   int stages;
+  int dbg;             // timing experiments only (results are garbage): 1 = no TMA loads, 2 = no MMAs, 4 = no epilogue work
   int pairw;           // 1: stride-2 conv whose input is viewed as horizontal pixel PAIRS (2*pix_stride channels per
                        // position): the column phase of a tap is a channel offset, so TMA reads contiguous rows
   int in_pix_stride;
@@ -292,12 +293,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
               ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
               uint8_t* sa = smem + (size_t)s * stage_bytes;
               uint8_t* sb = sa + p.a_bytes;
-              ptx::mbar_expect_tx(&full_bar[s], p.a_tx_bytes + (uint32_t)p.b_per_stage * p.b_bytes);
-              ptx::tma_load_4d(sa, &p.tmA, &full_bar[s], cbase + kc * p.BK, wi, hi, c.b);
-              for (int j = 0; j < p.b_per_stage; ++j) {
-                const int tap = (p.rowshift ? j : kh) * p.KW + kw;
-                ptx::tma_load_2d(sb + (size_t)j * p.b_stage_bytes, &p.tmB, &full_bar[s], kc * p.BK,
-                                 tap * p.cout_pad + c.n0);
+              if (p.dbg & 1) {
+                ptx::mbar_arrive(&full_bar[s]);
+              } else {
+                ptx::mbar_expect_tx(&full_bar[s], p.a_tx_bytes + (uint32_t)p.b_per_stage * p.b_bytes);
+                ptx::tma_load_4d(sa, &p.tmA, &full_bar[s], cbase + kc * p.BK, wi, hi, c.b);
+                for (int j = 0; j < p.b_per_stage; ++j) {
+                  const int tap = (p.rowshift ? j : kh) * p.KW + kw;
+                  ptx::tma_load_2d(sb + (size_t)j * p.b_stage_bytes, &p.tmB, &full_bar[s], kc * p.BK,
+                                   tap * p.cout_pad + c.n0);
+                }
               }
               if (++s == p.stages) {
                 s = 0;
@@ -337,7 +342,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             ptx::tc_fence_after();
             const uint32_t sa = ring_u32 + (uint32_t)s * stage_bytes;
             const uint32_t sb = sa + p.a_bytes;
-            for (int u = 0; u < ksub; ++u) {
+            for (int u = 0; u < ((p.dbg & 2) ? 0 : ksub); ++u) {
               const int tap = p.rowshift ? u * p.KW + tap_outer : tap_outer;
               const uint32_t baddr = p.b_resident ? sres + (uint32_t)(tap * p.kchunks + kc) * p.b_stage_bytes
                                                   : sb + (uint32_t)(p.rowshift ? u : 0) * p.b_stage_bytes;
@@ -387,6 +392,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
 
       ptx::mbar_wait(&tmem_full[acc], acc_ph);
       ptx::tc_fence_after();
+      if (p.dbg & 4) {
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&tmem_empty[acc]);
+        continue;
+      }
       const uint32_t taddr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(q * 32) << 16);
 
       if (p.mode == MODE_CONV) {
@@ -681,6 +691,7 @@ int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
   k.pairw = (d->stride == 2 && !(d->Win & 1) && in_row_stride == d->in_pix_stride * d->Win &&
              !(d->flags & Y5OBB_CONV_NO_PAIRW)) ? 1 : 0;
   k.in_pix_stride = (int)d->in_pix_stride;
+  k.dbg = (d->flags >> 8) & 7;
   {  // activations: (C, W, H, B), element strides (1, s, s, 1)
     cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->Win, (cuuint64_t)d->Hin, (cuuint64_t)d->B};
     cuuint64_t strides[3] = {(cuuint64_t)d->in_pix_stride * 2, (cuuint64_t)in_row_stride * 2,

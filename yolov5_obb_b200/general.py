@@ -14,7 +14,7 @@ MAX_NMS = 30000   # general.py:794
 
 def non_max_suppression_obb(prediction: torch.Tensor, conf_thres: float = 0.25, iou_thres: float = 0.45,
                             classes: Optional[Sequence[int]] = None, agnostic: bool = False, multi_label: bool = False,
-                            labels=(), max_det: int = 1500) -> List[torch.Tensor]:
+                            labels=(), max_det: int = 1500, return_packed: bool = False):
     """Runs Non-Maximum Suppression (NMS) on inference results_obb.
 
     Args:
@@ -62,4 +62,6 @@ def non_max_suppression_obb(prediction: torch.Tensor, conf_thres: float = 0.25, 
         cap = min(worst, max(c[B], cap * 4))  # rare: more candidates than the optimistic capacity
     if any(k < 0 for k in c[:B]):
         raise RuntimeError("y5obb_nms_obb_f32: internal capacity error")
+    if return_packed:  # (device [B, max_det, 7], per-image row counts) — one buffer for a single D2H copy
+        return out, c[:B]
     return [out[b, :c[b]] for b in range(B)]

@@ -1,0 +1,74 @@
+"""End-to-end detection pipeline from HOST images: the loop of /root/reference/detect.py:104-122 and
+val.py:183-207 (pre-process, inference, NMS) with the host->device copy of batch i+1 overlapped with the
+compute of batch i on a second stream (two device input buffers, event-ordered)."""
+from typing import Iterable, Iterator, List
+
+import torch
+
+from .general import non_max_suppression_obb
+
+
+class DetectPipeline:
+    def __init__(self, model, conf_thres: float = 0.25, iou_thres: float = 0.45, max_det: int = 1500,
+                 multi_label: bool = True, classes=None, agnostic: bool = False, device=None):
+        self.model = model
+        self.kw = dict(conf_thres=conf_thres, iou_thres=iou_thres, classes=classes, agnostic=agnostic,
+                       multi_label=multi_label, max_det=max_det)
+        self.device = torch.device(device) if device is not None else next(model.parameters()).device
+        if self.device.type != "cuda":
+            raise RuntimeError("DetectPipeline needs a CUDA device; there is no CPU path")
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self._bufs = [None, None]
+        self._copied = [torch.cuda.Event(), torch.cuda.Event()]
+        self._consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def _host_out(self, B, max_det):
+        h = getattr(self, "_hout", None)
+        if h is None or h.shape[0] != B or h.shape[1] != max_det:
+            self._hout = torch.empty((B, max_det, 7), dtype=torch.float32).pin_memory()
+        return self._hout
+
+    def _upload(self, slot: int, x_host: torch.Tensor, first_use: bool) -> None:
+        if self._bufs[slot] is None or self._bufs[slot].shape != x_host.shape or self._bufs[slot].dtype != x_host.dtype:
+            self._bufs[slot] = torch.empty(x_host.shape, dtype=x_host.dtype, device=self.device)
+            first_use = True
+        with torch.cuda.stream(self.copy_stream):
+            if not first_use:
+                self.copy_stream.wait_event(self._consumed[slot])  # the engine finished reading this buffer
+            self._bufs[slot].copy_(x_host, non_blocking=True)
+            self._copied[slot].record(self.copy_stream)
+        self.h2d_bytes += x_host.numel() * x_host.element_size()
+
+    def __call__(self, host_batches: Iterable[torch.Tensor]) -> Iterator[List[torch.Tensor]]:
+        """host_batches: pinned uint8 (0..255) or float (0..1) tensors [B,3,H,W].  Yields, per batch, the list of
+        per-image detections [n,7] (cx, cy, l, s, theta, conf, cls) as HOST tensors."""
+        it = iter(host_batches)
+        cur = next(it, None)
+        if cur is None:
+            return
+        used = [False, False]
+        self._upload(0, cur, True)
+        used[0] = True
+        i = 0
+        compute = torch.cuda.current_stream(self.device)
+        while cur is not None:
+            slot = i & 1
+            nxt = next(it, None)
+            if nxt is not None:
+                self._upload(slot ^ 1, nxt, not used[slot ^ 1])
+                used[slot ^ 1] = True
+            compute.wait_event(self._copied[slot])
+            pred, _ = self.model(self._bufs[slot])
+            self._consumed[slot].record(compute)  # the first kernel has consumed the input by now (stream order)
+            packed, counts = non_max_suppression_obb(pred, return_packed=True, **self.kw)
+            kmax = max(counts) if counts else 0
+            host = self._host_out(packed.shape[0], packed.shape[1])
+            if kmax:
+                host[:, :kmax].copy_(packed[:, :kmax], non_blocking=True)  # D2H of this batch's result, one copy
+                compute.synchronize()
+            self.d2h_bytes += packed.shape[0] * kmax * 7 * 4
+            yield [host[b, :k].clone() for b, k in enumerate(counts)]
+            cur = nxt
+            i += 1
