@@ -174,3 +174,24 @@ def test_conv_rejects_bad_arguments():
         Conv(Slice.full(x), wp, bp, 64, 1, 3, 0, True, out=Slice.full(torch.zeros_like(x)))  # stride 3
     with pytest.raises(RuntimeError):
         Conv(Slice.full(x), wp, bp, 64, 1, 1, 0, True, out=None)  # no destination
+
+
+@pytest.mark.parametrize("H,W,C", [(5, 7, 8), (32, 32, 32), (40, 70, 16)])
+def test_sppf_pool_matches_chained_maxpool(H, W, C):
+    """models/common.py:190-196: y1 = m(x), y2 = m(y1), y3 = m(y2) with m = MaxPool2d(5, 1, 2), written at channel
+    offsets C, 2C, 3C of the same buffer (bit-exact: max is exact in bf16)."""
+    from yolov5_obb_b200 import _lib
+    B = 2
+    buf = torch.zeros((B, H, W, 4 * C + 8), dtype=torch.bfloat16, device=DEV)  # wider than 4C: a slice of a bigger buffer
+    x = _mk(B, H, W, C, 12)
+    buf[..., :C] = x
+    rc = _lib.lib().y5obb_sppf_pool(buf.data_ptr(), buf.shape[3], B, H, W, C, _lib.stream_ptr(torch.device(DEV)))
+    assert rc == 0
+    torch.cuda.synchronize()
+    xn = x.float().permute(0, 3, 1, 2)
+    y1 = F.max_pool2d(xn, 5, 1, 2)
+    y2 = F.max_pool2d(y1, 5, 1, 2)
+    y3 = F.max_pool2d(y2, 5, 1, 2)
+    for k, y in enumerate((y1, y2, y3), 1):
+        assert torch.equal(buf[..., k * C:(k + 1) * C].float(), y.permute(0, 2, 3, 1)), k
+    assert torch.equal(buf[..., :C], x) and (buf[..., 4 * C:] == 0).all()

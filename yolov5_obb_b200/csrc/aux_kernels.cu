@@ -90,37 +90,80 @@ __device__ __forceinline__ void vmax8(uint4& a, const uint4& b) {
   for (int i = 0; i < 4; ++i) x[i] = __hmax2(x[i], y[i]);
 }
 
-// one thread = one pixel x 8 channels; windows clipped at the border (max-pool pads with -inf)
-__global__ void k_sppf_pool(__nv_bfloat16* __restrict__ buf, long long pix_stride, int B, int H, int W, int C) {
+// One CTA = one image x 8 channels x one 32x32 spatial tile (+6 halo).  Separable: a horizontal pass builds the
+// 5/9/13-wide row maxima in shared memory, a vertical pass the 5/9/13-tall column maxima of those (max-pool pads
+// with -inf, so clipped windows are exact).  13 + 27 shared-memory reads per pixel instead of 169 global ones.
+constexpr int PT = 32, PH = 6, PIN = PT + 2 * PH;
+__global__ void __launch_bounds__(256) k_sppf_pool(__nv_bfloat16* __restrict__ buf, long long pix_stride, int B, int H,
+                                                    int W, int C, int tiles_w, int tiles_h) {
+  extern __shared__ __align__(16) uint4 sm[];
+  uint4* in = sm;                       // [PIN][PIN]
+  uint4* r5 = in + PIN * PIN;           // [PIN][PT]
+  uint4* r9 = r5 + PIN * PT;
+  uint4* r13 = r9 + PIN * PT;
   const int vec = C >> 3;
-  const long long total = (long long)B * H * W * vec;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int cv = (int)(i % vec);
-    long long r = i / vec;
-    const int w = (int)(r % W);
-    r /= W;
-    const int h = (int)(r % H);
-    const int b = (int)(r / H);
-    const uint4 ninf = make_uint4(0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u);
-    uint4 m5 = ninf, m9 = ninf, m13 = ninf;
-    for (int dy = -6; dy <= 6; ++dy) {
-      const int hh = h + dy;
-      if (hh < 0 || hh >= H) continue;
-      uint4 r5 = ninf, r9 = ninf, r13 = ninf;
-      const __nv_bfloat16* row = buf + (((long long)b * H + hh) * W) * pix_stride + cv * 8;
-      for (int dx = -6; dx <= 6; ++dx) {
-        const int ww = w + dx;
-        if (ww < 0 || ww >= W) continue;
-        const uint4 v = *reinterpret_cast<const uint4*>(row + (long long)ww * pix_stride);
-        vmax8(r13, v);
-        if (dx >= -4 && dx <= 4) vmax8(r9, v);
-        if (dx >= -2 && dx <= 2) vmax8(r5, v);
-      }
-      vmax8(m13, r13);
-      if (dy >= -4 && dy <= 4) vmax8(m9, r9);
-      if (dy >= -2 && dy <= 2) vmax8(m5, r5);
+  int bid = blockIdx.x;
+  const int cv = bid % vec;
+  bid /= vec;
+  const int tw = bid % tiles_w;
+  bid /= tiles_w;
+  const int th = bid % tiles_h;
+  const int b = bid / tiles_h;
+  const int h0 = th * PT, w0 = tw * PT;
+  const uint4 ninf = make_uint4(0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u);
+  const __nv_bfloat16* base = buf + (long long)b * H * W * pix_stride + cv * 8;
+  for (int i = threadIdx.x; i < PIN * PIN; i += 256) {
+    const int y = i / PIN, x = i - y * PIN;
+    const int hh = h0 + y - PH, ww = w0 + x - PH;
+    uint4 v = ninf;
+    if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = *reinterpret_cast<const uint4*>(base + ((long long)hh * W + ww) * pix_stride);
+    in[i] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < PIN * PT; i += 256) {
+    const int y = i / PT, x = i - y * PT;
+    const uint4* row = in + y * PIN + x + PH;
+    uint4 a5 = row[0];
+    vmax8(a5, row[-1]);
+    vmax8(a5, row[1]);
+    vmax8(a5, row[-2]);
+    vmax8(a5, row[2]);
+    uint4 a9 = a5;
+    vmax8(a9, row[-3]);
+    vmax8(a9, row[3]);
+    vmax8(a9, row[-4]);
+    vmax8(a9, row[4]);
+    uint4 a13 = a9;
+    vmax8(a13, row[-5]);
+    vmax8(a13, row[5]);
+    vmax8(a13, row[-6]);
+    vmax8(a13, row[6]);
+    r5[i] = a5;
+    r9[i] = a9;
+    r13[i] = a13;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < PT * PT; i += 256) {
+    const int y = i / PT, x = i - y * PT;
+    const int hh = h0 + y, ww = w0 + x;
+    if (hh >= H || ww >= W) continue;
+    const int c = (y + PH) * PT + x;
+    uint4 m5 = r5[c];
+    for (int d = 1; d <= 2; ++d) {
+      vmax8(m5, r5[c - d * PT]);
+      vmax8(m5, r5[c + d * PT]);
     }
-    __nv_bfloat16* o = buf + (((long long)b * H + h) * W + w) * pix_stride + cv * 8;
+    uint4 m9 = r9[c];
+    for (int d = 1; d <= 4; ++d) {
+      vmax8(m9, r9[c - d * PT]);
+      vmax8(m9, r9[c + d * PT]);
+    }
+    uint4 m13 = r13[c];
+    for (int d = 1; d <= 6; ++d) {
+      vmax8(m13, r13[c - d * PT]);
+      vmax8(m13, r13[c + d * PT]);
+    }
+    __nv_bfloat16* o = buf + (((long long)b * H + hh) * W + ww) * pix_stride + cv * 8;
     *reinterpret_cast<uint4*>(o + C) = m5;
     *reinterpret_cast<uint4*>(o + 2 * C) = m9;
     *reinterpret_cast<uint4*>(o + 3 * C) = m13;
@@ -158,9 +201,17 @@ int y5obb_sppf_pool(void* buf, int64_t pix_stride, int B, int H, int W, int C, v
   if (!buf || B <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 7) || (pix_stride & 7) || pix_stride < 4 * (int64_t)C)
     return Y5OBB_EINVAL;
   if (reinterpret_cast<uintptr_t>(buf) & 15) return Y5OBB_EINVAL;
-  const long long total = (long long)B * H * W * (C / 8);
-  const int grid = (int)std::min<long long>((total + 127) / 128, (long long)sm_count() * 32);
-  k_sppf_pool<<<grid, 128, 0, (cudaStream_t)stream>>>(static_cast<__nv_bfloat16*>(buf), pix_stride, B, H, W, C);
+  const int tiles_w = (W + PT - 1) / PT, tiles_h = (H + PT - 1) / PT;
+  const long long grid = (long long)B * (C / 8) * tiles_w * tiles_h;
+  if (grid > 0x7FFFFFFFll) return Y5OBB_EINVAL;
+  const size_t smem = (size_t)(PIN * PIN + 3 * PIN * PT) * sizeof(uint4);
+  static bool attr_set = false;
+  if (!attr_set) {
+    Y5_CUDA(cudaFuncSetAttribute(k_sppf_pool, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  k_sppf_pool<<<(unsigned)grid, 256, smem, (cudaStream_t)stream>>>(static_cast<__nv_bfloat16*>(buf), pix_stride, B, H, W,
+                                                                  C, tiles_w, tiles_h);
   Y5_LAUNCH_CHECK();
   return Y5OBB_OK;
 }

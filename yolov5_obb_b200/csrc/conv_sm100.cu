@@ -23,6 +23,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -78,7 +79,9 @@ struct ConvK {
                        // groups work on every tile and split its columns (few tiles per CTA)
   int rowshift;    // 1: one A stage holds Ht + KH - 1 image rows; the KH taps of a column read it at row offsets
   int b_resident;  // 1: every weight tile stays in shared memory for the whole kernel (loaded once)
-  int b_per_stage; // weight tiles streamed with each A stage (0 when resident)
+  int b_per_stage; // weight tiles streamed with each A unit (0 when resident)
+  int group;       // (tap, K-chunk) units per pipeline stage: one mbarrier round trip serves `group` TMA boxes
+  int n_units;     // units per tile = (rowshift ? KW : KH*KW) * kchunks
   uint32_t a_bytes, a_tx_bytes, b_bytes, b_stage_bytes, b_res_bytes, row_shift_bytes, epi_stage_bytes;
   uint32_t idesc;
   // epilogue
@@ -231,7 +234,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
   // 1024-byte aligned: [resident weights][operand ring][epilogue staging] (swizzle patterns repeat every 8 rows)
   uint8_t* smem_res = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem = smem_res + p.b_res_bytes;
-  const uint32_t stage_bytes = p.a_bytes + (uint32_t)p.b_per_stage * p.b_stage_bytes;
+  const uint32_t unit_bytes = p.a_bytes + (uint32_t)p.b_per_stage * p.b_stage_bytes;
+  const uint32_t stage_bytes = unit_bytes * (uint32_t)p.group;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -275,11 +279,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       }
       int s = 0;
       uint32_t ph = 0;
+      const uint32_t unit_tx = p.a_tx_bytes + (uint32_t)p.b_per_stage * p.b_bytes;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const TileCoord c = decode_tile(p, t);
-        const int kh_n = p.rowshift ? 1 : p.KH;
-        for (int kh = 0; kh < kh_n; ++kh)
-          for (int kw = 0; kw < p.KW; ++kw) {
+        int tap_outer = 0, kc = 0;  // unit = (tap_outer, kc), kc fastest; rowshift: tap_outer = kw, else kh * KW + kw
+        for (int u0 = 0; u0 < p.n_units; u0 += p.group) {
+          const int ng = min(p.group, p.n_units - u0);
+          ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
+          uint8_t* sbase = smem + (size_t)s * stage_bytes;
+          if (p.dbg & 1) {
+            ptx::mbar_arrive(&full_bar[s]);
+          } else {
+            ptx::mbar_expect_tx(&full_bar[s], unit_tx * (uint32_t)ng);
+          }
+          for (int g = 0; g < ng; ++g) {
+            const int kh = p.rowshift ? 0 : tap_outer / p.KW;
+            const int kw = p.rowshift ? tap_outer : tap_outer - kh * p.KW;
             int wi = c.w0 * p.stride + kw - p.pad_w;
             const int hi = c.h0 * p.stride + kh - p.pad_h;
             int cbase = 0;
@@ -289,27 +304,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
               wi = c.w0 + ((off - phase) >> 1);
               cbase = phase * p.in_pix_stride;
             }
-            for (int kc = 0; kc < p.kchunks; ++kc) {
-              ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
-              uint8_t* sa = smem + (size_t)s * stage_bytes;
+            if (!(p.dbg & 1)) {
+              uint8_t* sa = sbase + (size_t)g * unit_bytes;
               uint8_t* sb = sa + p.a_bytes;
-              if (p.dbg & 1) {
-                ptx::mbar_arrive(&full_bar[s]);
-              } else {
-                ptx::mbar_expect_tx(&full_bar[s], p.a_tx_bytes + (uint32_t)p.b_per_stage * p.b_bytes);
-                ptx::tma_load_4d(sa, &p.tmA, &full_bar[s], cbase + kc * p.BK, wi, hi, c.b);
-                for (int j = 0; j < p.b_per_stage; ++j) {
-                  const int tap = (p.rowshift ? j : kh) * p.KW + kw;
-                  ptx::tma_load_2d(sb + (size_t)j * p.b_stage_bytes, &p.tmB, &full_bar[s], kc * p.BK,
-                                   tap * p.cout_pad + c.n0);
-                }
-              }
-              if (++s == p.stages) {
-                s = 0;
-                ph ^= 1u;
+              ptx::tma_load_4d(sa, &p.tmA, &full_bar[s], cbase + kc * p.BK, wi, hi, c.b);
+              for (int j = 0; j < p.b_per_stage; ++j) {
+                const int tap = (p.rowshift ? j : kh) * p.KW + kw;
+                ptx::tma_load_2d(sb + (size_t)j * p.b_stage_bytes, &p.tmB, &full_bar[s], kc * p.BK,
+                                 tap * p.cout_pad + c.n0);
               }
             }
+            if (++kc == p.kchunks) {
+              kc = 0;
+              ++tap_outer;
+            }
           }
+          if (++s == p.stages) {
+            s = 0;
+            ph ^= 1u;
+          }
+        }
       }
     }
   } else if (warp == 1) {
@@ -333,14 +347,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
         uint32_t accumulate = 0u;
-        const int n_outer_taps = p.rowshift ? p.KW : p.KH * p.KW;
-        for (int tap_outer = 0; tap_outer < n_outer_taps; ++tap_outer)  // rowshift: kw ; classic: kh * KW + kw
-          for (int kc = 0; kc < p.kchunks; ++kc) {
+        int tap_outer = 0, kc = 0;
+        for (int u0 = 0; u0 < p.n_units; u0 += p.group) {
+          const int ng = min(p.group, p.n_units - u0);
+          ptx::mbar_wait(&full_bar[s], ph);
+          ptx::tc_fence_after();
+          const uint32_t sbase = ring_u32 + (uint32_t)s * stage_bytes;
+          for (int g = 0; g < ng; ++g) {
             // K sub-blocks of 16 that hold real channels (the zero-filled tail of a ragged chunk is skipped)
             const int nk = (min(p.BK, p.Cin - kc * p.BK) + 15) >> 4;
-            ptx::mbar_wait(&full_bar[s], ph);
-            ptx::tc_fence_after();
-            const uint32_t sa = ring_u32 + (uint32_t)s * stage_bytes;
+            const uint32_t sa = sbase + (uint32_t)g * unit_bytes;
             const uint32_t sb = sa + p.a_bytes;
             for (int u = 0; u < ((p.dbg & 2) ? 0 : ksub); ++u) {
               const int tap = p.rowshift ? u * p.KW + tap_outer : tap_outer;
@@ -354,12 +370,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 accumulate = 1u;
               }
             }
-            ptx::umma_commit(&empty_bar[s]);
-            if (++s == p.stages) {
-              s = 0;
-              ph ^= 1u;
+            if (++kc == p.kchunks) {
+              kc = 0;
+              ++tap_outer;
             }
           }
+          ptx::umma_commit(&empty_bar[s]);
+          if (++s == p.stages) {
+            s = 0;
+            ph ^= 1u;
+          }
+        }
         ptx::umma_commit(&tmem_full[acc]);
       }
     }
@@ -536,6 +557,7 @@ int y5obb_conv_tiling(int cin, int cout, int mode, int det_no, int* block_k, int
                       int* cout_pad, int* n_tiles_n) {
   if (cin <= 0 || cout <= 0 || !block_k || !block_n || !cin_pad || !cout_pad || !n_tiles_n) return Y5OBB_EINVAL;
   int bk = cin > 32 ? 64 : (cin > 16 ? 32 : 16);
+  if (cin > 16 && getenv("Y5OBB_EXP_BK64")) bk = 64;  // experiment: 128-byte swizzled rows even for Cin = 32
   int bn, nt;
   if (mode == MODE_DETECT) {
     if (det_no <= 0 || cout % det_no) return Y5OBB_EINVAL;
@@ -646,7 +668,17 @@ int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
         (nt == 1 && b_all + 3 * a_stage <= SMEM_BUDGET && !(d->flags & Y5OBB_CONV_NO_RESIDENT)) ? 1 : 0;
     k.b_res_bytes = k.b_resident ? (uint32_t)b_all : 0u;
     k.b_per_stage = k.b_resident ? 0 : (rowshift ? d->KH : 1);
-    stage_bytes = a_stage + (size_t)k.b_per_stage * k.b_stage_bytes;
+    const size_t unit_bytes = a_stage + (size_t)k.b_per_stage * k.b_stage_bytes;
+    k.n_units = (rowshift ? d->KW : d->KH * d->KW) * k.kchunks;
+    // small units share a stage: every mbarrier round trip (~300-500 cycles in the two single-thread loops)
+    // then moves >= ~24 KB
+    int group = 1;
+    if (!(d->flags & Y5OBB_CONV_NO_GROUP))
+      while (group < k.n_units && group < 4 && (size_t)(group + 1) * unit_bytes <= 40 * 1024 &&
+             (SMEM_BUDGET - k.b_res_bytes) / ((size_t)(group + 1) * unit_bytes) >= 3)
+        ++group;
+    k.group = group;
+    stage_bytes = unit_bytes * group;
     k.stages = (int)std::min<size_t>(MAX_STAGES, (SMEM_BUDGET - k.b_res_bytes) / stage_bytes);
     return k.stages >= (rowshift ? 3 : 2);
   };
