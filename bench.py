@@ -39,7 +39,7 @@ FWD_GFLOP_PER_IMG = 44.60  # BASELINE.md §2 (conv-only forward, yolov5s @1024, 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default=MODEL)
@@ -250,11 +250,11 @@ def run_ours(args):
             ms = float(t.item())
         return ms, r
 
+    # nvidia-smi takes ~100 ms to start: launch it before the warm-up so that it is sampling (every 100 ms) while
+    # the timed region runs; warm-up and timed steps are the same load
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         dets = step_device()
-    cand_per_img = None
-
-    sampler = ClockSampler(local) if rank == 0 else None
     ms_total, dets = timed(step_device, args.steps)
     clocks = sampler.stop() if sampler else None
     ms_step = ms_total / args.steps

@@ -80,6 +80,8 @@ struct ConvK {
   int rowshift;    // 1: one A stage holds Ht + KH - 1 image rows; the KH taps of a column read it at row offsets
   int b_resident;  // 1: every weight tile stays in shared memory for the whole kernel (loaded once)
   int b_per_stage; // weight tiles streamed with each A unit (0 when resident)
+  int kparts;      // partial accumulators per tile: consecutive MMAs rotate over `kparts` TMEM column ranges so that
+                   // back-to-back MMAs never wait on each other's accumulate latency (small-N layers); the epilogue sums them
   int group;       // (tap, K-chunk) units per pipeline stage: one mbarrier round trip serves `group` TMA boxes
   int n_units;     // units per tile = (rowshift ? KW : KH*KW) * kchunks
   uint32_t a_bytes, a_tx_bytes, b_bytes, b_stage_bytes, b_res_bytes, row_shift_bytes, epi_stage_bytes;
@@ -145,6 +147,7 @@ struct EpiTile {
   __nv_bfloat16* urow;        // up-sampled destination of this thread's pixel (+ n0) or null
   long long up_pix, up_row;
   int nvalid, col_first, col_step;
+  int kparts, bn;     // partial accumulators to sum, their column pitch
   const CUtensorMap* tm;
   int cn0, cw, chh, cb;
 };
@@ -154,6 +157,16 @@ __device__ __forceinline__ void conv_epi_tile(const EpiTile& e, int& sbuf) {
   for (int c0 = e.col_first; c0 < e.nvalid; c0 += e.col_step) {
     uint32_t r[32];
     ptx::tmem_ld_32x32b_x32(e.taddr + (uint32_t)c0, r);
+    if (e.kparts > 1) {  // sum the partial accumulators (K was dealt round-robin over them)
+      for (int q = 1; q < e.kparts; ++q) {
+        uint32_t r2[32];
+        ptx::tmem_ld_wait();
+        ptx::tmem_ld_32x32b_x32(e.taddr + (uint32_t)(q * e.bn + c0), r2);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(__uint_as_float(r[k]) + __uint_as_float(r2[k]));
+      }
+    }
     uint4 rv[4];
     if (RES) {  // all four 16-byte residual loads are in flight before anything waits on them
 #pragma unroll
@@ -346,7 +359,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         ptx::mbar_wait(&tmem_empty[acc], acc_ph ^ 1u);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
-        uint32_t accumulate = 0u;
+        int mma_i = 0;  // MMAs issued for this tile; MMA i accumulates into partial i % kparts
+        int part = 0;
         int tap_outer = 0, kc = 0;
         for (int u0 = 0; u0 < p.n_units; u0 += p.group) {
           const int ng = min(p.group, p.n_units - u0);
@@ -366,8 +380,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
               const uint64_t da = desc_hi | (uint64_t)(((sa + (uint32_t)u * p.row_shift_bytes) & 0x3FFFFu) >> 4);
               const uint64_t db = desc_hi | (uint64_t)((baddr & 0x3FFFFu) >> 4);
               for (int j = 0; j < nk; ++j) {
-                ptx::umma_bf16(d_tmem, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), p.idesc, accumulate);
-                accumulate = 1u;
+                ptx::umma_bf16(d_tmem + (uint32_t)(part * p.BN), da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), p.idesc,
+                               mma_i >= p.kparts ? 1u : 0u);
+                ++mma_i;
+                if (++part == p.kparts) part = 0;
               }
             }
             if (++kc == p.kchunks) {
@@ -439,6 +455,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         et.nvalid = nvalid;
         et.col_first = col_first;
         et.col_step = col_step;
+        et.kparts = p.kparts;
+        et.bn = p.BN;
         et.tm = &p.tmO;
         et.cn0 = c.n0;
         et.cw = c.w0 + box_w0;
@@ -465,7 +483,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         for (int c0 = col_first; c0 < p.det_no; c0 += col_step) {
           uint32_t r[32];
           ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)c0, r);
-          ptx::tmem_ld_wait();
+          ptx::tmem_ld_wait();  // Detect tiles are wide (BN = 208): kparts == 1
           if (lane == 0) ptx::tma_store_wait_read<1>();
           __syncwarp();
           uint8_t* sb = stage + sbuf * p.epi_stage_bytes;
@@ -557,7 +575,6 @@ int y5obb_conv_tiling(int cin, int cout, int mode, int det_no, int* block_k, int
                       int* cout_pad, int* n_tiles_n) {
   if (cin <= 0 || cout <= 0 || !block_k || !block_n || !cin_pad || !cout_pad || !n_tiles_n) return Y5OBB_EINVAL;
   int bk = cin > 32 ? 64 : (cin > 16 ? 32 : 16);
-  if (cin > 16 && getenv("Y5OBB_EXP_BK64")) bk = 64;  // experiment: 128-byte swizzled rows even for Cin = 32
   int bn, nt;
   if (mode == MODE_DETECT) {
     if (det_no <= 0 || cout % det_no) return Y5OBB_EINVAL;
@@ -686,6 +703,14 @@ int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
   if (!(want_rowshift && plan(true)) && !plan(false)) {
     delete o;
     return Y5OBB_EINVAL;
+  }
+  {  // MMAs per tile; partial accumulators fit beside each other in one 256-column TMEM buffer
+    int mmas = 0;
+    for (int kc = 0; kc < k.kchunks; ++kc) mmas += (std::min(bk, d->Cin - kc * bk) + 15) / 16;
+    mmas *= (k.rowshift ? d->KW : d->KH * d->KW) * (k.rowshift ? d->KH : 1);
+    int parts = std::min(4, 256 / bn);
+    if (d->mode == MODE_DETECT || (d->flags & Y5OBB_CONV_NO_KPARTS)) parts = 1;
+    k.kparts = std::max(1, std::min(parts, mmas));
   }
   k.fd_ntn = make_fastdiv((uint32_t)k.n_tiles_n);
   k.fd_per_img = make_fastdiv((uint32_t)(k.tiles_h * k.tiles_w));

@@ -46,7 +46,8 @@ def non_max_suppression_obb(prediction: torch.Tensor, conf_thres: float = 0.25, 
     out = torch.empty((B, max_det, 7), dtype=torch.float32, device=dev)
     counts = torch.empty(B + 1, dtype=torch.int64, device=dev)
     worst = B * A * (nc if (multi_label and nc > 1) else 1)
-    cap = min(worst, max(B * 4 * MAX_NMS, 1 << 18))
+    # optimistic capacity (every kernel of the pipeline runs over `cap` slots); grown on overflow below
+    cap = min(worst, max(B * 8192, 1 << 16))
     while True:
         with torch.cuda.device(dev):
             nbytes = L.y5obb_nms_obb_workspace_bytes(B, A, cap, MAX_NMS)
