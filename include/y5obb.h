@@ -98,7 +98,6 @@ typedef struct y5obb_conv y5obb_conv_t;
 #define Y5OBB_CONV_NO_RESIDENT 2   /* flags: always stream the weight tiles */
 #define Y5OBB_CONV_BIAS_HALVED 8    /* flags: REQUIRED when act = 1: `bias` holds 0.5 * b (SiLU is evaluated as h + h*tanh(h), h = x/2) */
 #define Y5OBB_CONV_NO_GROUP 16      /* flags: one (tap, K-chunk) unit per pipeline stage */
-#define Y5OBB_CONV_NO_KPARTS 32     /* flags: one accumulator per tile (no K round-robin over partial accumulators) */
 #define Y5OBB_CONV_NO_PAIRW 4      /* flags: stride-2 convs use TMA element strides along W instead of the pixel-pair view */
 
 typedef struct {

@@ -80,8 +80,6 @@ struct ConvK {
   int rowshift;    // 1: one A stage holds Ht + KH - 1 image rows; the KH taps of a column read it at row offsets
   int b_resident;  // 1: every weight tile stays in shared memory for the whole kernel (loaded once)
   int b_per_stage; // weight tiles streamed with each A unit (0 when resident)
-  int kparts;      // partial accumulators per tile: consecutive MMAs rotate over `kparts` TMEM column ranges so that
-                   // back-to-back MMAs never wait on each other's accumulate latency (small-N layers); the epilogue sums them
   int group;       // (tap, K-chunk) units per pipeline stage: one mbarrier round trip serves `group` TMA boxes
   int n_units;     // units per tile = (rowshift ? KW : KH*KW) * kchunks
   uint32_t a_bytes, a_tx_bytes, b_bytes, b_stage_bytes, b_res_bytes, row_shift_bytes, epi_stage_bytes;
@@ -135,6 +133,22 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 
 
+
+// One (tap, K-chunk) unit: KSUB vertical taps x NK sub-blocks of 16 channels, fully unrolled
+template <int KSUB, int NK>
+__device__ __forceinline__ void issue_unit(uint32_t d_tmem, uint64_t da0, uint64_t db0, uint32_t a_step, uint32_t b_step,
+                                           uint32_t idesc, uint32_t& accumulate) {
+#pragma unroll
+  for (int u = 0; u < KSUB; ++u) {
+#pragma unroll
+    for (int j = 0; j < NK; ++j) {
+      ptx::umma_bf16(d_tmem, da0 + (uint64_t)(u * a_step + 2 * j), db0 + (uint64_t)(u * b_step + 2 * j), idesc,
+                     (u | j) ? 1u : accumulate);
+    }
+  }
+  accumulate = 1u;
+}
+
 // ---- epilogue of one MODE_CONV tile for one warp -----------------------------------------------------
 struct EpiTile {
   uint32_t taddr;     // TMEM address of this warp's lane quarter, column 0 of the accumulator
@@ -147,7 +161,6 @@ struct EpiTile {
   __nv_bfloat16* urow;        // up-sampled destination of this thread's pixel (+ n0) or null
   long long up_pix, up_row;
   int nvalid, col_first, col_step;
-  int kparts, bn;     // partial accumulators to sum, their column pitch
   const CUtensorMap* tm;
   int cn0, cw, chh, cb;
 };
@@ -157,16 +170,6 @@ __device__ __forceinline__ void conv_epi_tile(const EpiTile& e, int& sbuf) {
   for (int c0 = e.col_first; c0 < e.nvalid; c0 += e.col_step) {
     uint32_t r[32];
     ptx::tmem_ld_32x32b_x32(e.taddr + (uint32_t)c0, r);
-    if (e.kparts > 1) {  // sum the partial accumulators (K was dealt round-robin over them)
-      for (int q = 1; q < e.kparts; ++q) {
-        uint32_t r2[32];
-        ptx::tmem_ld_wait();
-        ptx::tmem_ld_32x32b_x32(e.taddr + (uint32_t)(q * e.bn + c0), r2);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(__uint_as_float(r[k]) + __uint_as_float(r2[k]));
-      }
-    }
     uint4 rv[4];
     if (RES) {  // all four 16-byte residual loads are in flight before anything waits on them
 #pragma unroll
@@ -353,14 +356,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       const uint32_t sres = ptx::smem_u32(smem_res);
       const uint32_t ring_u32 = ptx::smem_u32(smem);
       const uint64_t desc_hi = ptx::make_kmajor_desc(0u, row_bytes);
+      // per vertical tap u (row-shift mode): A moves by one image row of the tile, B by KW weight tiles (resident:
+      // tap = u * KW + kw) or by one streamed tile; both in units of 16 bytes
+      const uint32_t a_step = p.row_shift_bytes >> 4;
+      const uint32_t b_step = (p.b_resident ? (uint32_t)(p.KW * p.kchunks) * p.b_stage_bytes : p.b_stage_bytes) >> 4;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
         const int acc = it & 1;
         const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
         ptx::mbar_wait(&tmem_empty[acc], acc_ph ^ 1u);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
-        int mma_i = 0;  // MMAs issued for this tile; MMA i accumulates into partial i % kparts
-        int part = 0;
+        uint32_t accumulate = 0u;
         int tap_outer = 0, kc = 0;
         for (int u0 = 0; u0 < p.n_units; u0 += p.group) {
           const int ng = min(p.group, p.n_units - u0);
@@ -371,19 +377,34 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             // K sub-blocks of 16 that hold real channels (the zero-filled tail of a ragged chunk is skipped)
             const int nk = (min(p.BK, p.Cin - kc * p.BK) + 15) >> 4;
             const uint32_t sa = sbase + (uint32_t)g * unit_bytes;
-            const uint32_t sb = sa + p.a_bytes;
-            for (int u = 0; u < ((p.dbg & 2) ? 0 : ksub); ++u) {
-              const int tap = p.rowshift ? u * p.KW + tap_outer : tap_outer;
-              const uint32_t baddr = p.b_resident ? sres + (uint32_t)(tap * p.kchunks + kc) * p.b_stage_bytes
-                                                  : sb + (uint32_t)(p.rowshift ? u : 0) * p.b_stage_bytes;
-              // descriptors differ only in the 14-bit (address >> 4) field; +2 there = 32 bytes = 16 K-elements
-              const uint64_t da = desc_hi | (uint64_t)(((sa + (uint32_t)u * p.row_shift_bytes) & 0x3FFFFu) >> 4);
-              const uint64_t db = desc_hi | (uint64_t)((baddr & 0x3FFFFu) >> 4);
-              for (int j = 0; j < nk; ++j) {
-                ptx::umma_bf16(d_tmem + (uint32_t)(part * p.BN), da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), p.idesc,
-                               mma_i >= p.kparts ? 1u : 0u);
-                ++mma_i;
-                if (++part == p.kparts) part = 0;
+            // descriptors differ only in the 14-bit (address >> 4) field
+            const uint64_t da0 = desc_hi | (uint64_t)((sa & 0x3FFFFu) >> 4);
+            const uint32_t b0 = p.b_resident ? sres + (uint32_t)(tap_outer * p.kchunks + kc) * p.b_stage_bytes
+                                             : sa + p.a_bytes;
+            const uint64_t db0 = desc_hi | (uint64_t)((b0 & 0x3FFFFu) >> 4);
+            if (!(p.dbg & 2)) {
+              // fully unrolled issue sequences: the single issuing thread does ~4 scalar instructions per MMA
+              if (ksub == 3) {
+                switch (nk) {
+                  case 1: issue_unit<3, 1>(d_tmem, da0, db0, a_step, b_step, p.idesc, accumulate); break;
+                  case 2: issue_unit<3, 2>(d_tmem, da0, db0, a_step, b_step, p.idesc, accumulate); break;
+                  case 3: issue_unit<3, 3>(d_tmem, da0, db0, a_step, b_step, p.idesc, accumulate); break;
+                  default: issue_unit<3, 4>(d_tmem, da0, db0, a_step, b_step, p.idesc, accumulate); break;
+                }
+              } else if (ksub == 1) {
+                switch (nk) {
+                  case 1: issue_unit<1, 1>(d_tmem, da0, db0, a_step, b_step, p.idesc, accumulate); break;
+                  case 2: issue_unit<1, 2>(d_tmem, da0, db0, a_step, b_step, p.idesc, accumulate); break;
+                  case 3: issue_unit<1, 3>(d_tmem, da0, db0, a_step, b_step, p.idesc, accumulate); break;
+                  default: issue_unit<1, 4>(d_tmem, da0, db0, a_step, b_step, p.idesc, accumulate); break;
+                }
+              } else {
+                for (int u = 0; u < ksub; ++u)
+                  for (int j = 0; j < nk; ++j) {
+                    ptx::umma_bf16(d_tmem, da0 + (uint64_t)(u * a_step + 2 * j), db0 + (uint64_t)(u * b_step + 2 * j),
+                                   p.idesc, accumulate);
+                    accumulate = 1u;
+                  }
               }
             }
             if (++kc == p.kchunks) {
@@ -455,8 +476,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         et.nvalid = nvalid;
         et.col_first = col_first;
         et.col_step = col_step;
-        et.kparts = p.kparts;
-        et.bn = p.BN;
         et.tm = &p.tmO;
         et.cn0 = c.n0;
         et.cw = c.w0 + box_w0;
@@ -483,7 +502,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         for (int c0 = col_first; c0 < p.det_no; c0 += col_step) {
           uint32_t r[32];
           ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)c0, r);
-          ptx::tmem_ld_wait();  // Detect tiles are wide (BN = 208): kparts == 1
+          ptx::tmem_ld_wait();
           if (lane == 0) ptx::tma_store_wait_read<1>();
           __syncwarp();
           uint8_t* sb = stage + sbuf * p.epi_stage_bytes;
@@ -703,14 +722,6 @@ int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
   if (!(want_rowshift && plan(true)) && !plan(false)) {
     delete o;
     return Y5OBB_EINVAL;
-  }
-  {  // MMAs per tile; partial accumulators fit beside each other in one 256-column TMEM buffer
-    int mmas = 0;
-    for (int kc = 0; kc < k.kchunks; ++kc) mmas += (std::min(bk, d->Cin - kc * bk) + 15) / 16;
-    mmas *= (k.rowshift ? d->KW : d->KH * d->KW) * (k.rowshift ? d->KH : 1);
-    int parts = std::min(4, 256 / bn);
-    if (d->mode == MODE_DETECT || (d->flags & Y5OBB_CONV_NO_KPARTS)) parts = 1;
-    k.kparts = std::max(1, std::min(parts, mmas));
   }
   k.fd_ntn = make_fastdiv((uint32_t)k.n_tiles_n);
   k.fd_per_img = make_fastdiv((uint32_t)(k.tiles_h * k.tiles_w));
