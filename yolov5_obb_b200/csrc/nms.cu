@@ -145,6 +145,23 @@ __device__ __forceinline__ void load_prebox(PreBox* dst, const PreBox* src) {
   d[1] = s[1];
 }
 
+// Conservative separating-axis test: true only if the rectangles are apart by more than 1e-3 of their size on one of
+// the four edge normals (then the reference finds no intersection point and no contained vertex: IoU == 0).
+__device__ __forceinline__ bool sat_separated(const PreBox& A, const PreBox& B) {
+  const float dx = B.cx - A.cx, dy = B.cy - A.cy;
+  // unit axes of A: u = (cos, -sin) along w, v = (-sin, -cos) along h (box_corners); c2/s2 hold cos/2, sin/2
+  const float ac = 2.f * A.c2, as = 2.f * A.s2, bc = 2.f * B.c2, bs = 2.f * B.s2;
+  const float ahw = 0.5f * A.w, ahh = 0.5f * A.h, bhw = 0.5f * B.w, bhh = 0.5f * B.h;
+  const float cab = fabsf(ac * bc + as * bs);   // |uA.uB| = |vA.vB|
+  const float sab = fabsf(ac * bs - as * bc);   // |uA.vB| = |vA.uB|
+  const float m = 1e-3f * (ahw + ahh + bhw + bhh) + 1e-3f;
+  if (fabsf(dx * ac - dy * as) > ahw + bhw * cab + bhh * sab + m) return true;   // axis uA
+  if (fabsf(-dx * as - dy * ac) > ahh + bhw * sab + bhh * cab + m) return true;  // axis vA
+  if (fabsf(dx * bc - dy * bs) > bhw + ahw * cab + ahh * sab + m) return true;   // axis uB
+  if (fabsf(-dx * bs - dy * bc) > bhh + ahw * sab + ahh * cab + m) return true;  // axis vB
+  return false;
+}
+
 constexpr int CAND_CAP = 8192;  // candidate pairs buffered per work unit before the IoU phase runs
 
 __global__ void __launch_bounds__(TILE_THREADS)
@@ -160,6 +177,9 @@ k_tiles(const PreBox* __restrict__ pre, const NmsSeg* __restrict__ seg, int n_im
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const long long total = ctrl->total_units;
+  // decision-exact shortcuts need a margin against the ~1e-6 relative error of the reference's own arithmetic;
+  // they are only taken for ordinary thresholds
+  const float thr_lo = thr >= 0.01f ? thr * 0.999f : -1.0f;
 
   for (;;) {
     if (tid == 0) s_unit = (long long)atomicAdd(&ctrl->next_unit, 1ull);
@@ -201,6 +221,7 @@ k_tiles(const PreBox* __restrict__ pre, const NmsSeg* __restrict__ seg, int n_im
         const int r = pr >> 9, cbl = (pr >> 6) & 7, j = pr & 63;
         PreBox cbx;
         load_prebox(&cbx, &pre[S.off + (cb0 + cbl) * TB + j]);
+        if (thr_lo > 0.f && sat_separated(s_row[r], cbx)) continue;  // disjoint rectangles: IoU == 0 < thr
         const float v = rbox_iou(s_row[r], cbx);
         const bool sup = strict ? (v > thr) : (v >= thr);
         if (sup) atomicOr(&s_mask[r * CHUNK + cbl], 1ull << j);
@@ -218,7 +239,7 @@ k_tiles(const PreBox* __restrict__ pre, const NmsSeg* __restrict__ seg, int n_im
         const int r = tid & (TB - 1);
         const int half = tid >> 6;
         const bool rvalid = r < nrow;
-        const float rx = s_row[r].cx, ry = s_row[r].cy, rr = s_row[r].rad;
+        const float rx = s_row[r].cx, ry = s_row[r].cy, rr = s_row[r].rad, ra = s_row[r].area;
         const int tag = (r << 9) | ((cb - cb0) << 6);
 #pragma unroll 4
         for (int jj = 0; jj < TB / 2; ++jj) {
@@ -228,6 +249,9 @@ k_tiles(const PreBox* __restrict__ pre, const NmsSeg* __restrict__ seg, int n_im
             float dx = rx - s_col[j].cx, dy = ry - s_col[j].cy;
             float R = rr + s_col[j].rad;
             c = (dx * dx + dy * dy) <= R * R;
+            // IoU <= min(area) / max(area): boxes of very different size can never reach the threshold
+            const float ca = s_col[j].area;
+            if (ra >= 0.f && ca >= 0.f && fminf(ra, ca) < thr_lo * fmaxf(ra, ca)) c = false;
           }
           const unsigned bal = __ballot_sync(0xffffffffu, c);
           if (bal) {
