@@ -187,6 +187,22 @@ int y5obb_scale_polys_f32(float* polys8, int64_t n, float pad_x, float pad_y, fl
 int y5obb_gaussian_label(const double* angle_deg, float* csl_out, int64_t n, int num_class, double sigma,
                          void* stream);
 
+/* ---- training-mode BatchNorm + SiLU (NHWC bf16) ------------------------------------------------
+ * Conv.forward = act(bn(conv(x))) in train mode (models/common.py:45-46; BN eps 1e-3, momentum 0.03,
+ * utils/torch_utils.py:160-162).  The conv runs raw (act = 0, zero bias) through y5obb_conv_*; then
+ *   y5obb_bn_stats      per-channel sum / sum of squares over npix pixels (fp32, zeroed inside)
+ *   y5obb_bn_finalize   scale = gamma / sqrt(var_biased + eps), shift = beta - mean * scale, mean / invstd saved
+ *                       for backward, running statistics updated as torch.nn.BatchNorm2d does (unbiased var)
+ *   y5obb_bn_silu_apply y = [res +] act(z * scale + shift) into a channel slice, optional 2x nearest copy (W = image
+ *                       width in pixels, needed only for the up-sampled copy) */
+int y5obb_bn_stats(const void* z, int64_t z_pix_stride, int64_t npix, int C, float* sum, float* sumsq, void* stream);
+int y5obb_bn_finalize(const float* sum, const float* sumsq, int64_t npix, int C, const float* gamma, const float* beta,
+                      float eps, float momentum, float* running_mean, float* running_var, float* scale, float* shift,
+                      float* mean_out, float* invstd_out, void* stream);
+int y5obb_bn_silu_apply(const void* z, int64_t z_pix_stride, int64_t npix, int C, int W, const float* scale,
+                        const float* shift, int act, const void* res, int64_t res_pix_stride, void* y,
+                        int64_t y_pix_stride, void* y2x, int64_t y2x_pix_stride, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

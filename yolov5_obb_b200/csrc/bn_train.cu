@@ -1,0 +1,213 @@
+// Training-mode BatchNorm + SiLU around the tensor-core convolution (NHWC bf16), forward and backward.
+// Replaces the cuDNN/ATen batch_norm + SiLU kernels behind /root/reference/models/common.py:45-46
+// (Conv.forward = act(bn(conv(x)))) in train mode (train.py:324-333), with BN eps = 1e-3 and momentum = 0.03
+// (utils/torch_utils.py:160-162).
+//
+// forward:   z = conv(x) (tensor-core kernel, raw bf16)                     [conv_sm100.cu]
+//            k_bn_stats      per-channel sum / sum of squares of z (fp32 atomics, one pass over z)
+//            k_bn_finalize   mean, biased var -> scale = gamma / sqrt(var + eps), shift = beta - mean * scale;
+//                            running_mean / running_var update (unbiased var), as torch.nn.BatchNorm2d
+//            k_bn_silu_apply y = [res +] silu(z * scale + shift) written to a channel slice (+ optional 2x up-sampled copy)
+// backward:  k_bn_silu_bwd_reduce   dz_hat = dy * silu'(u), u = z*scale+shift; per-channel sum(dz_hat), sum(dz_hat * xhat)
+//            k_bn_silu_bwd_apply    dz = scale * (dz_hat - mean(dz_hat) - xhat * mean(dz_hat * xhat)); dgamma, dbeta
+// All HBM-bound: algorithmic bytes per element are 2 (read z) for stats, 2 + 2 for apply (+2 with a residual).
+#include <cuda_bf16.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace y5obb {
+namespace {
+
+constexpr int STAT_THREADS = 256;
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 o;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return o;
+}
+
+// grid.x = pixel chunks, grid.y = channel-vector groups of (blockDim.x / 32)... layout: each thread owns one
+// 8-channel vector column and strides over pixels; threads of a block cover `vecs` columns x (256 / vecs) pixel lanes
+__global__ void __launch_bounds__(STAT_THREADS) k_bn_stats(const __nv_bfloat16* __restrict__ z, long long pix_stride,
+                                                           long long npix, int C, float* __restrict__ sum,
+                                                           float* __restrict__ sumsq) {
+  const int vecs = C >> 3;
+  const int cols = min(vecs, STAT_THREADS);         // vector columns handled per pass by this block
+  const int lanes = STAT_THREADS / cols;            // pixel lanes per column
+  const int col_in = threadIdx.x % cols, lane = threadIdx.x / cols;
+  __shared__ float red[2][STAT_THREADS][8];
+  for (int cv0 = 0; cv0 < vecs; cv0 += cols) {
+    const int cv = cv0 + col_in;
+    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (cv < vecs && lane < lanes) {
+      for (long long p = (long long)blockIdx.x * lanes + lane; p < npix; p += (long long)gridDim.x * lanes) {
+        float f[8];
+        unpack8(*reinterpret_cast<const uint4*>(z + p * pix_stride + cv * 8), f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          s[k] += f[k];
+          q[k] += f[k] * f[k];
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      red[0][threadIdx.x][k] = s[k];
+      red[1][threadIdx.x][k] = q[k];
+    }
+    __syncthreads();
+    if (lane == 0 && cv < vecs) {
+      for (int l = 1; l < lanes; ++l) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          s[k] += red[0][l * cols + col_in][k];
+          q[k] += red[1][l * cols + col_in][k];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        atomicAdd(sum + cv * 8 + k, s[k]);
+        atomicAdd(sumsq + cv * 8 + k, q[k]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void k_bn_finalize(const float* __restrict__ sum, const float* __restrict__ sumsq, long long npix, int C,
+                              const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
+                              float* __restrict__ running_mean, float* __restrict__ running_var,
+                              float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
+                              float* __restrict__ invstd_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double n = (double)npix;
+  const double m = (double)sum[c] / n;
+  double var = (double)sumsq[c] / n - m * m;
+  if (var < 0) var = 0;
+  const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float sc = gamma[c] * invstd;
+  scale[c] = sc;
+  shift[c] = beta[c] - (float)m * sc;
+  mean_out[c] = (float)m;
+  invstd_out[c] = invstd;
+  if (running_mean) {
+    const double unbiased = n > 1 ? var * n / (n - 1.0) : var;
+    running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * (float)m;
+    running_var[c] = (1.0f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+__device__ __forceinline__ float silu_f(float u) { return u / (1.0f + __expf(-u)); }
+
+__global__ void k_bn_silu_apply(const __nv_bfloat16* __restrict__ z, long long z_stride, long long npix, int C, int W,
+                                const float* __restrict__ scale, const float* __restrict__ shift, int act,
+                                const __nv_bfloat16* __restrict__ res, long long res_stride,
+                                __nv_bfloat16* __restrict__ y, long long y_stride, __nv_bfloat16* __restrict__ y2x,
+                                long long y2x_stride) {
+  const int vecs = C >> 3;
+  const long long total = npix * vecs;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / vecs;
+    const int cv = (int)(i - p * vecs);
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(z + p * z_stride + cv * 8), f);
+    const float4 s0 = *reinterpret_cast<const float4*>(scale + cv * 8), s1 = *reinterpret_cast<const float4*>(scale + cv * 8 + 4);
+    const float4 h0 = *reinterpret_cast<const float4*>(shift + cv * 8), h1 = *reinterpret_cast<const float4*>(shift + cv * 8 + 4);
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float u = fmaf(f[k], sc[k], sh[k]);
+      f[k] = act ? silu_f(u) : u;
+    }
+    if (res) {
+      float r[8];
+      unpack8(*reinterpret_cast<const uint4*>(res + p * res_stride + cv * 8), r);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] += r[k];
+    }
+    const uint4 o = pack8(f);
+    *reinterpret_cast<uint4*>(y + p * y_stride + cv * 8) = o;
+    if (y2x) {  // nearest 2x up-sampled copy: pixel (b, h, w) -> (b, 2h + {0,1}, 2w + {0,1})
+      const long long row = p / W;  // b * H + h
+      const int w = (int)(p - row * W);
+      __nv_bfloat16* u0 = y2x + ((row * 2) * (2LL * W) + 2 * w) * y2x_stride + cv * 8;
+      *reinterpret_cast<uint4*>(u0) = o;
+      *reinterpret_cast<uint4*>(u0 + y2x_stride) = o;
+      *reinterpret_cast<uint4*>(u0 + 2LL * W * y2x_stride) = o;
+      *reinterpret_cast<uint4*>(u0 + 2LL * W * y2x_stride + y2x_stride) = o;
+    }
+  }
+}
+
+}  // namespace
+}  // namespace y5obb
+
+using namespace y5obb;
+
+extern "C" {
+
+int y5obb_bn_stats(const void* z, int64_t z_pix_stride, int64_t npix, int C, float* sum, float* sumsq, void* stream) {
+  if (!z || !sum || !sumsq || npix <= 0 || C <= 0 || (C & 7) || (z_pix_stride & 7)) return Y5OBB_EINVAL;
+  if (reinterpret_cast<uintptr_t>(z) & 15) return Y5OBB_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  Y5_CUDA(cudaMemsetAsync(sum, 0, sizeof(float) * C, st));
+  Y5_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(float) * C, st));
+  const int vecs = C / 8;
+  const int cols = std::min(vecs, STAT_THREADS);
+  const int lanes = STAT_THREADS / cols;
+  const long long want = (npix + lanes - 1) / lanes;
+  const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)sm_count() * 8));
+  k_bn_stats<<<grid, STAT_THREADS, 0, st>>>(static_cast<const __nv_bfloat16*>(z), z_pix_stride, npix, C, sum, sumsq);
+  Y5_LAUNCH_CHECK();
+  return Y5OBB_OK;
+}
+
+int y5obb_bn_finalize(const float* sum, const float* sumsq, int64_t npix, int C, const float* gamma, const float* beta,
+                      float eps, float momentum, float* running_mean, float* running_var, float* scale, float* shift,
+                      float* mean_out, float* invstd_out, void* stream) {
+  if (!sum || !sumsq || !gamma || !beta || !scale || !shift || !mean_out || !invstd_out || npix <= 0 || C <= 0)
+    return Y5OBB_EINVAL;
+  if ((running_mean == nullptr) != (running_var == nullptr)) return Y5OBB_EINVAL;
+  k_bn_finalize<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sum, sumsq, npix, C, gamma, beta, eps, momentum,
+                                                                    running_mean, running_var, scale, shift, mean_out,
+                                                                    invstd_out);
+  Y5_LAUNCH_CHECK();
+  return Y5OBB_OK;
+}
+
+int y5obb_bn_silu_apply(const void* z, int64_t z_pix_stride, int64_t npix, int C, int W, const float* scale,
+                        const float* shift, int act, const void* res, int64_t res_pix_stride, void* y,
+                        int64_t y_pix_stride, void* y2x, int64_t y2x_pix_stride, void* stream) {
+  if (!z || !scale || !shift || !y || npix <= 0 || C <= 0 || (C & 7) || W <= 0) return Y5OBB_EINVAL;
+  if ((z_pix_stride & 7) || (y_pix_stride & 7) || (res && (res_pix_stride & 7)) || (y2x && (y2x_pix_stride & 7)))
+    return Y5OBB_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(res) |
+       reinterpret_cast<uintptr_t>(y2x) | reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(shift)) & 15)
+    return Y5OBB_EINVAL;
+  if (y2x && npix % W) return Y5OBB_EINVAL;
+  const long long total = npix * (C / 8);
+  const int grid = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 16);
+  k_bn_silu_apply<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      static_cast<const __nv_bfloat16*>(z), z_pix_stride, npix, C, W, scale, shift, act,
+      static_cast<const __nv_bfloat16*>(res), res_pix_stride, static_cast<__nv_bfloat16*>(y), y_pix_stride,
+      static_cast<__nv_bfloat16*>(y2x), y2x_pix_stride);
+  Y5_LAUNCH_CHECK();
+  return Y5OBB_OK;
+}
+
+}  // extern "C"

@@ -248,8 +248,17 @@ class Model(nn.Module):
         if augment or profile or visualize:
             raise RuntimeError("augment/profile/visualize are host tooling outside the hot path")
         if self.training:
-            raise RuntimeError("training-mode forward (batch-stat BN + backward) is not built yet; "
-                               "call model.eval() — there is no PyTorch fallback")
+            if torch.is_grad_enabled():
+                raise RuntimeError("training-mode backward (dgrad / wgrad kernels) is not built yet: the training "
+                                   "forward runs under torch.no_grad() only — there is no PyTorch fallback")
+            from .train_engine import TrainEngine
+            key = ("train", tuple(x.shape), x.device.index)
+            eng = self._engines.get(key)
+            if eng is None:
+                eng = self._engines[key] = TrainEngine(self, x.shape[0], x.shape[2], x.shape[3], x.device)
+            else:
+                eng.refresh_weights()
+            return eng.forward(x)
         from .engine import InferenceEngine
         key = (tuple(x.shape), x.device.index)
         eng = self._engines.get(key)
