@@ -203,6 +203,34 @@ int y5obb_bn_silu_apply(const void* z, int64_t z_pix_stride, int64_t npix, int C
                         const float* shift, int act, const void* res, int64_t res_pix_stride, void* y,
                         int64_t y_pix_stride, void* y2x, int64_t y2x_pix_stride, void* stream);
 
+/* backward of y = [res +] act(bn(z)): dz (bf16 NHWC) from dy; optional pass-through of dy into the residual branch's
+ * gradient (gres, overwritten or accumulated); dgamma / dbeta (fp32, overwritten or accumulated).  sum_du / sum_dux are
+ * [C] fp32 scratch. */
+int y5obb_bn_silu_bwd(const void* z, int64_t z_pix_stride, const void* dy, int64_t dy_pix_stride, int64_t npix, int C,
+                      const float* scale, const float* shift, const float* mean, const float* invstd, int act,
+                      float* sum_du, float* sum_dux, void* dz, int64_t dz_pix_stride, void* gres,
+                      int64_t gres_pix_stride, int gres_accumulate, float* dgamma, float* dbeta, int param_accumulate,
+                      void* stream);
+/* NHWC channel slice -> dense NCHW bf16 [B, C, hw] (hw = H*W, multiple of 8): the K-major operand layout of wgrad */
+int y5obb_nhwc_to_nchw(const void* src, int64_t src_pix_stride, void* dst_nchw, int B, int C, int64_t hw, int phase_w,
+                       void* stream);  /* phase_w = W > 0: de-interleaved [B][C][(h&1)*2+(w&1)][H/2][W/2] for stride-2 wgrad */
+
+/* ---- weight gradient (tcgen05 GEMM over the pixel axis) -------------------------------------------
+ * dW[tap][co][ci] (fp32, ACCUMULATED with atomics: zero it first) = sum_{b,ho,wo} dz[b,co,ho,wo] * x[b,ci,s*ho+kh-p,s*wo+kw-p].
+ * Replaces the cuDNN wgrad autograd calls for models/common.py:37-46 under train.py:333.  Operands are NCHW bf16 copies
+ * (y5obb_nhwc_to_nchw); for stride 2 the x copy must be the de-interleaved one.  Wo (and Wi, or Wi/2) multiples of 8. */
+typedef struct y5obb_wgrad y5obb_wgrad_t;
+typedef struct {
+  const void* dz_nchw;   /* [B][Cout][Ho][Wo] bf16 */
+  const void* x_nchw;    /* stride 1: [B][Cin][Hi][Wi]; stride 2: [B][Cin][4][Hi/2][Wi/2] */
+  float* dw;             /* [KH*KW][Cout][Cin] fp32 */
+  int B, Cout, Ho, Wo, Cin, Hi, Wi;
+  int KH, KW, stride, pad_h, pad_w;
+} y5obb_wgrad_desc;
+int y5obb_wgrad_create(const y5obb_wgrad_desc* desc, y5obb_wgrad_t** out);
+int y5obb_wgrad_run(const y5obb_wgrad_t* w, void* stream);
+void y5obb_wgrad_destroy(y5obb_wgrad_t* w);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,114 @@
+"""GPU parity of the training-only kernels against torch autograd (fp32 on the same bf16-rounded inputs):
+BatchNorm(train)+SiLU backward, NHWC->NCHW copies (plain and de-interleaved), tensor-core wgrad."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from yolov5_obb_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _bf(t):
+    return t.to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("act,with_res", [(True, False), (True, True), (False, False)])
+def test_bn_silu_forward_backward(act, with_res):
+    L = _lib.lib()
+    st = _lib.stream_ptr(torch.device(DEV))
+    B, H, W, C = 2, 12, 16, 48
+    g = torch.Generator().manual_seed(3)
+    z = _bf(torch.randn(B, H, W, C, generator=g) * 1.5 + 0.3).to(DEV)
+    res = _bf(torch.randn(B, H, W, C, generator=g)).to(DEV) if with_res else None
+    dy = _bf(torch.randn(B, H, W, C, generator=g)).to(DEV)
+    gamma = (torch.rand(C, generator=g) + 0.5).to(DEV)
+    beta = (torch.randn(C, generator=g) * 0.2).to(DEV)
+    rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+    npix = B * H * W
+    f32 = lambda: torch.empty(C, dtype=torch.float32, device=DEV)
+    s1, s2, scale, shift, mean, invstd = f32(), f32(), f32(), f32(), f32(), f32()
+    y = torch.zeros_like(z)
+    assert L.y5obb_bn_stats(z.data_ptr(), C, npix, C, s1.data_ptr(), s2.data_ptr(), st) == 0
+    assert L.y5obb_bn_finalize(s1.data_ptr(), s2.data_ptr(), npix, C, gamma.data_ptr(), beta.data_ptr(), 1e-3, 0.03,
+                               rm.data_ptr(), rv.data_ptr(), scale.data_ptr(), shift.data_ptr(), mean.data_ptr(),
+                               invstd.data_ptr(), st) == 0
+    assert L.y5obb_bn_silu_apply(z.data_ptr(), C, npix, C, W, scale.data_ptr(), shift.data_ptr(), int(act),
+                                 res.data_ptr() if with_res else None, C, y.data_ptr(), C, None, 0, st) == 0
+    # reference (fp32 autograd on the same bf16 values)
+    zr = z.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rm_r, rv_r = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+    u = F.batch_norm(zr, rm_r, rv_r, gr, br, True, 0.03, 1e-3)
+    yr = F.silu(u) if act else u
+    if with_res:
+        yr = yr + res.float().permute(0, 3, 1, 2)
+    torch.cuda.synchronize()
+    assert (y.float() - yr.permute(0, 2, 3, 1)).abs().max().item() < 0.03 * yr.abs().max().item() + 0.02
+    assert torch.allclose(rm, rm_r, atol=1e-4) and torch.allclose(rv, rv_r, rtol=1e-3, atol=1e-4)
+    yr.backward(dy.float().permute(0, 3, 1, 2))
+    dz = torch.zeros_like(z)
+    gres = torch.zeros_like(z) if with_res else None
+    dgam, dbet = f32(), f32()
+    rc = L.y5obb_bn_silu_bwd(z.data_ptr(), C, dy.data_ptr(), C, npix, C, scale.data_ptr(), shift.data_ptr(),
+                             mean.data_ptr(), invstd.data_ptr(), int(act), s1.data_ptr(), s2.data_ptr(), dz.data_ptr(), C,
+                             gres.data_ptr() if with_res else None, C, 0, dgam.data_ptr(), dbet.data_ptr(), 0, st)
+    assert rc == 0
+    torch.cuda.synchronize()
+    ref_dz = zr.grad.permute(0, 2, 3, 1)
+    assert (dz.float() - ref_dz).abs().max().item() < 0.02 * ref_dz.abs().max().item() + 1e-3
+    assert torch.allclose(dgam, gr.grad, rtol=2e-3, atol=2e-2) and torch.allclose(dbet, br.grad, rtol=2e-3, atol=2e-2)
+    if with_res:
+        assert torch.equal(gres, dy)
+
+
+@pytest.mark.parametrize("phase", [False, True])
+def test_nhwc_to_nchw(phase):
+    from yolov5_obb_b200.train_ops import nhwc_to_nchw
+    B, H, W, Ctot, c_off, C = 2, 16, 24, 96, 16, 40
+    g = torch.Generator().manual_seed(1)
+    buf = _bf(torch.randn(B, H, W, Ctot, generator=g)).to(DEV)
+    dst = torch.zeros((B, C, H, W), dtype=torch.bfloat16, device=DEV)
+    nhwc_to_nchw(buf.data_ptr() + 2 * c_off, Ctot, dst, B, C, H, W, phase_split=phase)
+    torch.cuda.synchronize()
+    ref = buf[..., c_off:c_off + C].permute(0, 3, 1, 2).contiguous()
+    if phase:
+        ref = torch.stack([ref[:, :, a::2, b::2] for a in (0, 1) for b in (0, 1)], 2).contiguous()  # [B,C,4,H/2,W/2]
+        assert torch.equal(dst.view(B, C, 4, H // 2, W // 2), ref)
+    else:
+        assert torch.equal(dst, ref)
+
+
+WG_CASES = [
+    # B, Cin, Cout, H, W, k, s
+    (2, 64, 64, 16, 64, 1, 1),
+    (2, 32, 48, 32, 32, 3, 1),
+    (1, 128, 256, 16, 16, 3, 1),
+    (2, 64, 128, 32, 64, 3, 2),
+    (3, 320, 160, 8, 8, 1, 1),
+    (2, 48, 96, 24, 40, 3, 2),
+]
+
+
+@pytest.mark.parametrize("B,Cin,Cout,H,W,k,s", WG_CASES)
+def test_wgrad_matches_autograd(B, Cin, Cout, H, W, k, s):
+    from yolov5_obb_b200.train_ops import Wgrad, nhwc_to_nchw
+    p = k // 2
+    Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    g = torch.Generator().manual_seed(Cin + Cout)
+    x = _bf(torch.randn(B, H, W, Cin, generator=g)).to(DEV)
+    dz = _bf(torch.randn(B, Ho, Wo, Cout, generator=g)).to(DEV)
+    xt = torch.zeros((B, Cin, H, W), dtype=torch.bfloat16, device=DEV)
+    dzt = torch.zeros((B, Cout, Ho, Wo), dtype=torch.bfloat16, device=DEV)
+    nhwc_to_nchw(x.data_ptr(), Cin, xt, B, Cin, H, W, phase_split=(s == 2))
+    nhwc_to_nchw(dz.data_ptr(), Cout, dzt, B, Cout, Ho, Wo)
+    dw = torch.zeros((k * k, Cout, Cin), dtype=torch.float32, device=DEV)
+    Wgrad(dzt, xt, dw, B, Cout, Ho, Wo, Cin, H, W, k, s, p).run()
+    torch.cuda.synchronize()
+    w = torch.zeros((Cout, Cin, k, k), device=DEV, requires_grad=True)
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), w, None, s, p)
+    y.backward(dz.float().permute(0, 3, 1, 2))
+    ref = w.grad.permute(2, 3, 0, 1).reshape(k * k, Cout, Cin)
+    err = (dw - ref).abs().max().item()
+    assert err < 2e-3 * ref.abs().max().item() + 1e-3, f"max err {err} vs scale {ref.abs().max().item()}"

@@ -50,6 +50,13 @@ PROTOTYPES = {
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "y5obb_bn_silu_apply": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,
                                     c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
+    "y5obb_bn_silu_bwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int,
+                                  c_void_p, c_void_p, c_int, c_void_p]),
+    "y5obb_nhwc_to_nchw": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_int64, c_int, c_void_p]),
+    "y5obb_wgrad_create": (c_int, [c_void_p, ctypes.POINTER(c_void_p)]),
+    "y5obb_wgrad_run": (c_int, [c_void_p, c_void_p]),
+    "y5obb_wgrad_destroy": (None, [c_void_p]),
     "y5obb_stem_s2d": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "y5obb_stem_s2d_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "y5obb_sppf_pool": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p]),

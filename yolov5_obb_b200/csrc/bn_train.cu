@@ -154,6 +154,165 @@ __global__ void k_bn_silu_apply(const __nv_bfloat16* __restrict__ z, long long z
   }
 }
 
+
+__device__ __forceinline__ float silu_grad(float u) {
+  const float sg = 1.0f / (1.0f + __expf(-u));
+  return sg * (1.0f + u * (1.0f - sg));
+}
+
+// per-channel sum(du) and sum(du * xhat), du = dy * act'(u), u = z*scale + shift, xhat = (z - mean) * invstd
+__global__ void __launch_bounds__(STAT_THREADS) k_bn_bwd_reduce(const __nv_bfloat16* __restrict__ z, long long z_stride,
+                                                                const __nv_bfloat16* __restrict__ dy, long long dy_stride,
+                                                                long long npix, int C, const float* __restrict__ scale,
+                                                                const float* __restrict__ shift,
+                                                                const float* __restrict__ mean,
+                                                                const float* __restrict__ invstd, int act,
+                                                                float* __restrict__ sum_du, float* __restrict__ sum_dux) {
+  const int vecs = C >> 3;
+  const int cols = min(vecs, STAT_THREADS);
+  const int lanes = STAT_THREADS / cols;
+  const int col_in = threadIdx.x % cols, lane = threadIdx.x / cols;
+  __shared__ float red[2][STAT_THREADS][8];
+  for (int cv0 = 0; cv0 < vecs; cv0 += cols) {
+    const int cv = cv0 + col_in;
+    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (cv < vecs && lane < lanes) {
+      float sc[8], sh[8], mu[8], is[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        sc[k] = scale[cv * 8 + k];
+        sh[k] = shift[cv * 8 + k];
+        mu[k] = mean[cv * 8 + k];
+        is[k] = invstd[cv * 8 + k];
+      }
+      for (long long p = (long long)blockIdx.x * lanes + lane; p < npix; p += (long long)gridDim.x * lanes) {
+        float zf[8], df[8];
+        unpack8(*reinterpret_cast<const uint4*>(z + p * z_stride + cv * 8), zf);
+        unpack8(*reinterpret_cast<const uint4*>(dy + p * dy_stride + cv * 8), df);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float u = fmaf(zf[k], sc[k], sh[k]);
+          const float du = act ? df[k] * silu_grad(u) : df[k];
+          s[k] += du;
+          q[k] += du * (zf[k] - mu[k]) * is[k];
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      red[0][threadIdx.x][k] = s[k];
+      red[1][threadIdx.x][k] = q[k];
+    }
+    __syncthreads();
+    if (lane == 0 && cv < vecs) {
+      for (int l = 1; l < lanes; ++l) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          s[k] += red[0][l * cols + col_in][k];
+          q[k] += red[1][l * cols + col_in][k];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        atomicAdd(sum_du + cv * 8 + k, s[k]);
+        atomicAdd(sum_dux + cv * 8 + k, q[k]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// dz = scale * (du - sum_du / N - xhat * sum_dux / N); optional pass-through of dy into the residual branch
+__global__ void k_bn_bwd_apply(const __nv_bfloat16* __restrict__ z, long long z_stride,
+                               const __nv_bfloat16* __restrict__ dy, long long dy_stride, long long npix, int C,
+                               const float* __restrict__ scale, const float* __restrict__ shift,
+                               const float* __restrict__ mean, const float* __restrict__ invstd, int act,
+                               const float* __restrict__ sum_du, const float* __restrict__ sum_dux,
+                               __nv_bfloat16* __restrict__ dz, long long dz_stride, __nv_bfloat16* __restrict__ gres,
+                               long long gres_stride, int gres_accumulate) {
+  const int vecs = C >> 3;
+  const long long total = npix * vecs;
+  const float inv_n = 1.0f / (float)npix;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / vecs;
+    const int cv = (int)(i - p * vecs);
+    float zf[8], df[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(z + p * z_stride + cv * 8), zf);
+    const uint4 dyv = *reinterpret_cast<const uint4*>(dy + p * dy_stride + cv * 8);
+    unpack8(dyv, df);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = cv * 8 + k;
+      const float sc = scale[c];
+      const float u = fmaf(zf[k], sc, shift[c]);
+      const float du = act ? df[k] * silu_grad(u) : df[k];
+      const float xh = (zf[k] - mean[c]) * invstd[c];
+      o[k] = sc * (du - sum_du[c] * inv_n - xh * sum_dux[c] * inv_n);
+    }
+    *reinterpret_cast<uint4*>(dz + p * dz_stride + cv * 8) = pack8(o);
+    if (gres) {
+      __nv_bfloat16* g = gres + p * gres_stride + cv * 8;
+      if (gres_accumulate) {
+        float a[8];
+        unpack8(*reinterpret_cast<const uint4*>(g), a);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] += df[k];
+        *reinterpret_cast<uint4*>(g) = pack8(a);
+      } else {
+        *reinterpret_cast<uint4*>(g) = dyv;
+      }
+    }
+  }
+}
+
+// dgamma (+)= sum_dux, dbeta (+)= sum_du   (fp32 parameter gradients)
+__global__ void k_bn_param_grads(const float* __restrict__ sum_du, const float* __restrict__ sum_dux, int C,
+                                 float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  dgamma[c] = (accumulate ? dgamma[c] : 0.f) + sum_dux[c];
+  dbeta[c] = (accumulate ? dbeta[c] : 0.f) + sum_du[c];
+}
+
+// NHWC channel slice -> NCHW (bf16), 64 pixels x 64 channels per block through shared memory
+// phase_w > 0: de-interleave for a stride-2 consumer: dst[b][c][(h&1)*2 + (w&1)][h/2][w/2] (phase_w = image width W)
+__global__ void __launch_bounds__(256) k_nhwc_to_nchw(const __nv_bfloat16* __restrict__ src, long long src_stride,
+                                                      __nv_bfloat16* __restrict__ dst, int C, long long hw, int B,
+                                                      int phase_w) {
+  __shared__ __nv_bfloat16 tile[64][64 + 8];
+  const long long p0 = (long long)blockIdx.x * 64;  // pixel within the image
+  const int c0 = blockIdx.y * 64;
+  const int b = blockIdx.z;
+  const __nv_bfloat16* s = src + ((long long)b * hw) * src_stride;
+  for (int i = threadIdx.x; i < 64 * 8; i += 256) {  // 64 pixels x 8 vectors of 8 channels
+    const int px = i >> 3, v = i & 7;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (p0 + px < hw && c0 + v * 8 < C) val = *reinterpret_cast<const uint4*>(s + (p0 + px) * src_stride + c0 + v * 8);
+    *reinterpret_cast<uint4*>(&tile[px][v * 8]) = val;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 64 * 8; i += 256) {  // 64 channels x 8 vectors of 8 pixels
+    const int ch = i >> 3, v = i & 7;
+    if (c0 + ch >= C || p0 + v * 8 >= hw) continue;
+    __nv_bfloat16* plane = dst + ((long long)b * C + c0 + ch) * hw;
+    if (phase_w > 0) {  // scatter: pixel (h, w) -> plane (h&1, w&1), position (h/2, w/2)
+      const int W = phase_w, W2 = W >> 1;
+      const long long q = hw >> 2;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const long long pp = p0 + v * 8 + k;
+        const int h = (int)(pp / W), w = (int)(pp - (long long)h * W);
+        plane[(long long)((h & 1) * 2 + (w & 1)) * q + (long long)(h >> 1) * W2 + (w >> 1)] = tile[v * 8 + k][ch];
+      }
+      continue;
+    }
+    __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = tile[v * 8 + k][ch];
+    *reinterpret_cast<uint4*>(plane + p0 + v * 8) = *reinterpret_cast<const uint4*>(o);
+  }
+}
+
 }  // namespace
 }  // namespace y5obb
 
@@ -206,6 +365,55 @@ int y5obb_bn_silu_apply(const void* z, int64_t z_pix_stride, int64_t npix, int C
       static_cast<const __nv_bfloat16*>(z), z_pix_stride, npix, C, W, scale, shift, act,
       static_cast<const __nv_bfloat16*>(res), res_pix_stride, static_cast<__nv_bfloat16*>(y), y_pix_stride,
       static_cast<__nv_bfloat16*>(y2x), y2x_pix_stride);
+  Y5_LAUNCH_CHECK();
+  return Y5OBB_OK;
+}
+
+
+int y5obb_bn_silu_bwd(const void* z, int64_t z_pix_stride, const void* dy, int64_t dy_pix_stride, int64_t npix, int C,
+                      const float* scale, const float* shift, const float* mean, const float* invstd, int act,
+                      float* sum_du, float* sum_dux, void* dz, int64_t dz_pix_stride, void* gres,
+                      int64_t gres_pix_stride, int gres_accumulate, float* dgamma, float* dbeta, int param_accumulate,
+                      void* stream) {
+  if (!z || !dy || !scale || !shift || !mean || !invstd || !sum_du || !sum_dux || !dz || npix <= 0 || C <= 0 || (C & 7))
+    return Y5OBB_EINVAL;
+  if ((z_pix_stride & 7) || (dy_pix_stride & 7) || (dz_pix_stride & 7) || (gres && (gres_pix_stride & 7))) return Y5OBB_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dz) |
+       reinterpret_cast<uintptr_t>(gres)) & 15)
+    return Y5OBB_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  Y5_CUDA(cudaMemsetAsync(sum_du, 0, sizeof(float) * C, st));
+  Y5_CUDA(cudaMemsetAsync(sum_dux, 0, sizeof(float) * C, st));
+  const int vecs = C / 8;
+  const int cols = std::min(vecs, STAT_THREADS);
+  const int lanes = STAT_THREADS / cols;
+  const long long want = (npix + lanes - 1) / lanes;
+  const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)sm_count() * 8));
+  k_bn_bwd_reduce<<<grid, STAT_THREADS, 0, st>>>(static_cast<const __nv_bfloat16*>(z), z_pix_stride,
+                                                 static_cast<const __nv_bfloat16*>(dy), dy_pix_stride, npix, C, scale,
+                                                 shift, mean, invstd, act, sum_du, sum_dux);
+  Y5_LAUNCH_CHECK();
+  const long long total = npix * vecs;
+  const int g2 = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 16);
+  k_bn_bwd_apply<<<g2, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(z), z_pix_stride,
+                                     static_cast<const __nv_bfloat16*>(dy), dy_pix_stride, npix, C, scale, shift, mean,
+                                     invstd, act, sum_du, sum_dux, static_cast<__nv_bfloat16*>(dz), dz_pix_stride,
+                                     static_cast<__nv_bfloat16*>(gres), gres_pix_stride, gres_accumulate);
+  Y5_LAUNCH_CHECK();
+  if (dgamma && dbeta) {
+    k_bn_param_grads<<<(C + 127) / 128, 128, 0, st>>>(sum_du, sum_dux, C, dgamma, dbeta, param_accumulate);
+    Y5_LAUNCH_CHECK();
+  }
+  return Y5OBB_OK;
+}
+
+int y5obb_nhwc_to_nchw(const void* src, int64_t src_pix_stride, void* dst_nchw, int B, int C, int64_t hw, int phase_w,
+                       void* stream) {
+  if (!src || !dst_nchw || B <= 0 || C <= 0 || hw <= 0 || (src_pix_stride & 7) || (C & 7) || (hw & 7)) return Y5OBB_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst_nchw)) & 15) return Y5OBB_EINVAL;
+  dim3 grid((unsigned)((hw + 63) / 64), (unsigned)((C + 63) / 64), (unsigned)B);
+  k_nhwc_to_nchw<<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<const __nv_bfloat16*>(src), src_pix_stride,
+                                                         static_cast<__nv_bfloat16*>(dst_nchw), C, hw, B, phase_w);
   Y5_LAUNCH_CHECK();
   return Y5OBB_OK;
 }

@@ -1,0 +1,51 @@
+"""ctypes handles for the training-only kernels (BatchNorm backward, layout copies, tensor-core wgrad)."""
+import ctypes
+from ctypes import c_void_p, c_int
+
+import torch
+
+from . import _lib
+
+
+class WgradDesc(ctypes.Structure):
+    """Mirror of y5obb_wgrad_desc (include/y5obb.h)."""
+    _fields_ = [("dz_nchw", c_void_p), ("x_nchw", c_void_p), ("dw", c_void_p),
+                ("B", c_int), ("Cout", c_int), ("Ho", c_int), ("Wo", c_int), ("Cin", c_int), ("Hi", c_int), ("Wi", c_int),
+                ("KH", c_int), ("KW", c_int), ("stride", c_int), ("pad_h", c_int), ("pad_w", c_int)]
+
+
+class Wgrad:
+    """dW[tap][co][ci] += sum_pixels dz * x for fixed buffers (TMA descriptors baked at creation)."""
+
+    def __init__(self, dz_nchw: torch.Tensor, x_nchw: torch.Tensor, dw: torch.Tensor, B, Cout, Ho, Wo, Cin, Hi, Wi, k, stride,
+                 pad):
+        kh, kw = (k, k) if isinstance(k, int) else k
+        ph, pw = (pad, pad) if isinstance(pad, int) else pad
+        d = WgradDesc(dz_nchw.data_ptr(), x_nchw.data_ptr(), dw.data_ptr(), B, Cout, Ho, Wo, Cin, Hi, Wi, kh, kw, stride, ph, pw)
+        assert dw.dtype == torch.float32 and dw.numel() == kh * kw * Cout * Cin
+        self._keep = (dz_nchw, x_nchw, dw)
+        self._h = c_void_p()
+        self.device = dz_nchw.device
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().y5obb_wgrad_create(ctypes.byref(d), ctypes.byref(self._h))
+        _lib.check(rc, "y5obb_wgrad_create")
+
+    def run(self, stream=None):
+        rc = _lib.lib().y5obb_wgrad_run(self._h, stream if stream is not None else _lib.stream_ptr(self.device))
+        _lib.check(rc, "y5obb_wgrad_run")
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                _lib.lib().y5obb_wgrad_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+
+def nhwc_to_nchw(src_ptr: int, src_pix_stride: int, dst: torch.Tensor, B: int, C: int, H: int, W: int, phase_split=False,
+                 stream=None):
+    rc = _lib.lib().y5obb_nhwc_to_nchw(src_ptr, src_pix_stride, dst.data_ptr(), B, C, H * W, W if phase_split else 0,
+                                       stream if stream is not None else _lib.stream_ptr(dst.device))
+    _lib.check(rc, "y5obb_nhwc_to_nchw")
