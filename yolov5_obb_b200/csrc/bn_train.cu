@@ -313,6 +313,125 @@ __global__ void __launch_bounds__(256) k_nhwc_to_nchw(const __nv_bfloat16* __res
   }
 }
 
+
+// gdst[b,h,w,:] (+)= sum of the 2x2 block gsrc[b,2h+{0,1},2w+{0,1},:]   (backward of nn.Upsample(2x nearest))
+__global__ void k_upsample2x_bwd(const __nv_bfloat16* __restrict__ gsrc, long long src_stride,
+                                 __nv_bfloat16* __restrict__ gdst, long long dst_stride, long long npix, int C, int W,
+                                 int accumulate) {
+  const int vecs = C >> 3;
+  const long long total = npix * vecs;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / vecs;
+    const int cv = (int)(i - p * vecs);
+    const long long row = p / W;
+    const int w = (int)(p - row * W);
+    const __nv_bfloat16* s0 = gsrc + ((row * 2) * (2LL * W) + 2 * w) * src_stride + cv * 8;
+    float a[8], t[8];
+    unpack8(*reinterpret_cast<const uint4*>(s0), a);
+    unpack8(*reinterpret_cast<const uint4*>(s0 + src_stride), t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] += t[k];
+    unpack8(*reinterpret_cast<const uint4*>(s0 + 2LL * W * src_stride), t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] += t[k];
+    unpack8(*reinterpret_cast<const uint4*>(s0 + 2LL * W * src_stride + src_stride), t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] += t[k];
+    __nv_bfloat16* d = gdst + p * dst_stride + cv * 8;
+    if (accumulate) {
+      unpack8(*reinterpret_cast<const uint4*>(d), t);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a[k] += t[k];
+    }
+    *reinterpret_cast<uint4*>(d) = pack8(a);
+  }
+}
+
+// dst[b, 2h, 2w, :] = src[b, h, w, :], every other position zero (dst pre-zeroed once; odd positions are never written):
+// the zero-stuffed dz that turns the dgrad of a stride-2 conv into a stride-1 conv
+__global__ void k_zero_stuff2x(const __nv_bfloat16* __restrict__ src, long long src_stride, __nv_bfloat16* __restrict__ dst,
+                               long long dst_stride, long long npix, int C, int W) {
+  const int vecs = C >> 3;
+  const long long total = npix * vecs;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / vecs;
+    const int cv = (int)(i - p * vecs);
+    const long long row = p / W;
+    const int w = (int)(p - row * W);
+    *reinterpret_cast<uint4*>(dst + ((row * 2) * (2LL * W) + 2 * w) * dst_stride + cv * 8) =
+        *reinterpret_cast<const uint4*>(src + p * src_stride + cv * 8);
+  }
+}
+
+// one 5x5/s1/p2 max-pool backward step: gin[argmax window position] += gout (first maximum in row-major window order,
+// as ATen's max_pool2d_with_indices picks); fp32 accumulation buffer gin32 [npix][C]
+__global__ void k_maxpool5_bwd(const __nv_bfloat16* __restrict__ xin, long long in_stride, const float* __restrict__ gout32,
+                               const __nv_bfloat16* __restrict__ gout16, long long gout_stride, float* __restrict__ gin32,
+                               int B, int H, int W, int C) {
+  const long long total = (long long)B * H * W * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long r = i / C;
+    const int w = (int)(r % W);
+    r /= W;
+    const int h = (int)(r % H);
+    const int b = (int)(r / H);
+    const long long pix = ((long long)b * H + h) * W + w;
+    float g = gout16 ? __bfloat162float(gout16[pix * gout_stride + c]) : 0.f;
+    if (gout32) g += gout32[pix * C + c];
+    if (g == 0.f) continue;
+    float best = -INFINITY;
+    long long bp = -1;
+    for (int dy = -2; dy <= 2; ++dy) {
+      const int hh = h + dy;
+      if (hh < 0 || hh >= H) continue;
+      for (int dx = -2; dx <= 2; ++dx) {
+        const int ww = w + dx;
+        if (ww < 0 || ww >= W) continue;
+        const long long q = ((long long)b * H + hh) * W + ww;
+        const float v = __bfloat162float(xin[q * in_stride + c]);
+        if (v > best) {
+          best = v;
+          bp = q;
+        }
+      }
+    }
+    if (bp >= 0) atomicAdd(gin32 + bp * C + c, g);
+  }
+}
+
+// bf16 slice (+)= fp32 dense
+__global__ void k_add_f32_to_bf16(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long dst_stride,
+                                  long long npix, int C, int accumulate) {
+  const long long total = npix * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / C;
+    const int c = (int)(i - p * C);
+    __nv_bfloat16* d = dst + p * dst_stride + c;
+    const float v = src[i] + (accumulate ? __bfloat162float(*d) : 0.f);
+    *d = __float2bfloat16(v);
+  }
+}
+
+// Detect: loss gradient fp32 [B, na, H, W, no] -> bf16 NHWC [B, H, W, na * bn] (anchor a at channels [a*bn, a*bn + no))
+__global__ void k_detect_grad_pack(const float* __restrict__ g, __nv_bfloat16* __restrict__ out, int B, int na, int H, int W,
+                                   int no, int bn) {
+  const long long total = (long long)B * H * W * na * bn;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % bn);
+    long long r = i / bn;
+    const int a = (int)(r % na);
+    r /= na;
+    const int w = (int)(r % W);
+    r /= W;
+    const int h = (int)(r % H);
+    const int b = (int)(r / H);
+    float v = 0.f;
+    if (c < no) v = g[((((long long)b * na + a) * H + h) * W + w) * no + c];
+    out[i] = __float2bfloat16(v);
+  }
+}
+
 }  // namespace
 }  // namespace y5obb
 
@@ -414,6 +533,64 @@ int y5obb_nhwc_to_nchw(const void* src, int64_t src_pix_stride, void* dst_nchw, 
   dim3 grid((unsigned)((hw + 63) / 64), (unsigned)((C + 63) / 64), (unsigned)B);
   k_nhwc_to_nchw<<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<const __nv_bfloat16*>(src), src_pix_stride,
                                                          static_cast<__nv_bfloat16*>(dst_nchw), C, hw, B, phase_w);
+  Y5_LAUNCH_CHECK();
+  return Y5OBB_OK;
+}
+
+
+int y5obb_upsample2x_bwd(const void* gsrc, int64_t src_pix_stride, void* gdst, int64_t dst_pix_stride, int64_t npix_dst,
+                         int C, int W_dst, int accumulate, void* stream) {
+  if (!gsrc || !gdst || npix_dst <= 0 || C <= 0 || (C & 7) || W_dst <= 0 || (src_pix_stride & 7) || (dst_pix_stride & 7))
+    return Y5OBB_EINVAL;
+  const long long total = npix_dst * (C / 8);
+  const int grid = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 16);
+  k_upsample2x_bwd<<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<const __nv_bfloat16*>(gsrc), src_pix_stride,
+                                                           static_cast<__nv_bfloat16*>(gdst), dst_pix_stride, npix_dst, C,
+                                                           W_dst, accumulate);
+  Y5_LAUNCH_CHECK();
+  return Y5OBB_OK;
+}
+
+int y5obb_zero_stuff2x(const void* src, int64_t src_pix_stride, void* dst, int64_t dst_pix_stride, int64_t npix_src, int C,
+                       int W_src, void* stream) {
+  if (!src || !dst || npix_src <= 0 || C <= 0 || (C & 7) || W_src <= 0 || (src_pix_stride & 7) || (dst_pix_stride & 7))
+    return Y5OBB_EINVAL;
+  const long long total = npix_src * (C / 8);
+  const int grid = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 16);
+  k_zero_stuff2x<<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<const __nv_bfloat16*>(src), src_pix_stride,
+                                                         static_cast<__nv_bfloat16*>(dst), dst_pix_stride, npix_src, C, W_src);
+  Y5_LAUNCH_CHECK();
+  return Y5OBB_OK;
+}
+
+int y5obb_maxpool5_bwd(const void* x_in, int64_t in_pix_stride, const float* gout_f32, const void* gout_bf16,
+                       int64_t gout_pix_stride, float* gin_f32, int B, int H, int W, int C, void* stream) {
+  if (!x_in || !gin_f32 || (!gout_f32 && !gout_bf16) || B <= 0 || H <= 0 || W <= 0 || C <= 0) return Y5OBB_EINVAL;
+  const long long total = (long long)B * H * W * C;
+  const int grid = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 16);
+  k_maxpool5_bwd<<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<const __nv_bfloat16*>(x_in), in_pix_stride, gout_f32,
+                                                         static_cast<const __nv_bfloat16*>(gout_bf16), gout_pix_stride,
+                                                         gin_f32, B, H, W, C);
+  Y5_LAUNCH_CHECK();
+  return Y5OBB_OK;
+}
+
+int y5obb_add_f32_to_bf16(const float* src, void* dst, int64_t dst_pix_stride, int64_t npix, int C, int accumulate,
+                          void* stream) {
+  if (!src || !dst || npix <= 0 || C <= 0) return Y5OBB_EINVAL;
+  const long long total = npix * C;
+  const int grid = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 16);
+  k_add_f32_to_bf16<<<grid, 256, 0, (cudaStream_t)stream>>>(src, static_cast<__nv_bfloat16*>(dst), dst_pix_stride, npix, C,
+                                                            accumulate);
+  Y5_LAUNCH_CHECK();
+  return Y5OBB_OK;
+}
+
+int y5obb_detect_grad_pack(const float* g, void* out_nhwc, int B, int na, int H, int W, int no, int bn, void* stream) {
+  if (!g || !out_nhwc || B <= 0 || na <= 0 || H <= 0 || W <= 0 || no <= 0 || bn < no) return Y5OBB_EINVAL;
+  const long long total = (long long)B * H * W * na * bn;
+  const int grid = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 16);
+  k_detect_grad_pack<<<grid, 256, 0, (cudaStream_t)stream>>>(g, static_cast<__nv_bfloat16*>(out_nhwc), B, na, H, W, no, bn);
   Y5_LAUNCH_CHECK();
   return Y5OBB_OK;
 }
