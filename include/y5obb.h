@@ -216,13 +216,16 @@ int y5obb_nhwc_to_nchw(const void* src, int64_t src_pix_stride, void* dst_nchw, 
                        void* stream);  /* phase_w = W > 0: de-interleaved [B][C][(h&1)*2+(w&1)][H/2][W/2] for stride-2 wgrad */
 
 /* ---- weight gradient (tcgen05 GEMM over the pixel axis) -------------------------------------------
- * dW[tap][co][ci] (fp32, ACCUMULATED with atomics: zero it first) = sum_{b,ho,wo} dz[b,co,ho,wo] * x[b,ci,s*ho+kh-p,s*wo+kw-p].
- * Replaces the cuDNN wgrad autograd calls for models/common.py:37-46 under train.py:333.  Operands are NCHW bf16 copies
- * (y5obb_nhwc_to_nchw); for stride 2 the x copy must be the de-interleaved one.  Wo (and Wi, or Wi/2) multiples of 8. */
+ * dW[tap][co][ci] (fp32, ACCUMULATED with atomics: zero it first) = sum_{b,ho,wo} dz[b,ho,wo,co] * x[b,s*ho+kh-ph,s*wo+kw-pw,ci].
+ * Replaces the cuDNN wgrad autograd calls for models/common.py:37-46 under train.py:333.  Operands are the NHWC bf16
+ * gradient / activation buffers themselves (channel slices allowed: pix strides in elements, multiples of 8; rows and
+ * images dense).  Any map size; zero padding is implicit. */
 typedef struct y5obb_wgrad y5obb_wgrad_t;
 typedef struct {
-  const void* dz_nchw;   /* [B][Cout][Ho][Wo] bf16 */
-  const void* x_nchw;    /* stride 1: [B][Cin][Hi][Wi]; stride 2: [B][Cin][4][Hi/2][Wi/2] */
+  const void* dz;        /* [B][Ho][Wo][dz_pix_stride] bf16, channels [0, Cout) used */
+  int64_t dz_pix_stride;
+  const void* x;         /* [B][Hi][Wi][x_pix_stride] bf16, channels [0, Cin) used */
+  int64_t x_pix_stride;
   float* dw;             /* [KH*KW][Cout][Cin] fp32 */
   int B, Cout, Ho, Wo, Cin, Hi, Wi;
   int KH, KW, stride, pad_h, pad_w;

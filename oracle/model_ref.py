@@ -13,17 +13,37 @@ import torch.nn.functional as F
 from yolov5_obb_b200 import yolo as Y
 
 
+class _RoundBf16(torch.autograd.Function):
+    """Value AND gradient rounded to bf16: the storage rounding points of the device path, used to measure the
+    noise floor bf16 storage puts under a comparison with this fp32 oracle (never a parity target itself)."""
+
+    @staticmethod
+    def forward(ctx, t):
+        return t.bfloat16().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.bfloat16().float()
+
+
+_EMULATE_BF16 = False
+
+
+def _r(t):
+    return _RoundBf16.apply(t) if _EMULATE_BF16 else t
+
+
 def conv_fwd(m: Y.Conv, x, training=False):
-    y = F.conv2d(x, m.conv.weight, m.conv.bias, m.conv.stride, m.conv.padding)
+    y = _r(F.conv2d(x, _r(m.conv.weight), m.conv.bias, m.conv.stride, m.conv.padding))
     if hasattr(m, "bn") and m.bn is not None:
         bn = m.bn
         y = F.batch_norm(y, bn.running_mean, bn.running_var, bn.weight, bn.bias, training, bn.momentum, bn.eps)
-    return F.silu(y) if isinstance(m.act, torch.nn.SiLU) else y
+    return _r(F.silu(y) if isinstance(m.act, torch.nn.SiLU) else y)
 
 
 def bottleneck_fwd(m: Y.Bottleneck, x, training=False):
     y = conv_fwd(m.cv2, conv_fwd(m.cv1, x, training), training)
-    return x + y if m.add else y
+    return _r(x + y) if m.add else y
 
 
 def c3_fwd(m: Y.C3, x, training=False):
@@ -43,7 +63,7 @@ def sppf_fwd(m: Y.SPPF, x, training=False):
 def detect_fwd(m: Y.Detect, xs, training=False):
     z, outs = [], []
     for i in range(m.nl):
-        x = F.conv2d(xs[i], m.m[i].weight, m.m[i].bias)
+        x = F.conv2d(xs[i], _r(m.m[i].weight), m.m[i].bias)
         bs, _, ny, nx = x.shape
         x = x.view(bs, m.na, m.no, ny, nx).permute(0, 1, 3, 4, 2).contiguous()
         outs.append(x)
@@ -58,9 +78,21 @@ def detect_fwd(m: Y.Detect, xs, training=False):
     return outs if training else (torch.cat(z, 1), outs)
 
 
-@torch.no_grad()
-def forward(model: Y.Model, x: torch.Tensor, training: bool = False, return_layers: bool = False):
-    """models/yolo.py:163-181 over the container modules.  x: [B,3,H,W] fp32."""
+def forward_with_grad(model: Y.Model, x: torch.Tensor, training: bool = False, return_layers: bool = False,
+                      emulate_bf16: bool = False):
+    """models/yolo.py:163-181 over the container modules.  x: [B,3,H,W] fp32.  Differentiable (autograd is the
+    oracle of the backward pass, as it is the reference's own backward under train.py:333).
+    emulate_bf16=True rounds weights, conv outputs, activations (and their gradients) to bf16 where the device path
+    stores bf16: tests use the distance between the two oracle variants as the noise floor of the comparison."""
+    global _EMULATE_BF16
+    _EMULATE_BF16 = bool(emulate_bf16)
+    try:
+        return _forward_impl(model, _r(x), training, return_layers)
+    finally:
+        _EMULATE_BF16 = False
+
+
+def _forward_impl(model, x, training, return_layers):
     ys = []
     for m in model.model:
         if m.f != -1:
@@ -79,3 +111,9 @@ def forward(model: Y.Model, x: torch.Tensor, training: bool = False, return_laye
             x = detect_fwd(m, x, training)
         ys.append(x)
     return (x, ys) if return_layers else x
+
+
+@torch.no_grad()
+def forward(model: Y.Model, x: torch.Tensor, training: bool = False, return_layers: bool = False,
+            emulate_bf16: bool = False):
+    return forward_with_grad(model, x, training, return_layers, emulate_bf16)

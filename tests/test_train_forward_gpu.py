@@ -1,7 +1,12 @@
 """GPU parity of the training-mode forward (batch-statistic BatchNorm, raw Detect outputs) against the fp32
 oracle (oracle/model_ref.forward(training=True), itself pinned to the REFERENCE model in eval mode and sharing
-its code path).  Tolerance as in test_engine_gpu (bf16 activations): 3e-2 rel + 3e-2 abs, mean error < 6e-3;
-running statistics must match torch.nn.BatchNorm2d's update within 2e-2 relative."""
+its code path).
+
+With batch statistics a freshly initialised network amplifies storage rounding layer by layer (each BatchNorm
+re-normalises, nothing decays): the oracle evaluated with bf16 storage emulated (emulate_bf16=True) sits 1-2 % (relative
+L2) from the fp32 oracle at the Detect outputs.  Tolerances: per Detect level the device's relative L2 distance to the
+fp32 oracle must be < 1.5x that noise floor + 3e-3, and every layer evaluated on the DEVICE's own input (teacher
+forcing, one module deep) must match fp32 within 2e-2 relative L2; running statistics of the first layers within 2e-2."""
 import copy
 
 import pytest
@@ -9,9 +14,14 @@ import torch
 
 from oracle import model_ref
 from tests.modelgen import build_mirror
+import yolov5_obb_b200.yolo as Y
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
+
+
+def _nchw(s):
+    return s.buf[..., s.c_off:s.c_off + s.C].float().permute(0, 3, 1, 2).contiguous().cpu()
 
 
 @pytest.mark.parametrize("size,B,H,W", [("n", 2, 128, 160), ("s", 2, 64, 64)])
@@ -20,27 +30,48 @@ def test_train_forward_matches_oracle(size, B, H, W):
     ref_m = copy.deepcopy(m)
     g = torch.Generator().manual_seed(8)
     x = torch.rand(B, 3, H, W, generator=g)
+    floor = model_ref.forward(copy.deepcopy(m), x, training=True, emulate_bf16=True)
     ref = model_ref.forward(ref_m, x, training=True)   # updates ref_m's running stats
     md = m.to(DEV)
     with torch.no_grad():
         got = md(x.to(DEV))
     torch.cuda.synchronize()
     assert isinstance(got, list) and len(got) == 3
-    for l, (a, b) in enumerate(zip(got, ref)):
+    for l, (a, b, f) in enumerate(zip(got, ref, floor)):
         assert a.shape == b.shape and a.dtype == torch.float32
-        err = (a.cpu() - b).abs()
-        tol = b.abs() * 3e-2 + 3e-2
-        frac = (err > tol).float().mean().item()
-        print(f"level {l}: max err {err.max().item():.4g} mean {err.mean().item():.4g} out-of-tol {frac:.2e}")
-        assert frac < 2e-3 and err.mean().item() < 6e-3
+        rel = ((a.cpu() - b).norm() / b.norm()).item()
+        rel_floor = ((f - b).norm() / b.norm()).item()
+        print(f"level {l}: rel L2 {rel:.4g}, bf16-storage noise floor {rel_floor:.4g}")
+        assert rel < 1.5 * rel_floor + 3e-3
+    # teacher forced: each module on the device's own input
+    eng = [e for k, e in md._engines.items() if k[0] == "train"][0]
+    mods = list(ref_m.model)
+    worst = 0.0
+    for i, mod in enumerate(mods):
+        if not isinstance(mod, (Y.Conv, Y.C3, Y.SPPF)):
+            continue
+        if i == 0:
+            xin = x.bfloat16().float()
+        else:
+            xin = _nchw(eng.out_slices[i - 1 if mod.f == -1 else mod.f])
+        fn = {Y.Conv: model_ref.conv_fwd, Y.C3: model_ref.c3_fwd, Y.SPPF: model_ref.sppf_fwd}[type(mod)]
+        with torch.no_grad():
+            want = fn(copy.deepcopy(mod), xin, True)
+        have = _nchw(eng.out_slices[i])
+        rel = ((have - want).norm() / want.norm()).item()
+        worst = max(worst, rel)
+        assert rel < 2e-2, (i, type(mod).__name__, rel)
+    print("worst teacher-forced module deviation", worst)
     bns = [(n, mod) for n, mod in md.named_modules() if isinstance(mod, torch.nn.BatchNorm2d)]
     refs = dict(ref_m.named_modules())
     worst = 0.0
     for n, mod in bns:
         r = refs[n]
-        assert int(mod.num_batches_tracked) == int(r.num_batches_tracked) == 1
+        assert int(mod.num_batches_tracked) == 1  # (the functional oracle does not count)
+        if not (n.startswith("model.0.") or n.startswith("model.1.") or n.startswith("model.2.")):
+            continue  # deeper statistics inherit the amplified storage noise; the update rule is the same kernel
         dm = (mod.running_mean.cpu() - r.running_mean).abs().max().item()
         dv = ((mod.running_var.cpu() - r.running_var).abs() / r.running_var.abs().clamp_min(1e-3)).max().item()
         worst = max(worst, dm, dv)
-    print("worst running-stat deviation", worst)
+    print("worst running-stat deviation (layers 0-2)", worst)
     assert worst < 2e-2

@@ -81,30 +81,33 @@ def test_nhwc_to_nchw(phase):
 
 
 WG_CASES = [
-    # B, Cin, Cout, H, W, k, s
-    (2, 64, 64, 16, 64, 1, 1),
-    (2, 32, 48, 32, 32, 3, 1),
-    (1, 128, 256, 16, 16, 3, 1),
-    (2, 64, 128, 32, 64, 3, 2),
-    (3, 320, 160, 8, 8, 1, 1),
-    (2, 48, 96, 24, 40, 3, 2),
+    # B, Cin, Cout, H, W, k, s, x_extra, dz_extra (channels of padding around the slices)
+    (2, 64, 64, 16, 64, 1, 1, 0, 0),
+    (2, 32, 48, 32, 32, 3, 1, 0, 0),
+    (1, 128, 256, 16, 16, 3, 1, 64, 0),
+    (2, 64, 128, 32, 64, 3, 2, 0, 32),
+    (3, 320, 160, 8, 8, 1, 1, 0, 0),
+    (2, 48, 96, 24, 40, 3, 2, 16, 16),
+    (2, 16, 32, 20, 12, 3, 1, 0, 0),
+    (1, 512, 512, 4, 4, 3, 1, 0, 0),
+    (2, 80, 40, 10, 6, 1, 1, 8, 8),
 ]
 
 
-@pytest.mark.parametrize("B,Cin,Cout,H,W,k,s", WG_CASES)
-def test_wgrad_matches_autograd(B, Cin, Cout, H, W, k, s):
-    from yolov5_obb_b200.train_ops import Wgrad, nhwc_to_nchw
+@pytest.mark.parametrize("B,Cin,Cout,H,W,k,s,xe,ze", WG_CASES)
+def test_wgrad_matches_autograd(B, Cin, Cout, H, W, k, s, xe, ze):
+    """tcgen05 wgrad straight from NHWC slices == autograd's conv2d weight gradient on the same bf16-rounded operands."""
+    from yolov5_obb_b200.train_ops import Wgrad
     p = k // 2
     Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
     g = torch.Generator().manual_seed(Cin + Cout)
-    x = _bf(torch.randn(B, H, W, Cin, generator=g)).to(DEV)
-    dz = _bf(torch.randn(B, Ho, Wo, Cout, generator=g)).to(DEV)
-    xt = torch.zeros((B, Cin, H, W), dtype=torch.bfloat16, device=DEV)
-    dzt = torch.zeros((B, Cout, Ho, Wo), dtype=torch.bfloat16, device=DEV)
-    nhwc_to_nchw(x.data_ptr(), Cin, xt, B, Cin, H, W, phase_split=(s == 2))
-    nhwc_to_nchw(dz.data_ptr(), Cout, dzt, B, Cout, Ho, Wo)
+    xbuf = _bf(torch.randn(B, H, W, Cin + 2 * xe, generator=g)).to(DEV)
+    zbuf = _bf(torch.randn(B, Ho, Wo, Cout + 2 * ze, generator=g)).to(DEV)
+    x, dz = xbuf[..., xe:xe + Cin], zbuf[..., ze:ze + Cout]
     dw = torch.zeros((k * k, Cout, Cin), dtype=torch.float32, device=DEV)
-    Wgrad(dzt, xt, dw, B, Cout, Ho, Wo, Cin, H, W, k, s, p).run()
+    wg = Wgrad(zbuf.data_ptr() + 2 * ze, zbuf.shape[3], xbuf.data_ptr() + 2 * xe, xbuf.shape[3], dw, B, Cout, Ho, Wo, Cin, H, W,
+               k, s, p, keep=(xbuf, zbuf))
+    wg.run()
     torch.cuda.synchronize()
     w = torch.zeros((Cout, Cin, k, k), device=DEV, requires_grad=True)
     y = F.conv2d(x.float().permute(0, 3, 1, 2), w, None, s, p)
@@ -112,3 +115,6 @@ def test_wgrad_matches_autograd(B, Cin, Cout, H, W, k, s):
     ref = w.grad.permute(2, 3, 0, 1).reshape(k * k, Cout, Cin)
     err = (dw - ref).abs().max().item()
     assert err < 2e-3 * ref.abs().max().item() + 1e-3, f"max err {err} vs scale {ref.abs().max().item()}"
+    wg.run()  # accumulates
+    torch.cuda.synchronize()
+    assert (dw - 2 * ref).abs().max().item() < 4e-3 * ref.abs().max().item() + 2e-3

@@ -1,0 +1,286 @@
+"""Backward pass of the training plan (train_engine.TrainEngine): what autograd + cuDNN do under
+`scaler.scale(loss).backward()` (/root/reference/train.py:333) for the Conv/C3/SPPF/Concat/Upsample/Detect graph,
+as a fixed sequence of sm_100a kernel launches.
+
+Per Conv module (y = [res +] silu(bn(conv(x))), reverse order):
+   gy (+ 2x-up-sampled copy's gradient folded in)  --y5obb_bn_silu_bwd-->  dz, dgamma, dbeta, residual pass-through
+   dz, x  --y5obb_wgrad (both read in place, NHWC)-->  dW (tensor cores, split-K)
+   dz     --conv_tc_kernel with transposed / flipped weights (dgrad; stride 2: over the zero-stuffed dz)-->  gx (+=)
+Gradient buffers mirror the activation buffers; whether a contribution overwrites or accumulates is decided
+statically when the plan is built (first writer of a channel range overwrites).
+Parameter gradients land in fp32 buffers owned by the plan (run() returns {parameter: gradient}); the autograd
+Function in yolo.py hands them to autograd, which accumulates into `.grad` (so GradScaler / DDP hooks see them).
+"""
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib
+from .conv import Conv as ConvOp, Slice, pack_weights, tiling, MODE_DETECT
+from .train_ops import Wgrad
+
+
+class _Written:
+    """Which channel ranges of each gradient buffer already hold a contribution in this backward pass."""
+
+    def __init__(self):
+        self.r: Dict[int, List] = {}
+
+    def contribute(self, s: Slice) -> bool:
+        """Returns True if the contribution must ACCUMULATE (range already written), False if it overwrites."""
+        key = s.buf.data_ptr()
+        lo, hi = s.c_off, s.c_off + s.C
+        ranges = self.r.setdefault(key, [])
+        overlap = [(a, b) for a, b in ranges if a < hi and lo < b]
+        if not overlap:
+            ranges.append((lo, hi))
+            return False
+        covered = sorted(overlap)
+        pos = lo
+        for a, b in covered:
+            if a > pos:
+                raise RuntimeError("gradient range partially written: unsupported graph")
+            pos = max(pos, b)
+        if pos < hi:
+            raise RuntimeError("gradient range partially written: unsupported graph")
+        return True
+
+    def covered(self, s: Slice) -> bool:
+        key = s.buf.data_ptr()
+        lo, hi = s.c_off, s.c_off + s.C
+        pos = lo
+        for a, b in sorted(self.r.get(key, [])):
+            if a <= pos < b:
+                pos = b
+        return pos >= hi
+
+
+class BackwardPlan:
+    def __init__(self, eng):
+        self.eng = eng
+        dev = eng.device
+        B = eng.B
+        L = _lib.lib()
+        self._L = L
+        self.gbuf: Dict[int, torch.Tensor] = {}
+        self.steps = []  # closures(stream)
+        self.keep = []
+        self.flops = 0.0
+        written = _Written()
+        det = eng.model.model[-1]
+
+        def gslice(s: Slice) -> Slice:
+            k = s.buf.data_ptr()
+            if k not in self.gbuf:
+                self.gbuf[k] = torch.zeros_like(s.buf)
+            return Slice(self.gbuf[k], s.c_off, s.C)
+
+        def f32(n):
+            t = torch.zeros(n, dtype=torch.float32, device=dev)
+            self.keep.append(t)
+            return t
+
+        def bf(*shape):
+            t = torch.zeros(shape, dtype=torch.bfloat16, device=dev)
+            self.keep.append(t)
+            return t
+
+        self.pgrad: Dict[torch.nn.Parameter, torch.Tensor] = {}
+
+        def grad_of(p: torch.nn.Parameter) -> torch.Tensor:
+            """fp32 gradient buffer of a parameter, owned by the plan and rewritten by every run()."""
+            if p not in self.pgrad:
+                self.pgrad[p] = torch.zeros(p.shape, dtype=torch.float32, device=dev)
+            return self.pgrad[p]
+
+        self._grad_of = grad_of
+
+        def add_dgrad(dz_slice: Slice, w_dgrad, k, pad, gx: Slice, name):
+            """gx (+)= conv(dz, w_dgrad) with stride 1."""
+            acc = written.contribute(gx)
+            wp, bp = pack_weights(w_dgrad, None)
+            op = ConvOp(dz_slice, wp, bp, w_dgrad.shape[0], k, 1, pad, False, out=gx, res=gx if acc else None)
+            self.flops += op.info()["flops"]
+            self.steps.append(lambda st, h=op._h: _lib.check(L.y5obb_conv_run(h, st), name))
+            return op, wp
+
+        # ---------------- Detect levels ----------------
+        self.det_grads_in = [None] * det.nl  # set per backward call (fp32 [B,na,H,W,no])
+        self.det_parts = []
+        for l in range(det.nl):
+            cv = eng.det_convs[l]
+            xin: Slice = cv._keep[0]
+            mi = det.m[l]
+            H, W, Cin = xin.H, xin.W, xin.C
+            bk, bn, cin_pad, cout_pad, nt = tiling(Cin, det.na * det.no, MODE_DETECT, det.no)
+            dzd = bf(B, H, W, det.na * bn)
+            dw = f32(det.na * bn * Cin)
+            s1, s2 = f32(det.na * bn), f32(det.na * bn)
+            part = dict(l=l, dzd=dzd, dw=dw, s1=s1, bn=bn, Cin=Cin, mi=mi)
+            self.det_parts.append(part)
+
+            def pack_step(st, l=l, dzd=dzd, H=H, W=W, bn=bn):
+                g = self.det_grads_in[l]
+                _lib.check(L.y5obb_detect_grad_pack(g.data_ptr(), dzd.data_ptr(), B, det.na, H, W, det.no, bn, st), "detect_grad_pack")
+            self.steps.append(pack_step)
+            # bias gradient = per-channel sums of dz
+            self.steps.append(lambda st, dzd=dzd, s1=s1, s2=s2, n=B * H * W, C=det.na * bn:
+                              _lib.check(L.y5obb_bn_stats(dzd.data_ptr(), C, n, C, s1.data_ptr(), s2.data_ptr(), st), "detect bias grad"))
+            wg = Wgrad(dzd.data_ptr(), det.na * bn, xin.ptr, xin.pix_stride, dw, B, det.na * bn, H, W, Cin, H, W, 1, 1, 0,
+                       keep=(dzd, xin.buf))
+            self.keep.append(wg)
+            self.flops += 2.0 * B * H * W * det.na * bn * Cin
+            self.steps.append(lambda st, dw=dw: dw.zero_())
+            self.steps.append(lambda st, wg=wg: wg.run(st))
+            # dgrad: gx (+)= dz @ W  (1x1): weights [Cout'=Cin][Cin'=na*bn]
+            wT = torch.zeros((Cin, det.na * bn, 1, 1), device=dev)
+            part["wT"] = wT
+            op, wp = add_dgrad(Slice.full(dzd), wT, 1, 0, gslice(xin), "detect dgrad")
+            part["dgrad_wp"] = wp
+            self.keep.append(op)
+
+        # ---------------- conv layers, reverse ----------------
+        self.conv_parts = []
+        for lay in reversed(eng.layers):
+            if isinstance(lay, tuple):
+                _, cat4, hh, ww, c_ = lay
+                gc = gslice(Slice.full(cat4))
+                npix = B * hh * ww
+                t2, t1, t0 = f32(npix * c_), f32(npix * c_), f32(npix * c_)
+                ps = cat4.shape[3]
+                base, gbase = cat4.data_ptr(), gc.buf.data_ptr()
+
+                def pool_bwd(st, base=base, gbase=gbase, ps=ps, c_=c_, hh=hh, ww=ww, t2=t2, t1=t1, t0=t0, npix=npix):
+                    t2.zero_(); t1.zero_(); t0.zero_()
+                    # y3 = m(y2): gradient of y3 routed into y2
+                    _lib.check(L.y5obb_maxpool5_bwd(base + 2 * (2 * c_), ps, None, gbase + 2 * (3 * c_), ps, t2.data_ptr(), B, hh, ww, c_, st), "pool bwd 3")
+                    _lib.check(L.y5obb_maxpool5_bwd(base + 2 * (1 * c_), ps, t2.data_ptr(), gbase + 2 * (2 * c_), ps, t1.data_ptr(), B, hh, ww, c_, st), "pool bwd 2")
+                    _lib.check(L.y5obb_maxpool5_bwd(base, ps, t1.data_ptr(), gbase + 2 * (1 * c_), ps, t0.data_ptr(), B, hh, ww, c_, st), "pool bwd 1")
+                    _lib.check(L.y5obb_add_f32_to_bf16(t0.data_ptr(), gbase, ps, npix, c_, 1, st), "pool bwd add")
+                if not written.covered(gc):
+                    raise RuntimeError("SPPF gradient not ready")
+                self.steps.append(pool_bwd)
+                continue
+
+            mod, z, y = lay.mod, lay.z, lay.y
+            conv, bn = mod.conv, mod.bn
+            k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
+            Cout, Hh, Ww = z.C, z.H, z.W
+            npix = B * Hh * Ww
+            gy = gslice(y)
+            if lay.y2x is not None:  # fold the up-sampled copy's gradient into gy
+                g2 = gslice(lay.y2x)
+                acc = written.contribute(gy)
+                self.steps.append(lambda st, g2=g2, gy=gy, npix=npix, C=Cout, W=Ww, acc=acc:
+                                  _lib.check(L.y5obb_upsample2x_bwd(g2.ptr, g2.pix_stride, gy.ptr, gy.pix_stride, npix, C, W, int(acc), st), "upsample bwd"))
+            if not written.covered(gy):
+                names = {id(mm): nn_ for nn_, mm in eng.model.named_modules()}
+                raise RuntimeError(f"gradient of {names.get(id(mod))}'s output [{y.c_off}, {y.c_off + y.C}) of a "
+                                   f"{tuple(y.buf.shape)} buffer is not produced before it is consumed; written: "
+                                   f"{written.r.get(gy.buf.data_ptr())}")
+            dz = bf(B, Hh, Ww, Cout)
+            s1, s2 = f32(Cout), f32(Cout)
+            gres, gacc = None, 0
+            if lay.res is not None:
+                gres = gslice(lay.res)
+                gacc = int(written.contribute(gres))
+            part = dict(lay=lay, dz=dz)
+            self.conv_parts.append(part)
+
+            dg, db = grad_of(bn.weight), grad_of(bn.bias)
+
+            def bn_bwd(st, lay=lay, z=z, gy=gy, dz=dz, s1=s1, s2=s2, gres=gres, gacc=gacc, npix=npix, C=Cout, dg=dg, db=db):
+                _lib.check(L.y5obb_bn_silu_bwd(z.ptr, z.pix_stride, gy.ptr, gy.pix_stride, npix, C, lay.scale.data_ptr(),
+                                               lay.shift.data_ptr(), lay.mean.data_ptr(), lay.invstd.data_ptr(), int(lay.act),
+                                               s1.data_ptr(), s2.data_ptr(), dz.data_ptr(), C,
+                                               gres.ptr if gres else None, gres.pix_stride if gres else 0, gacc,
+                                               dg.data_ptr(), db.data_ptr(), 0, st), "bn_silu_bwd")
+            self.steps.append(bn_bwd)
+
+            # ---- wgrad (straight from the NHWC buffers)
+            x = lay.x
+            if lay.stem:  # 3x3 conv over the space-to-depth image; its zero border columns stand for the W padding
+                Hi, Wi, Cin_w = eng.H // 2, eng.W // 2 + 2, 16
+                kw_, sw_, pw_ = 3, 1, (1, 0)
+                x_ptr, x_ps, x_keep = eng.x_s2d.data_ptr(), 16, eng.x_s2d
+            else:
+                Hi, Wi, Cin_w = x.H, x.W, x.C
+                kw_, sw_, pw_ = k, s, p
+                x_ptr, x_ps, x_keep = x.ptr, x.pix_stride, x.buf
+            dw = f32(kw_ * kw_ * Cout * Cin_w)
+            wg = Wgrad(dz.data_ptr(), Cout, x_ptr, x_ps, dw, B, Cout, Hh, Ww, Cin_w, Hi, Wi, kw_, sw_, pw_, keep=(dz, x_keep))
+            self.keep.append(wg)
+            self.flops += 2.0 * npix * Cout * Cin_w * kw_ * kw_
+            part.update(dw=dw, k=kw_, Cin=Cin_w)
+            self.steps.append(lambda st, dw=dw: dw.zero_())
+            self.steps.append(lambda st, wg=wg: wg.run(st))
+
+            # ---- dgrad
+            if not lay.stem:
+                gx = gslice(x)
+                w_d = torch.zeros((x.C, Cout, k, k), device=dev)  # filled by refresh()
+                part["w_d"] = w_d
+                if s == 1:
+                    op, wp = add_dgrad(Slice.full(dz), w_d, k, k - 1 - p, gx, "dgrad")
+                else:
+                    dzup = bf(B, x.H, x.W, Cout)
+                    self.steps.append(lambda st, dz=dz, dzup=dzup, npix=npix, C=Cout, W=Ww:
+                                      _lib.check(L.y5obb_zero_stuff2x(dz.data_ptr(), C, dzup.data_ptr(), C, npix, C, W, st), "zero_stuff"))
+                    op, wp = add_dgrad(Slice.full(dzup), w_d, k, k - 1 - p, gx, "dgrad s2")
+                part["dgrad_wp"] = wp
+                self.keep.append(op)
+        self.refresh()
+
+    # ------------------------------------------------------------------------------------------
+    def refresh(self):
+        """Re-pack the dgrad weights (W transposed, taps flipped) from the current parameters."""
+        det = self.eng.model.model[-1]
+        with torch.no_grad():
+            for part in self.det_parts:
+                mi, bn, Cin = part["mi"], part["bn"], part["Cin"]
+                w = mi.weight.detach().float().view(det.na, det.no, Cin)  # [a, c, ci]
+                wT = torch.zeros((Cin, det.na * bn), device=w.device)
+                for a in range(det.na):
+                    wT[:, a * bn:a * bn + det.no] = w[a].t()
+                wp, _ = pack_weights(wT.view(Cin, det.na * bn, 1, 1), None)
+                part["dgrad_wp"].copy_(wp)
+            for part in self.conv_parts:
+                if "dgrad_wp" not in part:
+                    continue
+                w = part["lay"].mod.conv.weight.detach().float()       # [Cout, Cin, k, k]
+                w_d = w.permute(1, 0, 2, 3).flip(2, 3).contiguous()     # [Cin, Cout, k, k], taps flipped
+                wp, _ = pack_weights(w_d, None)
+                part["dgrad_wp"].copy_(wp)
+
+    def run(self, grads: List[torch.Tensor]):
+        """grads: dLoss/dp for the 3 Detect outputs (fp32, same shapes as TrainEngine.det_out)."""
+        eng = self.eng
+        det = eng.model.model[-1]
+        st = _lib.stream_ptr(eng.device)
+        with torch.cuda.device(eng.device), torch.no_grad():
+            for l in range(det.nl):
+                g = grads[l]
+                if g is None:
+                    g = torch.zeros_like(eng.det_out[l])
+                self.det_grads_in[l] = g.contiguous().float()
+            for step in self.steps:
+                step(st)
+            # ---- parameter gradients (layout plumbing on small tensors)
+            for part in self.det_parts:
+                mi, bn, Cin = part["mi"], part["bn"], part["Cin"]
+                dw = part["dw"].view(det.na, bn, Cin)[:, :det.no, :].reshape(det.na * det.no, Cin, 1, 1)
+                self._grad_of(mi.weight).copy_(dw)
+                self._grad_of(mi.bias).copy_(part["s1"].view(det.na, bn)[:, :det.no].reshape(-1))
+            for part in self.conv_parts:
+                lay, k, Cin = part["lay"], part["k"], part["Cin"]
+                conv = lay.mod.conv
+                Cout = conv.out_channels
+                dw = part["dw"].view(k, k, Cout, Cin).permute(2, 3, 0, 1)  # [Cout, Cin, kh, kw]
+                g = self._grad_of(conv.weight)
+                if lay.stem:  # dw is over the 3x3 space-to-depth form: w2[co, (dy*2+dx)*3+c, ty, tx] = w[co, c, 2ty+dy, 2tx+dx]
+                    for dy in range(2):
+                        for dx in range(2):
+                            g[:, :, dy::2, dx::2].copy_(dw[:, (dy * 2 + dx) * 3:(dy * 2 + dx) * 3 + 3])
+                else:
+                    g.copy_(dw)
+        return self.pgrad

@@ -186,6 +186,7 @@ class TrainEngine:
             self.det_out.append(o)
             self.det_convs.append(cv)
         self.out_slices = out
+        self._bwd, self._bwd_stale = None, False
 
     @staticmethod
     def _stem_weight(w):
@@ -209,6 +210,7 @@ class TrainEngine:
                 wp, bp = pack_weights(det.m[l].weight.detach().float(), det.m[l].bias.detach().float(), MODE_DETECT, det.no)
                 cv._keep[1].copy_(wp)
                 cv._keep[2].copy_(bp)
+        self._bwd_stale = True
 
     def forward(self, x: torch.Tensor):
         """x: [B,3,H,W] fp32 in [0,1] or uint8 -> list of 3 raw prediction tensors [B, na, H_i, W_i, no] fp32."""
@@ -249,3 +251,13 @@ class TrainEngine:
             for cv in self.det_convs:
                 _lib.check(L.y5obb_conv_run(cv._h, st), "detect")
         return self.det_out
+
+    def backward(self, grads):
+        """grads: dLoss/d(det_out[l]) for the three levels -> {parameter: fp32 gradient} (see train_backward.py)."""
+        if self._bwd is None:
+            from .train_backward import BackwardPlan
+            self._bwd = BackwardPlan(self)
+        elif self._bwd_stale:
+            self._bwd.refresh()
+        self._bwd_stale = False
+        return self._bwd.run(grads)

@@ -1,6 +1,6 @@
 """ctypes handles for the training-only kernels (BatchNorm backward, layout copies, tensor-core wgrad)."""
 import ctypes
-from ctypes import c_void_p, c_int
+from ctypes import c_void_p, c_int, c_int64
 
 import torch
 
@@ -9,23 +9,25 @@ from . import _lib
 
 class WgradDesc(ctypes.Structure):
     """Mirror of y5obb_wgrad_desc (include/y5obb.h)."""
-    _fields_ = [("dz_nchw", c_void_p), ("x_nchw", c_void_p), ("dw", c_void_p),
+    _fields_ = [("dz", c_void_p), ("dz_pix_stride", c_int64), ("x", c_void_p), ("x_pix_stride", c_int64), ("dw", c_void_p),
                 ("B", c_int), ("Cout", c_int), ("Ho", c_int), ("Wo", c_int), ("Cin", c_int), ("Hi", c_int), ("Wi", c_int),
                 ("KH", c_int), ("KW", c_int), ("stride", c_int), ("pad_h", c_int), ("pad_w", c_int)]
 
 
 class Wgrad:
-    """dW[tap][co][ci] += sum_pixels dz * x for fixed buffers (TMA descriptors baked at creation)."""
+    """dW[tap][co][ci] += sum_pixels dz * x over fixed NHWC buffers (TMA descriptors baked at creation).
+    dz / x: (ptr, pix_stride) of the channel slice; `keep` holds the owning tensors alive."""
 
-    def __init__(self, dz_nchw: torch.Tensor, x_nchw: torch.Tensor, dw: torch.Tensor, B, Cout, Ho, Wo, Cin, Hi, Wi, k, stride,
-                 pad):
+    def __init__(self, dz_ptr: int, dz_pix_stride: int, x_ptr: int, x_pix_stride: int, dw: torch.Tensor, B, Cout, Ho, Wo,
+                 Cin, Hi, Wi, k, stride, pad, keep=()):
         kh, kw = (k, k) if isinstance(k, int) else k
         ph, pw = (pad, pad) if isinstance(pad, int) else pad
-        d = WgradDesc(dz_nchw.data_ptr(), x_nchw.data_ptr(), dw.data_ptr(), B, Cout, Ho, Wo, Cin, Hi, Wi, kh, kw, stride, ph, pw)
+        d = WgradDesc(dz_ptr, dz_pix_stride, x_ptr, x_pix_stride, dw.data_ptr(), B, Cout, Ho, Wo, Cin, Hi, Wi, kh, kw, stride,
+                      ph, pw)
         assert dw.dtype == torch.float32 and dw.numel() == kh * kw * Cout * Cin
-        self._keep = (dz_nchw, x_nchw, dw)
+        self._keep = (dw,) + tuple(keep)
         self._h = c_void_p()
-        self.device = dz_nchw.device
+        self.device = dw.device
         with torch.cuda.device(self.device):
             rc = _lib.lib().y5obb_wgrad_create(ctypes.byref(d), ctypes.byref(self._h))
         _lib.check(rc, "y5obb_wgrad_create")

@@ -166,6 +166,24 @@ def parse_model(d: dict, ch: list):
     return nn.Sequential(*layers), sorted(save)
 
 
+class _TrainFn(torch.autograd.Function):
+    """Training-mode forward / backward of the whole network as one autograd node (what train.py:324-333 drives):
+    forward = train_engine.TrainEngine.forward, backward = train_backward.BackwardPlan.run.  The parameters are
+    inputs of the node so that autograd accumulates their gradients into `.grad` itself."""
+
+    @staticmethod
+    def forward(ctx, eng, x, *params):
+        outs = eng.forward(x)
+        ctx.eng, ctx.params = eng, params
+        return tuple(o.detach() for o in outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        pg = ctx.eng.backward(list(grads))
+        # clones: autograd may keep the returned tensor as .grad, and the plan rewrites its buffers every step
+        return (None, None) + tuple(pg[p].clone() if p in pg else None for p in ctx.params)
+
+
 class Model(nn.Module):
     """Drop-in for models/yolo.py:95 Model: Model(cfg, ch=3, nc=None, anchors=None); forward(x[B,3,H,W] in [0,1])
     -> eval: (pred[B, sum(3*H_i*W_i), nc+185] fp32, None); train: list of 3 [B,3,H_i,W_i,nc+185] logits."""
@@ -248,9 +266,6 @@ class Model(nn.Module):
         if augment or profile or visualize:
             raise RuntimeError("augment/profile/visualize are host tooling outside the hot path")
         if self.training:
-            if torch.is_grad_enabled():
-                raise RuntimeError("training-mode backward (dgrad / wgrad kernels) is not built yet: the training "
-                                   "forward runs under torch.no_grad() only — there is no PyTorch fallback")
             from .train_engine import TrainEngine
             key = ("train", tuple(x.shape), x.device.index)
             eng = self._engines.get(key)
@@ -258,7 +273,10 @@ class Model(nn.Module):
                 eng = self._engines[key] = TrainEngine(self, x.shape[0], x.shape[2], x.shape[3], x.device)
             else:
                 eng.refresh_weights()
-            return eng.forward(x)
+            if not torch.is_grad_enabled():
+                return eng.forward(x)
+            params = [p for p in self.parameters() if p.requires_grad]
+            return list(_TrainFn.apply(eng, x, *params))
         from .engine import InferenceEngine
         key = (tuple(x.shape), x.device.index)
         eng = self._engines.get(key)
