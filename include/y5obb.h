@@ -211,10 +211,6 @@ int y5obb_bn_silu_bwd(const void* z, int64_t z_pix_stride, const void* dy, int64
                       float* sum_du, float* sum_dux, void* dz, int64_t dz_pix_stride, void* gres,
                       int64_t gres_pix_stride, int gres_accumulate, float* dgamma, float* dbeta, int param_accumulate,
                       void* stream);
-/* NHWC channel slice -> dense NCHW bf16 [B, C, hw] (hw = H*W, multiple of 8): the K-major operand layout of wgrad */
-int y5obb_nhwc_to_nchw(const void* src, int64_t src_pix_stride, void* dst_nchw, int B, int C, int64_t hw, int phase_w,
-                       void* stream);  /* phase_w = W > 0: de-interleaved [B][C][(h&1)*2+(w&1)][H/2][W/2] for stride-2 wgrad */
-
 /* ---- weight gradient (tcgen05 GEMM over the pixel axis) -------------------------------------------
  * dW[tap][co][ci] (fp32, ACCUMULATED with atomics: zero it first) = sum_{b,ho,wo} dz[b,ho,wo,co] * x[b,s*ho+kh-ph,s*wo+kw-pw,ci].
  * Replaces the cuDNN wgrad autograd calls for models/common.py:37-46 under train.py:333.  Operands are the NHWC bf16
@@ -226,9 +222,13 @@ typedef struct {
   int64_t dz_pix_stride;
   const void* x;         /* [B][Hi][Wi][x_pix_stride] bf16, channels [0, Cin) used */
   int64_t x_pix_stride;
-  float* dw;             /* [KH*KW][Cout][Cin] fp32 */
+  float* dw;             /* fp32; element (tap, co, ci) at dw[tap*dw_tap_stride + co*dw_co_stride + ci*dw_ci_stride] */
+  int64_t dw_tap_stride, dw_co_stride, dw_ci_stride;  /* all 0 = dense [KH*KW][Cout][Cin]; (1, Cin*KH*KW, KH*KW) = the
+                                                         nn.Conv2d parameter layout [Cout][Cin][KH][KW] */
   int B, Cout, Ho, Wo, Cin, Hi, Wi;
   int KH, KW, stride, pad_h, pad_w;
+  int co_group, co_group_pad;  /* Detect: dz channels come in groups of co_group_pad of which the first co_group are
+                                  real (padding rows are skipped): dw row = (co / pad) * group + co % pad.  0 = off */
 } y5obb_wgrad_desc;
 int y5obb_wgrad_create(const y5obb_wgrad_desc* desc, y5obb_wgrad_t** out);
 int y5obb_wgrad_run(const y5obb_wgrad_t* w, void* stream);
@@ -250,6 +250,27 @@ int y5obb_maxpool5_bwd(const void* x_in, int64_t in_pix_stride, const float* gou
 int y5obb_add_f32_to_bf16(const float* src, void* dst, int64_t dst_pix_stride, int64_t npix, int C, int accumulate,
                           void* stream);
 int y5obb_detect_grad_pack(const float* g, void* out_nhwc, int B, int na, int H, int W, int no, int bn, void* stream);
+
+/* ---- weight re-packing (every optimiser step, train.py:336) ---------------------------------------
+ * fp32 nn.Conv2d parameters [Cout][Cin][KH][KW] -> the bf16 operand layouts the conv kernel's TMA descriptors point at,
+ * all layers in one launch.  dst is [taps][rows_pad][cols_pad] bf16 (DETECT_BIAS: fp32 [cols_pad]):
+ *   FWD           rows = Cout, cols = Cin                         (y5obb_conv_run forward)
+ *   DGRAD         rows = Cin,  cols = Cout, taps flipped          (data gradient = conv with transposed weights)
+ *   STEM          the 6x6/s2 stem as a 3x1 conv over the 48-channel space-to-depth window (KH=6,KW=6 in; 3 taps out)
+ *   DETECT        rows grouped per anchor: group_real real rows padded to group_pad (models/yolo.py:49-65)
+ *   DETECT_DGRAD  rows = Cin, cols grouped per anchor
+ *   DETECT_BIAS   fp32 bias, grouped per anchor */
+enum { Y5OBB_PACK_FWD = 0, Y5OBB_PACK_DGRAD = 1, Y5OBB_PACK_STEM = 2, Y5OBB_PACK_DETECT = 3, Y5OBB_PACK_DETECT_DGRAD = 4,
+       Y5OBB_PACK_DETECT_BIAS = 5 };
+typedef struct y5obb_pack_plan y5obb_pack_plan_t;
+typedef struct {
+  const float* src;
+  void* dst;
+  int kind, Cout, Cin, KH, KW, rows_pad, cols_pad, group_real, group_pad;
+} y5obb_pack_entry;
+int y5obb_pack_plan_create(const y5obb_pack_entry* entries, int n, y5obb_pack_plan_t** out);
+int y5obb_pack_plan_run(const y5obb_pack_plan_t* plan, void* stream);
+void y5obb_pack_plan_destroy(y5obb_pack_plan_t* plan);
 
 #ifdef __cplusplus
 }

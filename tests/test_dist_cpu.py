@@ -48,3 +48,54 @@ def test_two_rank_replica_path():
 def test_single_process_is_identity():
     from yolov5_obb_b200.dist_util import shard_range, max_over_ranks
     assert list(shard_range(5, 0, 1)) == [0, 1, 2, 3, 4] and max_over_ranks(3.5) == 3.5
+
+
+def _grad_worker(rank, ws, port, q):
+    """The training exchange step (train_step.TrainStep._allreduce_grads): one all-reduce of the flat gradient buffer
+    gives every rank the SUM of the per-rank gradients (DDP mean of a loss x WORLD_SIZE, train.py:328)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(ws))
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    from types import SimpleNamespace
+    from yolov5_obb_b200.train_step import TrainStep
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3), torch.nn.BatchNorm2d(4), torch.nn.Conv2d(4, 2, 1))
+    n = sum(p.numel() for p in net.parameters())
+    flat = torch.arange(n, dtype=torch.float32) * (rank + 1)      # rank r holds (r+1) * [0, 1, 2, ...]
+    o = 0
+    for p in net.parameters():
+        p.grad = flat[o:o + p.numel()].view(p.shape)
+        o += p.numel()
+    net._last_train_engine = SimpleNamespace(last_grad_flat=flat)
+    ts = TrainStep.__new__(TrainStep)
+    ts.model, ts.world = net, ws
+    calls = []
+    orig = dist.all_reduce
+    dist.all_reduce = lambda t, op=dist.ReduceOp.SUM: (calls.append(t.numel()), orig(t, op=op))[1]
+    ts._allreduce_grads()
+    flat_calls = list(calls)
+    # gradients that are NOT views of the flat buffer fall back to one call per tensor
+    for p in net.parameters():
+        p.grad = p.grad.clone()
+    calls.clear()
+    ts._allreduce_grads()
+    dist.all_reduce = orig
+    q.put((rank, flat.tolist(), flat_calls, len(calls), [p.grad.flatten()[:1].item() for p in net.parameters()][-1]))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_allreduce_is_one_call_and_a_sum():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    n = len(res[0][1])
+    for rank, flat, flat_calls, per_tensor_calls, last in res:
+        assert flat == [3.0 * i for i in range(n)]           # 1x + 2x
+        assert flat_calls == [n]                             # ONE collective over the whole buffer
+        assert per_tensor_calls == 6                         # fallback path: conv w/b, bn w/b, conv w/b

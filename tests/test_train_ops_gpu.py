@@ -63,23 +63,6 @@ def test_bn_silu_forward_backward(act, with_res):
         assert torch.equal(gres, dy)
 
 
-@pytest.mark.parametrize("phase", [False, True])
-def test_nhwc_to_nchw(phase):
-    from yolov5_obb_b200.train_ops import nhwc_to_nchw
-    B, H, W, Ctot, c_off, C = 2, 16, 24, 96, 16, 40
-    g = torch.Generator().manual_seed(1)
-    buf = _bf(torch.randn(B, H, W, Ctot, generator=g)).to(DEV)
-    dst = torch.zeros((B, C, H, W), dtype=torch.bfloat16, device=DEV)
-    nhwc_to_nchw(buf.data_ptr() + 2 * c_off, Ctot, dst, B, C, H, W, phase_split=phase)
-    torch.cuda.synchronize()
-    ref = buf[..., c_off:c_off + C].permute(0, 3, 1, 2).contiguous()
-    if phase:
-        ref = torch.stack([ref[:, :, a::2, b::2] for a in (0, 1) for b in (0, 1)], 2).contiguous()  # [B,C,4,H/2,W/2]
-        assert torch.equal(dst.view(B, C, 4, H // 2, W // 2), ref)
-    else:
-        assert torch.equal(dst, ref)
-
-
 WG_CASES = [
     # B, Cin, Cout, H, W, k, s, x_extra, dz_extra (channels of padding around the slices)
     (2, 64, 64, 16, 64, 1, 1, 0, 0),
@@ -118,3 +101,67 @@ def test_wgrad_matches_autograd(B, Cin, Cout, H, W, k, s, xe, ze):
     wg.run()  # accumulates
     torch.cuda.synchronize()
     assert (dw - 2 * ref).abs().max().item() < 4e-3 * ref.abs().max().item() + 2e-3
+
+
+def test_wgrad_param_layout_and_padded_groups():
+    """dW written straight in the nn.Conv2d layout [Cout][Cin][KH][KW]; Detect's padded per-anchor channel groups."""
+    from yolov5_obb_b200.train_ops import Wgrad
+    g = torch.Generator().manual_seed(77)
+    B, Cin, Cout, H, W, k = 2, 48, 80, 12, 20, 3
+    x = _bf(torch.randn(B, H, W, Cin, generator=g)).to(DEV)
+    dz = _bf(torch.randn(B, H, W, Cout, generator=g)).to(DEV)
+    dw = torch.zeros((Cout, Cin, k, k), dtype=torch.float32, device=DEV)
+    Wgrad(dz.data_ptr(), Cout, x.data_ptr(), Cin, dw, B, Cout, H, W, Cin, H, W, k, 1, 1, keep=(x, dz), param_layout=True).run()
+    w = torch.zeros((Cout, Cin, k, k), device=DEV, requires_grad=True)
+    F.conv2d(x.float().permute(0, 3, 1, 2), w, None, 1, 1).backward(dz.float().permute(0, 3, 1, 2))
+    torch.cuda.synchronize()
+    assert (dw - w.grad).abs().max().item() < 2e-3 * w.grad.abs().max().item() + 1e-3
+    # 3 anchors x 200 real channels padded to 208
+    na, no, bn, Cin = 3, 200, 208, 64
+    dzp = _bf(torch.randn(B, H, W, na * bn, generator=g)).to(DEV)
+    x = _bf(torch.randn(B, H, W, Cin, generator=g)).to(DEV)
+    dw = torch.zeros((na * no, Cin, 1, 1), dtype=torch.float32, device=DEV)
+    Wgrad(dzp.data_ptr(), na * bn, x.data_ptr(), Cin, dw, B, na * bn, H, W, Cin, H, W, 1, 1, 0, keep=(x, dzp), param_layout=True,
+          co_group=(no, bn)).run()
+    real = dzp.view(B, H, W, na, bn)[..., :no].reshape(B, H, W, na * no)
+    w = torch.zeros((na * no, Cin, 1, 1), device=DEV, requires_grad=True)
+    F.conv2d(x.float().permute(0, 3, 1, 2), w).backward(real.float().permute(0, 3, 1, 2))
+    torch.cuda.synchronize()
+    assert (dw - w.grad).abs().max().item() < 2e-3 * w.grad.abs().max().item() + 1e-3
+
+
+def test_pack_plan_matches_host_packing():
+    """One-launch device packing (csrc/pack_weights.cu) == conv.pack_weights on the host-side formulas, every kind."""
+    from yolov5_obb_b200.conv import pack_weights, MODE_DETECT, tiling
+    from yolov5_obb_b200.train_engine import TrainEngine
+    from yolov5_obb_b200.train_ops import (PackPlan, PACK_FWD, PACK_DGRAD, PACK_STEM, PACK_DETECT, PACK_DETECT_DGRAD,
+                                           PACK_DETECT_BIAS)
+    g = torch.Generator().manual_seed(3)
+    ent, want = [], []
+
+    def add(kind, src, ref, g_real=0, g_pad=0):
+        dst = torch.full_like(ref, 7.0)
+        ent.append((kind, src, dst, g_real, g_pad))
+        want.append(ref)
+
+    for cout, cin, k in [(48, 24, 3), (96, 40, 1), (256, 128, 3), (80, 16, 3)]:
+        w = torch.randn(cout, cin, k, k, generator=g).to(DEV)
+        add(PACK_FWD, w, pack_weights(w, None)[0])
+        add(PACK_DGRAD, w, pack_weights(w.permute(1, 0, 2, 3).flip(2, 3).contiguous(), None)[0])
+    w = torch.randn(48, 3, 6, 6, generator=g).to(DEV)
+    add(PACK_STEM, w, pack_weights(TrainEngine._stem_weight(w), None)[0])
+    na, no, cin = 3, 200, 192
+    w = torch.randn(na * no, cin, 1, 1, generator=g).to(DEV)
+    b = torch.randn(na * no, generator=g).to(DEV)
+    wp, bp = pack_weights(w, b, MODE_DETECT, no)
+    bn = tiling(cin, na * no, MODE_DETECT, no)[1]
+    add(PACK_DETECT, w, wp, no, bn)
+    add(PACK_DETECT_BIAS, b, bp, no, bn)
+    wT = torch.zeros((cin, na * bn), device=DEV)
+    for a in range(na):
+        wT[:, a * bn:a * bn + no] = w.view(na, no, cin)[a].t()
+    add(PACK_DETECT_DGRAD, w, pack_weights(wT.view(cin, na * bn, 1, 1), None)[0], no, bn)
+    PackPlan(ent, DEV).run()
+    torch.cuda.synchronize()
+    for (kind, src, dst, _, _), ref in zip(ent, want):
+        assert torch.equal(dst, ref), (kind, tuple(src.shape))

