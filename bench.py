@@ -16,6 +16,12 @@ val.py:378-383).  Metric: images/s.
   cpu_baseline   the oracle port (fp32 torch restatement of the reference's eager CPU path + the reference's
              own CPU NMS kernel from oracle/_ref when present) on the host cores, bounded sample
 
+  train      the train-step leg of the metric ("train+infer"): yolov5m-OBB, 8 tiles of 1024x1024 per GPU (configs[2]'s per-GPU
+             share), one optimisation step = forward (batch-stat BN) + ComputeLoss + backward + [NCCL all-reduce of the
+             flat gradient, N>1] + SGD-Nesterov + EMA; device-timed value, e2e with H2D of the uint8 batch + targets and
+             D2H of the loss, achieved fraction of the tensor peak on the algorithmic 3x-forward FLOPs, and the CPU
+             restatement of train.py --device cpu beside it
+
 --impl reference runs that CPU arm alone (rank 0 only under torchrun).  N>1 = independent replicas, one
 b16 batch per GPU (the path shards by image batch, no data-path collective): weak scaling.
 """
@@ -32,6 +38,8 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 MODEL, BATCH, IMG, NC = "s", 16, 1024, 15
+TRAIN_MODEL, TRAIN_BATCH, TRAIN_TARGETS_PER_IMG = "m", 8, 24   # BASELINE configs[2]: yolov5m, b64 over 8 GPUs = 8 img / GPU
+TRAIN_GFLOP_PER_IMG = {"n": 3 * 12.70, "s": 3 * 44.60, "m": 384.0, "l": 3 * 284.09, "x": 1592.3}  # fprop+dgrad+wgrad
 CONF, IOU, MAX_DET = 0.25, 0.45, 1500
 FWD_GFLOP_PER_IMG = 44.60  # BASELINE.md §2 (conv-only forward, yolov5s @1024, nc=15)
 
@@ -45,6 +53,10 @@ def parse():
     ap.add_argument("--model", default=MODEL)
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the train-step leg (the `train` object of the JSON line)")
+    ap.add_argument("--train-model", default=TRAIN_MODEL)
+    ap.add_argument("--train-batch", type=int, default=TRAIN_BATCH)
+    ap.add_argument("--train-steps", type=int, default=10)
     return ap.parse_args()
 
 
@@ -186,6 +198,114 @@ def workload_config(args):
 
 
 # ------------------------------------------------------------------------------------------------
+# train-step leg (BASELINE metric "train+infer"; configs[2] per-GPU share: yolov5m, 8 tiles of 1024x1024 per GPU)
+# ------------------------------------------------------------------------------------------------
+def train_inputs(batch, rank):
+    import torch
+    from tests.lossgen import synth_targets
+    imgs = synth_batch(batch, seed=100 + rank)
+    tg = torch.from_numpy(synth_targets(batch, TRAIN_TARGETS_PER_IMG * batch, IMG, nc=NC, seed=200 + rank))
+    return imgs, tg
+
+
+def cpu_train_arm(size, budget_s=30.0):
+    """The reference's CPU training path (train.py --device cpu: eager fp32 torch forward, ComputeLoss, autograd
+    backward, SGD-Nesterov step) restated by the oracle, 1 tile per step on the host cores — a bounded sample."""
+    import torch
+    from oracle import model_ref, loss_ref
+    from tests.modelgen import build_mirror
+    m = build_mirror(size, nc=NC, seed=0).train()
+    det = m.model[-1]
+    hyp = loss_ref.scaled_hyp(loss_ref.DEFAULT_HYP, det.nl, NC, IMG)
+    opt = torch.optim.SGD(m.parameters(), lr=0.01, momentum=0.937, nesterov=True)
+    imgs, tg = train_inputs(1, 0)
+    cores = torch.get_num_threads()
+
+    def step():
+        with torch.enable_grad():
+            pred = model_ref.forward_with_grad(m, imgs.float() / 255, training=True)
+            loss, _ = loss_ref.compute_loss(pred, tg, det.anchors, det.stride, hyp, NC)
+            loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+
+    t0 = time.perf_counter()
+    step()
+    per = time.perf_counter() - t0
+    n = max(1, min(5, int(budget_s / max(per, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(n):
+        step()
+    dt = (time.perf_counter() - t0) / n
+    return dict(value=1.0 / dt, unit="images/s", cores=cores, kind="port", ms_per_step=dt * 1e3,
+                sample=f"yolov5{size} fp32 eager-torch restatement of train.py --device cpu (forward, ComputeLoss, autograd "
+                       f"backward, SGD-Nesterov), {n} steps of 1 tile 1024x1024, {cores} threads")
+
+
+def run_train_leg(args, dev, world, rank, dist, pk):
+    """One optimisation step per 'step': forward, ComputeLoss, backward, [NCCL all-reduce of the flat gradient],
+    SGD-Nesterov + EMA (yolov5_obb_b200.train_step.TrainStep = the loop body of train.py:296-342)."""
+    import torch
+    from tests.modelgen import build_mirror
+    from yolov5_obb_b200.train_step import TrainStep
+    size, TB = args.train_model, args.train_batch
+    m = build_mirror(size, nc=NC, seed=0).train().to(dev)
+    ts = TrainStep(m, batch_size=TB * world, imgsz=IMG)
+    imgs_h, tg_h = train_inputs(TB, rank)
+    imgs_h, tg_h = imgs_h.pin_memory(), tg_h.pin_memory()
+    imgs_d, tg_d = imgs_h.to(dev), tg_h.to(dev)
+    steps = max(1, args.train_steps)
+    losses = []
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run(n, e2e):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            if e2e:  # inputs from pinned host memory, the step's loss read back
+                imgs_d.copy_(imgs_h, non_blocking=True)
+                tg_d.copy_(tg_h, non_blocking=True)
+            loss, items = ts.step(imgs_d, tg_d)
+            if e2e:
+                losses.append(float(loss.cpu()))
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / n
+
+    run(max(3, min(args.warmup, 5)), False)
+    ms_dev = run(steps, False)
+    ms_e2e = run(steps, True)
+    value = world * TB / (ms_dev / 1e3)
+    flops_img = TRAIN_GFLOP_PER_IMG[size] * 1e9
+    out = {
+        "workload": f"yolov5{size}-OBB train step, {TB} tiles 1024x1024 per GPU (BASELINE configs[2] per-GPU share): Model.forward "
+                    f"(batch-stat BN) + ComputeLoss + backward + {'NCCL all-reduce of the flat gradient + ' if world > 1 else ''}"
+                    "SGD-Nesterov + EMA",
+        "value": value, "unit": "images/s", "ms_per_step": ms_dev, "steps": steps, "global_batch": TB * world,
+        "e2e": {"value": world * TB / (ms_e2e / 1e3), "unit": "images/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": int(imgs_h.numel() + tg_h.numel() * 4), "d2h_bytes_per_step": 4},
+        "tensor": {"algorithmic_TFLOP_per_step_per_gpu": flops_img * TB / 1e12,
+                   "achieved_TFLOPs_per_gpu": flops_img * TB / (ms_dev / 1e3) / 1e12, "peak": pk["tflops"],
+                   "frac": flops_img * TB / (ms_dev / 1e3) / 1e12 / pk["tflops"]},
+        "loss_first_last": [losses[0], losses[-1]] if losses else None,
+        "targets_per_step": int(tg_h.shape[0]), "dtype": "bf16 activations/gradients, fp32 accumulation and master weights",
+    }
+    del ts, m
+    torch.cuda.empty_cache()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
 def run_ours(args):
@@ -306,6 +426,14 @@ def run_ours(args):
             "hbm_view": {"algorithmic_GB_per_step": eng.hbm_bytes / 1e9,
                          "achieved_GBps": eng.hbm_bytes / (tot_conv_ms / 1e3) / 1e9, "peak_GBps": pk["hbm"]}}
 
+    # train-step leg (all ranks take part: the gradient all-reduce is the path's one exchange step)
+    train = None
+    if not args.no_train:
+        del pipe
+        model._engines.clear()
+        torch.cuda.empty_cache()
+        train = run_train_leg(args, dev, world, rank, dist, pk)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -326,6 +454,11 @@ def run_ours(args):
     if not args.no_cpu_baseline and world == 1:
         cb = cpu_arm(args.model, B, args.steps, args.warmup)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    if train is not None:
+        line["train"] = train
+        if not args.no_cpu_baseline and world == 1:
+            tb = cpu_train_arm(args.train_model)
+            train["cpu_baseline"] = {k: tb[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

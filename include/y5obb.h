@@ -190,12 +190,15 @@ int y5obb_gaussian_label(const double* angle_deg, float* csl_out, int64_t n, int
 /* ---- training-mode BatchNorm + SiLU (NHWC bf16) ------------------------------------------------
  * Conv.forward = act(bn(conv(x))) in train mode (models/common.py:45-46; BN eps 1e-3, momentum 0.03,
  * utils/torch_utils.py:160-162).  The conv runs raw (act = 0, zero bias) through y5obb_conv_*; then
- *   y5obb_bn_stats      per-channel sum / sum of squares over npix pixels (fp32, zeroed inside)
+ *   y5obb_bn_stats      per-channel sum / sum of squares over npix pixels (fp32; deterministic two-stage reduction:
+ *                       block partials in `scratch`, added in block order)
  *   y5obb_bn_finalize   scale = gamma / sqrt(var_biased + eps), shift = beta - mean * scale, mean / invstd saved
  *                       for backward, running statistics updated as torch.nn.BatchNorm2d does (unbiased var)
  *   y5obb_bn_silu_apply y = [res +] act(z * scale + shift) into a channel slice, optional 2x nearest copy (W = image
  *                       width in pixels, needed only for the up-sampled copy) */
-int y5obb_bn_stats(const void* z, int64_t z_pix_stride, int64_t npix, int C, float* sum, float* sumsq, void* stream);
+int64_t y5obb_bn_scratch_floats(int C);  /* scratch (fp32 elements) the two reductions below need for C channels */
+int y5obb_bn_stats(const void* z, int64_t z_pix_stride, int64_t npix, int C, float* sum, float* sumsq, float* scratch,
+                   int64_t scratch_floats, void* stream);
 int y5obb_bn_finalize(const float* sum, const float* sumsq, int64_t npix, int C, const float* gamma, const float* beta,
                       float eps, float momentum, float* running_mean, float* running_var, float* scale, float* shift,
                       float* mean_out, float* invstd_out, void* stream);
@@ -210,7 +213,7 @@ int y5obb_bn_silu_bwd(const void* z, int64_t z_pix_stride, const void* dy, int64
                       const float* scale, const float* shift, const float* mean, const float* invstd, int act,
                       float* sum_du, float* sum_dux, void* dz, int64_t dz_pix_stride, void* gres,
                       int64_t gres_pix_stride, int gres_accumulate, float* dgamma, float* dbeta, int param_accumulate,
-                      void* stream);
+                      float* scratch, int64_t scratch_floats, void* stream);
 /* ---- weight gradient (tcgen05 GEMM over the pixel axis) -------------------------------------------
  * dW[tap][co][ci] (fp32, ACCUMULATED with atomics: zero it first) = sum_{b,ho,wo} dz[b,ho,wo,co] * x[b,s*ho+kh-ph,s*wo+kw-pw,ci].
  * Replaces the cuDNN wgrad autograd calls for models/common.py:37-46 under train.py:333.  Operands are the NHWC bf16

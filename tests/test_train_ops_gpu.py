@@ -14,11 +14,12 @@ def _bf(t):
     return t.to(torch.bfloat16)
 
 
+@pytest.mark.parametrize("shape", [(2, 12, 16, 48), (3, 67, 50, 16), (2, 40, 64, 320)])
 @pytest.mark.parametrize("act,with_res", [(True, False), (True, True), (False, False)])
-def test_bn_silu_forward_backward(act, with_res):
+def test_bn_silu_forward_backward(act, with_res, shape):
     L = _lib.lib()
     st = _lib.stream_ptr(torch.device(DEV))
-    B, H, W, C = 2, 12, 16, 48
+    B, H, W, C = shape
     g = torch.Generator().manual_seed(3)
     z = _bf(torch.randn(B, H, W, C, generator=g) * 1.5 + 0.3).to(DEV)
     res = _bf(torch.randn(B, H, W, C, generator=g)).to(DEV) if with_res else None
@@ -30,7 +31,14 @@ def test_bn_silu_forward_backward(act, with_res):
     f32 = lambda: torch.empty(C, dtype=torch.float32, device=DEV)
     s1, s2, scale, shift, mean, invstd = f32(), f32(), f32(), f32(), f32(), f32()
     y = torch.zeros_like(z)
-    assert L.y5obb_bn_stats(z.data_ptr(), C, npix, C, s1.data_ptr(), s2.data_ptr(), st) == 0
+    scr = torch.empty(int(L.y5obb_bn_scratch_floats(C)), dtype=torch.float32, device=DEV)
+    assert L.y5obb_bn_stats(z.data_ptr(), C, npix, C, s1.data_ptr(), s2.data_ptr(), scr.data_ptr(), scr.numel(), st) == 0
+    s1b, s2b = f32(), f32()   # deterministic: a second pass gives the same bits
+    assert L.y5obb_bn_stats(z.data_ptr(), C, npix, C, s1b.data_ptr(), s2b.data_ptr(), scr.data_ptr(), scr.numel(), st) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(s1, s1b) and torch.equal(s2, s2b)
+    assert torch.allclose(s1, z.float().sum((0, 1, 2)), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(s2, (z.float() ** 2).sum((0, 1, 2)), rtol=1e-4, atol=1e-2)
     assert L.y5obb_bn_finalize(s1.data_ptr(), s2.data_ptr(), npix, C, gamma.data_ptr(), beta.data_ptr(), 1e-3, 0.03,
                                rm.data_ptr(), rv.data_ptr(), scale.data_ptr(), shift.data_ptr(), mean.data_ptr(),
                                invstd.data_ptr(), st) == 0
@@ -53,7 +61,8 @@ def test_bn_silu_forward_backward(act, with_res):
     dgam, dbet = f32(), f32()
     rc = L.y5obb_bn_silu_bwd(z.data_ptr(), C, dy.data_ptr(), C, npix, C, scale.data_ptr(), shift.data_ptr(),
                              mean.data_ptr(), invstd.data_ptr(), int(act), s1.data_ptr(), s2.data_ptr(), dz.data_ptr(), C,
-                             gres.data_ptr() if with_res else None, C, 0, dgam.data_ptr(), dbet.data_ptr(), 0, st)
+                             gres.data_ptr() if with_res else None, C, 0, dgam.data_ptr(), dbet.data_ptr(), 0,
+                             scr.data_ptr(), scr.numel(), st)
     assert rc == 0
     torch.cuda.synchronize()
     ref_dz = zr.grad.permute(0, 2, 3, 1)

@@ -51,9 +51,11 @@ def test_steps_reduce_the_loss_and_follow_sgd_nesterov_and_ema():
         if v.dtype.is_floating_point and not k.endswith("running_mean") and not k.endswith("running_var"):
             want = d * ema0[k] + (1 - d) * msd[k]
             assert torch.allclose(v, want, rtol=1e-5, atol=1e-7), k
-    for _ in range(7):
+    # A freshly initialised batch-norm network is chaotic (see test_train_backward_gpu): the first steps at lr0 wander,
+    # then the momentum-averaged direction takes over (measured: 4.78 -> 4.93 -> ... -> 4.56 after 16 steps).
+    for _ in range(27):
         l, items = ts.step(imgs, tg)
         losses.append(l.item())
-    print("losses", [f"{v:.4f}" for v in losses])
-    assert all(math.isfinite(v) for v in losses) and losses[-1] < losses[0]
+    print("losses", [f"{v:.3f}" for v in losses])
+    assert all(math.isfinite(v) for v in losses) and min(losses[-4:]) < losses[0] - 0.1
     assert items.shape == (4,) and torch.isfinite(items).all()

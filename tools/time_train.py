@@ -37,3 +37,27 @@ for it in range(warm + steps):
               f"{B / sum(d) * 1e3:.1f} img/s  loss {loss.item():.4f}", flush=True)
 eng = m._last_train_engine
 print("fwd flops %.3g  bwd flops %.3g  mem %.2f GB" % (eng.flops, eng._bwd.flops, torch.cuda.max_memory_allocated() / 2**30))
+
+# per-kernel-kind device times of one more step (events around every launch; serialises nothing but adds gaps)
+eng.prof = {}
+eng._bwd.prof = {}
+pred = m(imgs)
+loss, items = ts.compute_loss(pred, tg)
+loss.backward()
+torch.cuda.synchronize()
+for title, prof in (("forward", eng.prof), ("backward", eng._bwd.prof)):
+    tot = sum(sum(v) for v in prof.values())
+    print(title, f"{tot:.2f} ms:", "  ".join(f"{k} {sum(v):.2f} (x{len(v)})" for k, v in sorted(prof.items(), key=lambda kv: -sum(kv[1]))))
+# the ten slowest conv / wgrad / dgrad launches with their shapes
+convs = [l for l in eng.layers if not isinstance(l, tuple)]
+desc = lambda l: f"{l.x.C}->{l.z.C} k{l.mod.conv.kernel_size[0]} s{l.mod.conv.stride[0]} {l.z.H}x{l.z.W}"
+top = sorted(zip(eng.prof["conv"], convs), key=lambda t: -t[0])[:8]
+print("slowest fwd convs:", "; ".join(f"{t*1e3:.0f}us {desc(l)} ({l.conv.info()['flops']/t/1e9:.0f} TF/s)" for t, l in top))
+parts = eng._bwd.conv_parts
+wg = eng._bwd.prof["wgrad"][3:]   # first three are Detect levels
+top = sorted(zip(wg, parts), key=lambda t: -t[0])[:8]
+print("slowest wgrads:", "; ".join(f"{t*1e3:.0f}us {desc(p['lay'])} ({p['lay'].conv.info()['flops']/t/1e9:.0f} TF/s)" for t, p in top))
+dg = eng._bwd.prof["dgrad"][3:]
+dparts = [p for p in parts if "dgrad_wp" in p]
+top = sorted(zip(dg, dparts), key=lambda t: -t[0])[:8]
+print("slowest dgrads:", "; ".join(f"{t*1e3:.0f}us {desc(p['lay'])} ({p['lay'].conv.info()['flops']/t/1e9:.0f} TF/s)" for t, p in top))

@@ -275,7 +275,9 @@ int y5obb_wgrad_create(const y5obb_wgrad_desc* d, y5obb_wgrad_t** out) {
   k.b_chunks = (k.BN + 63) / 64;
   k.co_blks = (d->Cout + 127) / 128;
   const int items = d->KH * d->KW * k.co_blks * k.ci_blks;
-  k.ksplit = std::max(1, std::min(k.ksteps, (2 * sm_count() + items - 1) / items));
+  // split-K so that ~2 CTAs per SM exist, but never fewer than 16 pipeline steps per CTA: every split adds a
+  // 128 x BN fp32 atomic epilogue
+  k.ksplit = std::max(1, std::min(std::max(1, k.ksteps / 16), (2 * sm_count() + items - 1) / items));
   const uint32_t stage_bytes = (2u + (uint32_t)k.b_chunks) * WG_CHUNK;
   k.stages = (int)std::min<size_t>(WG_MAX_STAGES, WG_SMEM / stage_bytes);
   if (k.stages < 2) {

@@ -63,7 +63,12 @@ class BackwardPlan:
         L = _lib.lib()
         self._L = L
         self.gbuf: Dict[int, torch.Tensor] = {}
-        self.steps = []  # closures(stream)
+        self.steps = []  # (name, closure(stream))
+        self.prof = None  # set to {} to collect per-step-kind device times (ms) during run()
+
+        def add(tag, fn):
+            self.steps.append((tag, fn))
+
         self.keep = []
         self.flops = 0.0
         written = _Written()
@@ -107,7 +112,7 @@ class BackwardPlan:
             wp, bp = pack_weights(w_dgrad, None)
             op = ConvOp(dz_slice, wp, bp, w_dgrad.shape[0], k, 1, pad, False, out=gx, res=gx if acc else None)
             self.flops += op.info()["flops"]
-            self.steps.append(lambda st, h=op._h: _lib.check(L.y5obb_conv_run(h, st), name))
+            add("dgrad", lambda st, h=op._h: _lib.check(L.y5obb_conv_run(h, st), name))
             return op, wp
 
         # ---------------- Detect levels ----------------
@@ -127,15 +132,16 @@ class BackwardPlan:
             def pack_step(st, l=l, dzd=dzd, H=H, W=W, bn=bn):
                 g = self.det_grads_in[l]
                 _lib.check(L.y5obb_detect_grad_pack(g.data_ptr(), dzd.data_ptr(), B, det.na, H, W, det.no, bn, st), "detect_grad_pack")
-            self.steps.append(pack_step)
+            add("detect_pack", pack_step)
             # bias gradient = per-channel sums of dz
-            self.steps.append(lambda st, dzd=dzd, s1=s1, s2=s2, n=B * H * W, C=det.na * bn:
-                              _lib.check(L.y5obb_bn_stats(dzd.data_ptr(), C, n, C, s1.data_ptr(), s2.data_ptr(), st), "detect bias grad"))
+            add("detect_bias", lambda st, dzd=dzd, s1=s1, s2=s2, n=B * H * W, C=det.na * bn:
+                              _lib.check(L.y5obb_bn_stats(dzd.data_ptr(), C, n, C, s1.data_ptr(), s2.data_ptr(), eng.scratch.data_ptr(),
+                                                          eng.scratch.numel(), st), "detect bias grad"))
             wg = Wgrad(dzd.data_ptr(), det.na * bn, xin.ptr, xin.pix_stride, grad_of(mi.weight), B, det.na * bn, H, W, Cin, H, W,
                        1, 1, 0, keep=(dzd, xin.buf, self.flat), param_layout=True, co_group=(det.no, bn))
             self.keep.append(wg)
             self.flops += 2.0 * B * H * W * det.na * bn * Cin
-            self.steps.append(lambda st, wg=wg: wg.run(st))
+            add("wgrad", lambda st, wg=wg: wg.run(st))
             # dgrad: gx (+)= dz @ W  (1x1): weights [Cout'=Cin][Cin'=na*bn]
             wT = torch.zeros((Cin, det.na * bn, 1, 1), device=dev)
             part["wT"] = wT
@@ -163,7 +169,7 @@ class BackwardPlan:
                     _lib.check(L.y5obb_add_f32_to_bf16(t0.data_ptr(), gbase, ps, npix, c_, 1, st), "pool bwd add")
                 if not written.covered(gc):
                     raise RuntimeError("SPPF gradient not ready")
-                self.steps.append(pool_bwd)
+                add("pool_bwd", pool_bwd)
                 continue
 
             mod, z, y = lay.mod, lay.z, lay.y
@@ -175,7 +181,7 @@ class BackwardPlan:
             if lay.y2x is not None:  # fold the up-sampled copy's gradient into gy
                 g2 = gslice(lay.y2x)
                 acc = written.contribute(gy)
-                self.steps.append(lambda st, g2=g2, gy=gy, npix=npix, C=Cout, W=Ww, acc=acc:
+                add("upsample_bwd", lambda st, g2=g2, gy=gy, npix=npix, C=Cout, W=Ww, acc=acc:
                                   _lib.check(L.y5obb_upsample2x_bwd(g2.ptr, g2.pix_stride, gy.ptr, gy.pix_stride, npix, C, W, int(acc), st), "upsample bwd"))
             if not written.covered(gy):
                 names = {id(mm): nn_ for nn_, mm in eng.model.named_modules()}
@@ -198,8 +204,9 @@ class BackwardPlan:
                                                lay.shift.data_ptr(), lay.mean.data_ptr(), lay.invstd.data_ptr(), int(lay.act),
                                                s1.data_ptr(), s2.data_ptr(), dz.data_ptr(), C,
                                                gres.ptr if gres else None, gres.pix_stride if gres else 0, gacc,
-                                               dg.data_ptr(), db.data_ptr(), 0, st), "bn_silu_bwd")
-            self.steps.append(bn_bwd)
+                                               dg.data_ptr(), db.data_ptr(), 0, eng.scratch.data_ptr(), eng.scratch.numel(), st),
+                           "bn_silu_bwd")
+            add("bn_bwd", bn_bwd)
 
             # ---- wgrad (straight from the NHWC buffers)
             x = lay.x
@@ -214,14 +221,14 @@ class BackwardPlan:
             if lay.stem:  # gradient over the space-to-depth form, re-mapped to [Cout,3,6,6] at the end of run()
                 dw = f32(9 * Cout * 16)
                 part["stem_dw"] = dw
-                self.steps.append(lambda st, dw=dw: dw.zero_())
+                add("zero", lambda st, dw=dw: dw.zero_())
                 wg = Wgrad(dz.data_ptr(), Cout, x_ptr, x_ps, dw, B, Cout, Hh, Ww, Cin_w, Hi, Wi, kw_, sw_, pw_, keep=(dz, x_keep))
             else:
                 wg = Wgrad(dz.data_ptr(), Cout, x_ptr, x_ps, grad_of(conv.weight), B, Cout, Hh, Ww, Cin_w, Hi, Wi, kw_, sw_, pw_,
                            keep=(dz, x_keep, self.flat), param_layout=True)
             self.keep.append(wg)
             self.flops += 2.0 * npix * Cout * Cin_w * kw_ * kw_
-            self.steps.append(lambda st, wg=wg: wg.run(st))
+            add("wgrad", lambda st, wg=wg: wg.run(st))
 
             # ---- dgrad
             if not lay.stem:
@@ -232,7 +239,7 @@ class BackwardPlan:
                     op, wp = add_dgrad(Slice.full(dz), w_d, k, k - 1 - p, gx, "dgrad")
                 else:
                     dzup = bf(B, x.H, x.W, Cout)
-                    self.steps.append(lambda st, dz=dz, dzup=dzup, npix=npix, C=Cout, W=Ww:
+                    add("zero_stuff", lambda st, dz=dz, dzup=dzup, npix=npix, C=Cout, W=Ww:
                                       _lib.check(L.y5obb_zero_stuff2x(dz.data_ptr(), C, dzup.data_ptr(), C, npix, C, W, st), "zero_stuff"))
                     op, wp = add_dgrad(Slice.full(dzup), w_d, k, k - 1 - p, gx, "dgrad s2")
                 part["dgrad_wp"] = wp
@@ -266,8 +273,21 @@ class BackwardPlan:
                     g = torch.zeros_like(eng.det_out[l])
                 self.det_grads_in[l] = g.contiguous().float()
             self.flat.zero_()
-            for step in self.steps:
-                step(st)
+            if self.prof is None:
+                for _, step in self.steps:
+                    step(st)
+            else:  # debug: CUDA events around every step, summed per kind (and listed per wgrad / dgrad layer)
+                evs = []
+                for tag, step in self.steps:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    step(st)
+                    e1.record()
+                    evs.append((tag, e0, e1))
+                torch.cuda.synchronize()
+                self.prof = {}
+                for tag, e0, e1 in evs:
+                    self.prof.setdefault(tag, []).append(e0.elapsed_time(e1))
             # ---- the few gradients that need a re-mapping (tiny tensors)
             for part in self.det_parts:
                 mi, bn = part["mi"], part["bn"]

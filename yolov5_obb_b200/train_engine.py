@@ -187,6 +187,9 @@ class TrainEngine:
             self.det_convs.append(cv)
         self.out_slices = out
         self._bwd, self._pack, self._pack_has_bwd = None, None, False
+        self.prof = None  # set to {} to collect per-kernel-kind device times (ms) during forward()
+        cmax = max([lay.z.C for lay in self.layers if not isinstance(lay, tuple)] + [det.na * 256])
+        self.scratch = torch.zeros(int(L.y5obb_bn_scratch_floats(cmax)), dtype=torch.float32, device=device)  # reductions
 
     @staticmethod
     def _stem_weight(w):
@@ -223,38 +226,52 @@ class TrainEngine:
         if tuple(x.shape) != (self.B, 3, self.H, self.W):
             raise RuntimeError(f"engine was planned for {(self.B, 3, self.H, self.W)}, got {tuple(x.shape)}")
         L, st = self._L, _lib.stream_ptr(self.device)
+        evs = [] if self.prof is not None else None
+
+        def run(tag, rc_fn):
+            if evs is None:
+                _lib.check(rc_fn(), tag)
+                return
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.check(rc_fn(), tag)
+            e1.record()
+            evs.append((tag, e0, e1))
+
         with torch.cuda.device(self.device):
             if x.dtype == torch.uint8:
                 x = x.contiguous()
-                _lib.check(L.y5obb_stem_s2d_u8(x.data_ptr(), self.x_s2d.data_ptr(), self.B, self.H, self.W, 1, st), "s2d")
+                run("s2d", lambda: L.y5obb_stem_s2d_u8(x.data_ptr(), self.x_s2d.data_ptr(), self.B, self.H, self.W, 1, st))
             else:
                 x = x.contiguous().float()
-                _lib.check(L.y5obb_stem_s2d(x.data_ptr(), self.x_s2d.data_ptr(), self.B, self.H, self.W, 1, st), "s2d")
+                run("s2d", lambda: L.y5obb_stem_s2d(x.data_ptr(), self.x_s2d.data_ptr(), self.B, self.H, self.W, 1, st))
             for lay in self.layers:
                 if isinstance(lay, tuple):
                     _, cat4, hh, ww, c_ = lay
-                    _lib.check(L.y5obb_sppf_pool(cat4.data_ptr(), cat4.shape[3], self.B, hh, ww, c_, st), "pool")
+                    run("pool", lambda: L.y5obb_sppf_pool(cat4.data_ptr(), cat4.shape[3], self.B, hh, ww, c_, st))
                     continue
-                _lib.check(L.y5obb_conv_run(lay.conv._h, st), "conv")
+                run("conv", lambda: L.y5obb_conv_run(lay.conv._h, st))
                 z, y = lay.z, lay.y
                 npix = z.B * z.H * z.W
                 bn = lay.mod.bn
-                _lib.check(L.y5obb_bn_stats(z.ptr, z.pix_stride, npix, z.C, lay.sum.data_ptr(), lay.sumsq.data_ptr(), st),
-                           "bn_stats")
-                _lib.check(L.y5obb_bn_finalize(lay.sum.data_ptr(), lay.sumsq.data_ptr(), npix, z.C,
-                                               bn.weight.data_ptr(), bn.bias.data_ptr(), float(bn.eps), float(bn.momentum),
-                                               bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
-                                               lay.scale.data_ptr(), lay.shift.data_ptr(), lay.mean.data_ptr(),
-                                               lay.invstd.data_ptr(), st), "bn_finalize")
-                _lib.check(L.y5obb_bn_silu_apply(z.ptr, z.pix_stride, npix, z.C, z.W, lay.scale.data_ptr(),
-                                                 lay.shift.data_ptr(), int(lay.act),
-                                                 lay.res.ptr if lay.res else None, lay.res.pix_stride if lay.res else 0,
-                                                 y.ptr, y.pix_stride,
-                                                 lay.y2x.ptr if lay.y2x else None, lay.y2x.pix_stride if lay.y2x else 0, st),
-                           "bn_silu_apply")
+                run("bn_stats", lambda: L.y5obb_bn_stats(z.ptr, z.pix_stride, npix, z.C, lay.sum.data_ptr(), lay.sumsq.data_ptr(),
+                                                         self.scratch.data_ptr(), self.scratch.numel(), st))
+                run("bn_finalize", lambda: L.y5obb_bn_finalize(
+                    lay.sum.data_ptr(), lay.sumsq.data_ptr(), npix, z.C, bn.weight.data_ptr(), bn.bias.data_ptr(),
+                    float(bn.eps), float(bn.momentum), bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
+                    lay.scale.data_ptr(), lay.shift.data_ptr(), lay.mean.data_ptr(), lay.invstd.data_ptr(), st))
+                run("bn_apply", lambda: L.y5obb_bn_silu_apply(
+                    z.ptr, z.pix_stride, npix, z.C, z.W, lay.scale.data_ptr(), lay.shift.data_ptr(), int(lay.act),
+                    lay.res.ptr if lay.res else None, lay.res.pix_stride if lay.res else 0, y.ptr, y.pix_stride,
+                    lay.y2x.ptr if lay.y2x else None, lay.y2x.pix_stride if lay.y2x else 0, st))
                 bn.num_batches_tracked += 1
             for cv in self.det_convs:
-                _lib.check(L.y5obb_conv_run(cv._h, st), "detect")
+                run("detect", lambda: L.y5obb_conv_run(cv._h, st))
+        if evs is not None:
+            torch.cuda.synchronize()
+            self.prof = {}
+            for tag, e0, e1 in evs:
+                self.prof.setdefault(tag, []).append(e0.elapsed_time(e1))
         return self.det_out
 
     def backward(self, grads):

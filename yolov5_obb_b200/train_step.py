@@ -75,15 +75,16 @@ class ModelEMA:
 class TrainStep:
     """model: yolov5_obb_b200.yolo.Model on a CUDA device, in train() mode.  step(imgs, targets) -> (loss, loss_items)."""
 
-    def __init__(self, model, hyp: Optional[dict] = None, batch_size: int = 16, ema: bool = True):
+    def __init__(self, model, hyp: Optional[dict] = None, batch_size: int = 16, imgsz: int = 1024, ema: bool = True):
         self.model = model
         self.hyp = dict(HYP_FINETUNE_DOTA if hyp is None else hyp)
         nbs = 64
         self.accumulate = max(round(nbs / batch_size), 1)
         self.hyp["weight_decay"] *= batch_size * self.accumulate / nbs  # train.py:145
         nl = model.model[-1].nl
-        self.hyp["box"] *= 3.0 / nl                                     # train.py:220-222
+        self.hyp["box"] *= 3.0 / nl                                     # train.py:249-252
         self.hyp["cls"] *= model.model[-1].nc / 80.0 * 3.0 / nl
+        self.hyp["obj"] *= (imgsz / 640) ** 2 * 3.0 / nl
         self.hyp["theta"] *= 3.0 / nl
         self.hyp["label_smoothing"] = 0.0
         model.hyp = self.hyp
