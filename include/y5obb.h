@@ -225,6 +225,9 @@ typedef struct {
   int64_t dz_pix_stride;
   const void* x;         /* [B][Hi][Wi][x_pix_stride] bf16, channels [0, Cin) used */
   int64_t x_pix_stride;
+  int64_t x_row_stride, x_img_stride;  /* elements; 0 = dense (Wi * x_pix_stride, Hi * row).  With explicit strides
+                                          x_pix_stride < Cin is allowed: overlapping pixel windows (the stem reads the
+                                          3 horizontal taps x 16 space-to-depth channels as one 48-channel pixel) */
   float* dw;             /* fp32; element (tap, co, ci) at dw[tap*dw_tap_stride + co*dw_co_stride + ci*dw_ci_stride] */
   int64_t dw_tap_stride, dw_co_stride, dw_ci_stride;  /* all 0 = dense [KH*KW][Cout][Cin]; (1, Cin*KH*KW, KH*KW) = the
                                                          nn.Conv2d parameter layout [Cout][Cin][KH][KW] */

@@ -64,6 +64,8 @@ def test_engine_refuses_what_it_does_not_run():
         m(torch.zeros(1, 3, 64, 64))          # CPU tensor
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, 3, 72, 64, device=DEV))  # not a stride multiple
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 3, 64, 64, device=DEV), augment=True)  # TTA is host tooling outside the path
     m.train()
     with pytest.raises(RuntimeError):
-        m(torch.zeros(1, 3, 64, 64, device=DEV))
+        m(torch.zeros(1, 3, 64, 64))          # training mode has no CPU path either

@@ -12,6 +12,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -32,15 +33,19 @@ struct WgradK {
   CUtensorMap tmB;  // x NHWC slice: (Cin, Wi, Hi, B), box {64, kwp*s, khp*s, 1}, element strides {1, s, s, 1}
   int B, Ho, Wo, Cout, Cin;
   int KH, KW, stride, pad_h, pad_w;
-  int kwp, khp, BN;         // pixel tile kwp x khp = WG_BK; N tile (input channels, multiple of 16)
-  int tiles_w, tiles_h;     // pixel tiles per image
-  int ksteps;               // B * tiles_h * tiles_w
+  int kwp, khp, BN;         // pixel block kwp x khp = WG_BK pixels; N tile (input channels, multiple of 16)
+  int tiles_w, tiles_h;     // pixel blocks per image
+  int nblocks;              // B * tiles_h * tiles_w
+  int T, ngroups;           // taps handled by one CTA (they share the dz tile), tap groups
+  int PB;                   // pixel blocks per pipeline stage
+  int steps;                // ceil(nblocks / PB) pipeline steps over the whole pixel axis
   int ksplit, co_blks, ci_blks;
   int stages, a_chunks, b_chunks;
-  uint32_t idesc, tmem_cols;
+  uint32_t idesc, tmem_cols, stage_bytes;  // idesc without the N field (set per instruction)
   float* dW;                // element (tap, co, ci) at dW[tap * s_tap + row(co) * s_co + ci * s_ci]
   long long s_tap, s_co, s_ci;
   int co_group, co_group_pad;
+  int dbg;                  // timing experiments only (Y5OBB_WGRAD_DBG env; results are garbage): 1 = no TMA, 2 = no MMA
 };
 
 // MN-major, 128B-swizzled operand: 64-channel chunks of [pixels][128 B]; 8-pixel groups 1024 B apart (SBO), chunks
@@ -55,6 +60,11 @@ __device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr) {
   return d;
 }
 
+// One pipeline stage holds PB pixel blocks; per block: the dz tile (a_chunks chunks) followed by the x tiles of the T
+// taps this CTA accumulates (b_chunks chunks each).  The taps' tiles are consecutive 64-channel chunks, i.e. ONE N axis
+// of T * b_chunks * 64 columns: an instruction covers up to 4 chunks (N = 256), so the dz tile - which tcgen05.mma
+// re-reads from shared memory for every instruction - is fetched once per 4 chunks, and one mbarrier round trip
+// (~0.2 us) is amortised over the whole stage.
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_constant__ WgradK p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[WG_MAX_STAGES];
@@ -62,22 +72,23 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
   __shared__ __align__(8) uint64_t done_bar;
   __shared__ uint32_t tmem_base_smem;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const uint32_t a_bytes = 2u * WG_CHUNK;
-  const uint32_t stage_bytes = a_bytes + (uint32_t)p.b_chunks * WG_CHUNK;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t a_bytes = (uint32_t)p.a_chunks * WG_CHUNK, b_bytes = (uint32_t)p.b_chunks * WG_CHUNK;
+  const uint32_t blk_bytes = a_bytes + (uint32_t)p.T * b_bytes;
 
-  // work item: (tap, co block, ci block, k split)
+  // work item: (tap group, co block, ci block, k split)
   int item = blockIdx.x;
   const int ks = item % p.ksplit;
   item /= p.ksplit;
   const int cib = item % p.ci_blks;
   item /= p.ci_blks;
   const int cob = item % p.co_blks;
-  const int tap = item / p.co_blks;
-  const int kh = tap / p.KW, kw = tap - kh * p.KW;
-  const int k0 = (int)(((long long)p.ksteps * ks) / p.ksplit), k1 = (int)(((long long)p.ksteps * (ks + 1)) / p.ksplit);
+  const int grp = item / p.co_blks;
+  const int tap0 = grp * p.T;
+  const int ntap = min(p.T, p.KH * p.KW - tap0);
+  const int s0 = (int)(((long long)p.steps * ks) / p.ksplit), s1 = (int)(((long long)p.steps * (ks + 1)) / p.ksplit);
   // 64-channel chunks of A this block really has (rows of D beyond Cout are never stored)
-  const int a_chunks = min(2, (p.Cout - cob * 128 + 63) >> 6);
+  const int a_chunks = min(p.a_chunks, (p.Cout - cob * 128 + 63) >> 6);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&p.tmA);
@@ -103,20 +114,33 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      const uint32_t tx = (uint32_t)(a_chunks + p.b_chunks) * WG_CHUNK;
-      for (int k = k0; k < k1; ++k) {
-        const int b = k / per_img;
-        const int r = k - b * per_img;
-        const int th = r / p.tiles_w;
-        const int ho0 = th * p.khp, wo0 = (r - th * p.tiles_w) * p.kwp;
+      const uint32_t tx = (uint32_t)p.PB * (uint32_t)(a_chunks + ntap * p.b_chunks) * WG_CHUNK;
+      for (int st = s0; st < s1; ++st) {
         ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
-        uint8_t* sa = smem + (size_t)s * stage_bytes;
-        ptx::mbar_expect_tx(&full_bar[s], tx);
-        for (int c = 0; c < a_chunks; ++c)
-          ptx::tma_load_4d(sa + (size_t)c * WG_CHUNK, &p.tmA, &full_bar[s], cob * 128 + c * 64, wo0, ho0, b);
-        const int wi0 = wo0 * p.stride + kw - p.pad_w, hi0 = ho0 * p.stride + kh - p.pad_h;
-        for (int c = 0; c < p.b_chunks; ++c)
-          ptx::tma_load_4d(sa + a_bytes + (size_t)c * WG_CHUNK, &p.tmB, &full_bar[s], cib * p.BN + c * 64, wi0, hi0, b);
+        uint8_t* sbase = smem + (size_t)s * p.stage_bytes;
+        if (p.dbg & 1) {
+          ptx::mbar_arrive(&full_bar[s]);
+        } else {
+          ptx::mbar_expect_tx(&full_bar[s], tx);
+          for (int pb = 0; pb < p.PB; ++pb) {
+            const int k = st * p.PB + pb;        // pixel block; blocks past the end decode to b >= B: all zero fill
+            const int b = k / per_img;
+            const int r = k - b * per_img;
+            const int th = r / p.tiles_w;
+            const int ho0 = th * p.khp, wo0 = (r - th * p.tiles_w) * p.kwp;
+            uint8_t* sa = sbase + (size_t)pb * blk_bytes;
+            for (int c = 0; c < a_chunks; ++c)
+              ptx::tma_load_4d(sa + (size_t)c * WG_CHUNK, &p.tmA, &full_bar[s], cob * 128 + c * 64, wo0, ho0, b);
+            for (int t = 0; t < ntap; ++t) {
+              const int tap = tap0 + t;
+              const int kh = tap / p.KW, kw = tap - kh * p.KW;
+              const int wi0 = wo0 * p.stride + kw - p.pad_w, hi0 = ho0 * p.stride + kh - p.pad_h;
+              uint8_t* sb = sa + a_bytes + (size_t)t * b_bytes;
+              for (int c = 0; c < p.b_chunks; ++c)
+                ptx::tma_load_4d(sb + (size_t)c * WG_CHUNK, &p.tmB, &full_bar[s], cib * p.BN + c * 64, wi0, hi0, b);
+            }
+          }
+        }
         if (++s == p.stages) {
           s = 0;
           ph ^= 1u;
@@ -129,17 +153,31 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
       uint32_t ph = 0;
       const uint64_t desc_hi = make_mnmajor_desc(0u);
       const uint32_t ring = ptx::smem_u32(smem);
-      uint32_t accumulate = 0u;
-      for (int k = k0; k < k1; ++k) {
+      uint32_t started = 0u;  // bit g: accumulator group g holds a partial sum already
+      const int nchunks = ntap * p.b_chunks;  // the taps' x tiles are consecutive 64-channel chunks: ONE N axis
+      for (int st = s0; st < s1; ++st) {
         ptx::mbar_wait(&full_bar[s], ph);
         ptx::tc_fence_after();
-        const uint32_t sa = ring + (uint32_t)s * stage_bytes;
-        const uint64_t da = desc_hi | (uint64_t)((sa & 0x3FFFFu) >> 4);
-        const uint64_t db = desc_hi | (uint64_t)(((sa + a_bytes) & 0x3FFFFu) >> 4);
+        if (!(p.dbg & 2)) {
+          for (int pb = 0; pb < p.PB; ++pb) {
+            const uint32_t sa = ring + (uint32_t)s * p.stage_bytes + (uint32_t)pb * blk_bytes;
+            const uint64_t da = desc_hi | (uint64_t)((sa & 0x3FFFFu) >> 4);
+            // up to 4 chunks (N = 256) per instruction: the dz tile (A) is fetched once for all of them
+            for (int c0 = 0, g = 0; c0 < nchunks; c0 += 4, ++g) {
+              const int nn = min(4, nchunks - c0);
+              const uint32_t sb = sa + a_bytes + (uint32_t)c0 * WG_CHUNK;
+              const uint64_t db = desc_hi | (uint64_t)((sb & 0x3FFFFu) >> 4);
+              const uint32_t d_tmem = tmem_base + (uint32_t)(c0 * 64);
+              const uint32_t idesc = p.idesc | ((uint32_t)(nn * 8) << 17);
+              uint32_t accumulate = (started >> g) & 1u;
 #pragma unroll
-        for (int j = 0; j < WG_BK / 16; ++j) {  // 16 pixel rows = 2048 B per MMA
-          ptx::umma_bf16(tmem_base, da + (uint64_t)(128 * j), db + (uint64_t)(128 * j), p.idesc, accumulate);
-          accumulate = 1u;
+              for (int j = 0; j < WG_BK / 16; ++j) {  // 16 pixel rows = 2048 B per MMA
+                ptx::umma_bf16(d_tmem, da + (uint64_t)(128 * j), db + (uint64_t)(128 * j), idesc, accumulate);
+                accumulate = 1u;
+              }
+              started |= 1u << g;
+            }
+          }
         }
         ptx::umma_commit(&empty_bar[s]);
         if (++s == p.stages) {
@@ -150,7 +188,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
       ptx::umma_commit(&done_bar);
     }
   } else {
-    // epilogue: TMEM lane = output channel (row of dW), columns = input channels
+    // epilogue: TMEM lane = output channel (row of dW), columns = tap-major, then input channels
     const int q = warp & 3;
     const int co = cob * 128 + q * 32 + lane;
     int co_row = co;
@@ -160,21 +198,23 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
       co_ok = co_ok && c < p.co_group;
       co_row = a * p.co_group + c;
     }
-    if (k1 > k0) {
+    if (s1 > s0) {
       ptx::mbar_wait(&done_bar, 0u);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-      float* row = p.dW + (long long)tap * p.s_tap + (long long)co_row * p.s_co + (long long)(cib * p.BN) * p.s_ci;
       const int ncols = min(p.BN, p.Cin - cib * p.BN);
-      if (cob * 128 + q * 32 < p.Cout) {  // warp-uniform
-        for (int c0 = 0; c0 < ncols; c0 += 32) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)c0, r);
-          ptx::tmem_ld_wait();
-          if (co_ok) {
+      if (cob * 128 + q * 32 < p.Cout && !(p.dbg & 2)) {  // warp-uniform
+        for (int t = 0; t < ntap; ++t) {
+          float* row = p.dW + (long long)(tap0 + t) * p.s_tap + (long long)co_row * p.s_co + (long long)(cib * p.BN) * p.s_ci;
+          for (int c0 = 0; c0 < ncols; c0 += 16) {  // chunk (c0 / 64) of tap t starts at TMEM column (t * b_chunks) * 64
+            uint32_t r[16];
+            ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)(t * p.b_chunks * 64 + c0), r);
+            ptx::tmem_ld_wait();
+            if (co_ok) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (c0 + j < ncols) atomicAdd(row + (long long)(c0 + j) * p.s_ci, __uint_as_float(r[j]));
+              for (int j = 0; j < 16; ++j)
+                if (c0 + j < ncols) atomicAdd(row + (long long)(c0 + j) * p.s_ci, __uint_as_float(r[j]));
+            }
           }
         }
       }
@@ -222,8 +262,11 @@ int y5obb_wgrad_create(const y5obb_wgrad_desc* d, y5obb_wgrad_t** out) {
   if (!d || !out || !d->dz || !d->x || !d->dw) return Y5OBB_EINVAL;
   if (d->stride != 1 && d->stride != 2) return Y5OBB_EINVAL;
   if (d->B < 1 || d->Cout < 1 || d->Cin < 1 || d->KH < 1 || d->KW < 1 || d->Ho < 1 || d->Wo < 1) return Y5OBB_EINVAL;
-  if ((d->dz_pix_stride & 7) || (d->x_pix_stride & 7) || d->dz_pix_stride < d->Cout || d->x_pix_stride < d->Cin)
+  if ((d->dz_pix_stride & 7) || (d->x_pix_stride & 7) || (d->x_row_stride & 7) || (d->x_img_stride & 7) ||
+      d->dz_pix_stride < d->Cout)
     return Y5OBB_EINVAL;
+  if ((d->x_row_stride == 0) != (d->x_img_stride == 0)) return Y5OBB_EINVAL;
+  if (!d->x_row_stride && d->x_pix_stride < d->Cin) return Y5OBB_EINVAL;  // overlapping windows need explicit strides
   if ((reinterpret_cast<uintptr_t>(d->dz) | reinterpret_cast<uintptr_t>(d->x)) & 15) return Y5OBB_EINVAL;
   PFN_tmapEncodeTiled enc = wg_get_encode();
   if (!enc) return Y5OBB_ECUDA;
@@ -256,6 +299,7 @@ int y5obb_wgrad_create(const y5obb_wgrad_desc* d, y5obb_wgrad_t** out) {
   }
   k.co_group = d->co_group;
   k.co_group_pad = d->co_group_pad;
+  if (const char* e = getenv("Y5OBB_WGRAD_DBG")) k.dbg = atoi(e);
   // pixel tile kwp x khp = 64 output pixels: the shape that covers the map with the fewest tiles (ties: widest rows)
   long long best = -1;
   for (int kwp = 1; kwp <= WG_BK; kwp <<= 1) {
@@ -269,24 +313,49 @@ int y5obb_wgrad_create(const y5obb_wgrad_desc* d, y5obb_wgrad_t** out) {
   }
   k.tiles_w = (d->Wo + k.kwp - 1) / k.kwp;
   k.tiles_h = (d->Ho + k.khp - 1) / k.khp;
-  k.ksteps = d->B * k.tiles_w * k.tiles_h;
+  k.nblocks = d->B * k.tiles_w * k.tiles_h;
   k.ci_blks = (d->Cin + 255) / 256;
   k.BN = ((d->Cin + k.ci_blks - 1) / k.ci_blks + 15) / 16 * 16;
   k.b_chunks = (k.BN + 63) / 64;
   k.co_blks = (d->Cout + 127) / 128;
-  const int items = d->KH * d->KW * k.co_blks * k.ci_blks;
-  // split-K so that ~2 CTAs per SM exist, but never fewer than 16 pipeline steps per CTA: every split adds a
-  // 128 x BN fp32 atomic epilogue
-  k.ksplit = std::max(1, std::min(std::max(1, k.ksteps / 16), (2 * sm_count() + items - 1) / items));
-  const uint32_t stage_bytes = (2u + (uint32_t)k.b_chunks) * WG_CHUNK;
-  k.stages = (int)std::min<size_t>(WG_MAX_STAGES, WG_SMEM / stage_bytes);
-  if (k.stages < 2) {
+  k.a_chunks = d->Cout > 64 ? 2 : 1;
+  const int ntaps = d->KH * d->KW;
+  // taps per CTA: as many accumulators as TMEM (512 columns) holds, while one pixel block still fits >= 3 stages
+  const uint32_t a_bytes = (uint32_t)k.a_chunks * WG_CHUNK, b_bytes = (uint32_t)k.b_chunks * WG_CHUNK;
+  int T = std::max(1, std::min(ntaps, 8 / k.b_chunks));  // 8 chunks of 64 fp32 columns = the 512 TMEM columns
+  while (T > 1 && a_bytes + (uint32_t)T * b_bytes > WG_SMEM / 3) --T;
+  k.ngroups = (ntaps + T - 1) / T;
+  k.T = (ntaps + k.ngroups - 1) / k.ngroups;  // balanced groups
+  const uint32_t blk_bytes = a_bytes + (uint32_t)k.T * b_bytes;
+  if (blk_bytes > WG_SMEM / 2) {
     delete o;
     return Y5OBB_EINVAL;
   }
-  k.idesc = ptx::make_idesc_bf16(128, k.BN) | (1u << 15) | (1u << 16);  // A and B MN-major
-  k.tmem_cols = 32;
-  while ((int)k.tmem_cols < k.BN) k.tmem_cols <<= 1;
+  // pixel blocks per stage: narrow layers move few bytes per block; keep >= 3 stages and at most 4 blocks
+  k.PB = std::max(1, std::min(4, (int)(WG_SMEM / 3 / blk_bytes)));
+  k.PB = std::min(k.PB, std::max(1, k.nblocks));
+  k.stage_bytes = (uint32_t)k.PB * blk_bytes;
+  k.stages = (int)std::min<size_t>(WG_MAX_STAGES, WG_SMEM / k.stage_bytes);
+  k.steps = (k.nblocks + k.PB - 1) / k.PB;
+  const int items = k.ngroups * k.co_blks * k.ci_blks;
+  {  // split-K: minimise (waves) x (steps per CTA + the fixed cost of a CTA, ~8 steps: TMEM alloc, pipeline fill,
+     // fp32 atomic epilogue); 1 CTA per SM
+    const int sms = sm_count();
+    long long best_cost = -1;
+    int best = 1;
+    for (int ksp = 1; ksp <= std::min(k.steps, 4 * sms); ++ksp) {
+      const long long waves = ((long long)items * ksp + sms - 1) / sms;
+      const long long cost = waves * ((k.steps + ksp - 1) / ksp + 8);
+      if (best_cost < 0 || cost < best_cost) {
+        best_cost = cost;
+        best = ksp;
+      }
+    }
+    k.ksplit = best;
+  }
+  k.idesc = ptx::make_idesc_bf16(128, 0) | (1u << 15) | (1u << 16);  // A and B MN-major; N is set per instruction
+  k.tmem_cols = 64;
+  while (k.tmem_cols < (uint32_t)(k.T * k.b_chunks * 64)) k.tmem_cols <<= 1;
   {
     cuuint64_t dims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)d->Wo, (cuuint64_t)d->Ho, (cuuint64_t)d->B};
     cuuint64_t strides[3] = {(cuuint64_t)d->dz_pix_stride * 2, (cuuint64_t)d->dz_pix_stride * d->Wo * 2,
@@ -305,8 +374,9 @@ int y5obb_wgrad_create(const y5obb_wgrad_desc* d, y5obb_wgrad_t** out) {
   {
     const cuuint32_t s = (cuuint32_t)d->stride;
     cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->Wi, (cuuint64_t)d->Hi, (cuuint64_t)d->B};
-    cuuint64_t strides[3] = {(cuuint64_t)d->x_pix_stride * 2, (cuuint64_t)d->x_pix_stride * d->Wi * 2,
-                             (cuuint64_t)d->x_pix_stride * d->Wi * d->Hi * 2};
+    const cuuint64_t row = d->x_row_stride ? (cuuint64_t)d->x_row_stride : (cuuint64_t)d->x_pix_stride * d->Wi;
+    const cuuint64_t img = d->x_img_stride ? (cuuint64_t)d->x_img_stride : row * d->Hi;
+    cuuint64_t strides[3] = {(cuuint64_t)d->x_pix_stride * 2, row * 2, img * 2};
     cuuint32_t box[4] = {64, (cuuint32_t)k.kwp * s, (cuuint32_t)k.khp * s, 1};
     cuuint32_t es[4] = {1, s, s, 1};
     CUresult r = enc(&k.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->x), dims, strides, box, es,
@@ -319,7 +389,7 @@ int y5obb_wgrad_create(const y5obb_wgrad_desc* d, y5obb_wgrad_t** out) {
     }
   }
   o->grid = items * k.ksplit;
-  o->smem = std::max<size_t>((size_t)k.stages * stage_bytes + 1024, 116 * 1024);
+  o->smem = std::max<size_t>((size_t)k.stages * k.stage_bytes + 1024, 116 * 1024);
   o->flops = 2.0 * d->B * d->Ho * d->Wo * (double)d->Cout * d->Cin * d->KH * d->KW;
   static bool attr_set = false;
   if (!attr_set) {

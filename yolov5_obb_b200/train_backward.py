@@ -210,24 +210,29 @@ class BackwardPlan:
 
             # ---- wgrad (straight from the NHWC buffers)
             x = lay.x
-            if lay.stem:  # 3x3 conv over the space-to-depth image; its zero border columns stand for the W padding
-                Hi, Wi, Cin_w = eng.H // 2, eng.W // 2 + 2, 16
-                kw_, sw_, pw_ = 3, 1, (1, 0)
+            if lay.stem:  # the forward's view: a 3x1 conv over 48-channel windows (3 horizontal taps x 16 s2d channels)
+                Wp = eng.W // 2 + 2
+                Hi, Wi, Cin_w = eng.H // 2, eng.W // 2, 48
+                kw_, sw_, pw_ = (3, 1), 1, (1, 0)
                 x_ptr, x_ps, x_keep = eng.x_s2d.data_ptr(), 16, eng.x_s2d
+                x_strides = (Wp * 16, (eng.H // 2) * Wp * 16)
             else:
                 Hi, Wi, Cin_w = x.H, x.W, x.C
                 kw_, sw_, pw_ = k, s, p
                 x_ptr, x_ps, x_keep = x.ptr, x.pix_stride, x.buf
+                x_strides = (0, 0)
+            ntap = kw_[0] * kw_[1] if isinstance(kw_, tuple) else kw_ * kw_
             if lay.stem:  # gradient over the space-to-depth form, re-mapped to [Cout,3,6,6] at the end of run()
-                dw = f32(9 * Cout * 16)
+                dw = f32(3 * Cout * 48)
                 part["stem_dw"] = dw
                 add("zero", lambda st, dw=dw: dw.zero_())
-                wg = Wgrad(dz.data_ptr(), Cout, x_ptr, x_ps, dw, B, Cout, Hh, Ww, Cin_w, Hi, Wi, kw_, sw_, pw_, keep=(dz, x_keep))
+                wg = Wgrad(dz.data_ptr(), Cout, x_ptr, x_ps, dw, B, Cout, Hh, Ww, Cin_w, Hi, Wi, kw_, sw_, pw_, keep=(dz, x_keep),
+                           x_strides=x_strides)
             else:
                 wg = Wgrad(dz.data_ptr(), Cout, x_ptr, x_ps, grad_of(conv.weight), B, Cout, Hh, Ww, Cin_w, Hi, Wi, kw_, sw_, pw_,
                            keep=(dz, x_keep, self.flat), param_layout=True)
             self.keep.append(wg)
-            self.flops += 2.0 * npix * Cout * Cin_w * kw_ * kw_
+            self.flops += 2.0 * npix * Cout * Cin_w * ntap
             add("wgrad", lambda st, wg=wg: wg.run(st))
 
             # ---- dgrad
@@ -293,9 +298,9 @@ class BackwardPlan:
                 mi, bn = part["mi"], part["bn"]
                 self.pgrad[mi.bias].copy_(part["s1"].view(det.na, bn)[:, :det.no].reshape(-1))
             for part in self.conv_parts:
-                if "stem_dw" in part:  # w2[co, (dy*2+dx)*3+c, ty, tx] = w[co, c, 2ty+dy, 2tx+dx]
+                if "stem_dw" in part:  # dw[ty][co][tx * 16 + (dy*2+dx)*3 + c] is the gradient of w[co, c, 2ty+dy, 2tx+dx]
                     conv = part["lay"].mod.conv
-                    dw = part["stem_dw"].view(3, 3, conv.out_channels, 16).permute(2, 3, 0, 1)
+                    dw = part["stem_dw"].view(3, conv.out_channels, 3, 16).permute(1, 3, 0, 2)  # [co, ch16, ty, tx]
                     g = self.pgrad[conv.weight]
                     for dy in range(2):
                         for dx in range(2):

@@ -9,7 +9,8 @@ from . import _lib
 
 class WgradDesc(ctypes.Structure):
     """Mirror of y5obb_wgrad_desc (include/y5obb.h)."""
-    _fields_ = [("dz", c_void_p), ("dz_pix_stride", c_int64), ("x", c_void_p), ("x_pix_stride", c_int64), ("dw", c_void_p),
+    _fields_ = [("dz", c_void_p), ("dz_pix_stride", c_int64), ("x", c_void_p), ("x_pix_stride", c_int64),
+                ("x_row_stride", c_int64), ("x_img_stride", c_int64), ("dw", c_void_p),
                 ("dw_tap_stride", c_int64), ("dw_co_stride", c_int64), ("dw_ci_stride", c_int64),
                 ("B", c_int), ("Cout", c_int), ("Ho", c_int), ("Wo", c_int), ("Cin", c_int), ("Hi", c_int), ("Wi", c_int),
                 ("KH", c_int), ("KW", c_int), ("stride", c_int), ("pad_h", c_int), ("pad_w", c_int),
@@ -20,14 +21,16 @@ class Wgrad:
     """dW += sum_pixels dz * x over fixed NHWC buffers (TMA descriptors baked at creation).
     dz / x: (ptr, pix_stride) of the channel slice; `keep` holds the owning tensors alive.
     param_layout=False: dw is [KH*KW][Cout][Cin]; True: dw is the nn.Conv2d parameter layout [Cout][Cin][KH][KW].
-    co_group=(real, padded): Detect's per-anchor padded channel groups (rows of padding channels are skipped)."""
+    co_group=(real, padded): Detect's per-anchor padded channel groups (rows of padding channels are skipped).
+    x_strides=(row, image) in elements: explicit strides of x (allows overlapping pixel windows, x_pix_stride < Cin)."""
 
     def __init__(self, dz_ptr: int, dz_pix_stride: int, x_ptr: int, x_pix_stride: int, dw: torch.Tensor, B, Cout, Ho, Wo,
-                 Cin, Hi, Wi, k, stride, pad, keep=(), param_layout=False, co_group=(0, 0)):
+                 Cin, Hi, Wi, k, stride, pad, keep=(), param_layout=False, co_group=(0, 0), x_strides=(0, 0)):
         kh, kw = (k, k) if isinstance(k, int) else k
         ph, pw = (pad, pad) if isinstance(pad, int) else pad
         st = (1, Cin * kh * kw, kh * kw) if param_layout else (0, 0, 0)
-        d = WgradDesc(dz_ptr, dz_pix_stride, x_ptr, x_pix_stride, dw.data_ptr(), st[0], st[1], st[2], B, Cout, Ho, Wo, Cin, Hi,
+        d = WgradDesc(dz_ptr, dz_pix_stride, x_ptr, x_pix_stride, x_strides[0], x_strides[1], dw.data_ptr(), st[0], st[1], st[2],
+                      B, Cout, Ho, Wo, Cin, Hi,
                       Wi, kh, kw, stride, ph, pw, co_group[0], co_group[1])
         rows = Cout if not co_group[1] else Cout // co_group[1] * co_group[0]
         assert dw.dtype == torch.float32 and dw.is_contiguous() and dw.numel() == kh * kw * rows * Cin
