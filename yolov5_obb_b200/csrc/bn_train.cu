@@ -135,14 +135,33 @@ __global__ void __launch_bounds__(STAT_THREADS) k_bn_stats(const __nv_bfloat16* 
   }
 }
 
-// out[j] = sum over blocks (in order) of partial[b][j], j in [0, 2C): [0, C) -> out_a, [C, 2C) -> out_b
-__global__ void k_reduce_partials(const float* __restrict__ partial, int blocks, int C, float* __restrict__ out_a,
-                                  float* __restrict__ out_b) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= 2 * C) return;
+// out[j] = sum over blocks of partial[b][j], j in [0, 2C): [0, C) -> out_a, [C, 2C) -> out_b, in a FIXED order: thread
+// (seg, col) adds rows seg, seg + 32, ... and thread (0, col) then adds the 32 segment sums.  8 columns x 32 row
+// segments per block.  Optionally also writes the BatchNorm parameter gradients dgamma (+)= out_b, dbeta (+)= out_a.
+__global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict__ partial, int blocks, int C,
+                                                         float* __restrict__ out_a, float* __restrict__ out_b,
+                                                         float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                         int param_accumulate) {
+  __shared__ float red[32][8];
+  const int col = threadIdx.x & 7, seg = threadIdx.x >> 3;
+  const int j = blockIdx.x * 8 + col;
   float acc = 0.f;
-  for (int b = 0; b < blocks; ++b) acc += partial[(long long)b * 2 * C + j];
-  if (j < C) out_a[j] = acc; else out_b[j - C] = acc;
+  if (j < 2 * C)
+    for (int b = seg; b < blocks; b += 32) acc += partial[(long long)b * 2 * C + j];
+  red[seg][col] = acc;
+  __syncthreads();
+  if (seg == 0 && j < 2 * C) {
+    float t = red[0][col];
+#pragma unroll
+    for (int s2 = 1; s2 < 32; ++s2) t += red[s2][col];
+    if (j < C) {
+      out_a[j] = t;
+      if (dbeta) dbeta[j] = (param_accumulate ? dbeta[j] : 0.f) + t;
+    } else {
+      out_b[j - C] = t;
+      if (dgamma) dgamma[j - C] = (param_accumulate ? dgamma[j - C] : 0.f) + t;
+    }
+  }
 }
 
 __global__ void k_bn_finalize(const float* __restrict__ sum, const float* __restrict__ sumsq, long long npix, int C,
@@ -384,15 +403,6 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const __nv_bfloat16* __res
   }
 }
 
-// dgamma (+)= sum_dux, dbeta (+)= sum_du   (fp32 parameter gradients)
-__global__ void k_bn_param_grads(const float* __restrict__ sum_du, const float* __restrict__ sum_dux, int C,
-                                 float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  dgamma[c] = (accumulate ? dgamma[c] : 0.f) + sum_dux[c];
-  dbeta[c] = (accumulate ? dbeta[c] : 0.f) + sum_du[c];
-}
-
 // gdst[b,h,w,:] (+)= sum of the 2x2 block gsrc[b,2h+{0,1},2w+{0,1},:]   (backward of nn.Upsample(2x nearest))
 __global__ void k_upsample2x_bwd(const __nv_bfloat16* __restrict__ gsrc, long long src_stride,
                                  __nv_bfloat16* __restrict__ gdst, long long dst_stride, long long npix, int C, int W,
@@ -541,8 +551,8 @@ __global__ void k_detect_grad_pack1(const float* __restrict__ g, __nv_bfloat16* 
   }
 }
 
-int stat_blocks_max() { return sm_count() * 4; }
-// blocks of the two-stage reductions: >= 16 pixels per thread, at most 4 blocks per SM
+int stat_blocks_max() { return sm_count() * 2; }
+// blocks of the two-stage reductions: >= 16 pixels per thread, at most 2 blocks per SM (every block adds a partial row)
 int stat_blocks(long long npix, int C) {
   const int vecs = C / 8;
   const int cols = std::min(vecs, STAT_THREADS);
@@ -570,7 +580,7 @@ int y5obb_bn_stats(const void* z, int64_t z_pix_stride, int64_t npix, int C, flo
   const long long chunk = (npix + blocks - 1) / blocks;
   k_bn_stats<<<blocks, STAT_THREADS, 0, st>>>(static_cast<const __nv_bfloat16*>(z), z_pix_stride, npix, C, chunk, scratch);
   Y5_LAUNCH_CHECK();
-  k_reduce_partials<<<(2 * C + 255) / 256, 256, 0, st>>>(scratch, blocks, C, sum, sumsq);
+  k_reduce_partials<<<(2 * C + 7) / 8, 256, 0, st>>>(scratch, blocks, C, sum, sumsq, nullptr, nullptr, 0);
   Y5_LAUNCH_CHECK();
   return Y5OBB_OK;
 }
@@ -613,6 +623,7 @@ int y5obb_bn_silu_bwd(const void* z, int64_t z_pix_stride, const void* dy, int64
                       float* sum_du, float* sum_dux, void* dz, int64_t dz_pix_stride, void* gres,
                       int64_t gres_pix_stride, int gres_accumulate, float* dgamma, float* dbeta, int param_accumulate,
                       float* scratch, int64_t scratch_floats, void* stream) {
+  if ((dgamma == nullptr) != (dbeta == nullptr)) return Y5OBB_EINVAL;
   if (!z || !dy || !scale || !shift || !mean || !invstd || !sum_du || !sum_dux || !dz || !scratch || npix <= 0 || C <= 0 ||
       (C & 7))
     return Y5OBB_EINVAL;
@@ -628,7 +639,7 @@ int y5obb_bn_silu_bwd(const void* z, int64_t z_pix_stride, const void* dy, int64
                                                    static_cast<const __nv_bfloat16*>(dy), dy_pix_stride, npix, C, scale,
                                                    shift, mean, invstd, act, chunk, scratch);
   Y5_LAUNCH_CHECK();
-  k_reduce_partials<<<(2 * C + 255) / 256, 256, 0, st>>>(scratch, blocks, C, sum_du, sum_dux);
+  k_reduce_partials<<<(2 * C + 7) / 8, 256, 0, st>>>(scratch, blocks, C, sum_du, sum_dux, dgamma, dbeta, param_accumulate);
   Y5_LAUNCH_CHECK();
   const dim3 g2 = colwise_grid(npix, C);
   k_bn_bwd_apply<<<g2, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(z), z_pix_stride,
@@ -636,10 +647,6 @@ int y5obb_bn_silu_bwd(const void* z, int64_t z_pix_stride, const void* dy, int64
                                      invstd, act, sum_du, sum_dux, static_cast<__nv_bfloat16*>(dz), dz_pix_stride,
                                      static_cast<__nv_bfloat16*>(gres), gres_pix_stride, gres_accumulate);
   Y5_LAUNCH_CHECK();
-  if (dgamma && dbeta) {
-    k_bn_param_grads<<<(C + 127) / 128, 128, 0, st>>>(sum_du, sum_dux, C, dgamma, dbeta, param_accumulate);
-    Y5_LAUNCH_CHECK();
-  }
   return Y5OBB_OK;
 }
 

@@ -116,7 +116,8 @@ class BackwardPlan:
             return op, wp
 
         # ---------------- Detect levels ----------------
-        self.det_grads_in = [None] * det.nl  # set per backward call (fp32 [B,na,H,W,no])
+        self.det_grads_in = [torch.zeros_like(o) for o in eng.det_out]  # static copies of dLoss/dpred (graph inputs)
+        self._calls, self._graph = 0, None
         self.det_parts = []
         for l in range(det.nl):
             cv = eng.det_convs[l]
@@ -275,8 +276,29 @@ class BackwardPlan:
             for l in range(det.nl):
                 g = grads[l]
                 if g is None:
-                    g = torch.zeros_like(eng.det_out[l])
-                self.det_grads_in[l] = g.contiguous().float()
+                    self.det_grads_in[l].zero_()
+                else:
+                    self.det_grads_in[l].copy_(g)
+            if self.prof is not None or not eng.use_graph:
+                self._launch_all(st)
+            else:  # first run eager, second captured, then ONE graph launch replaces ~700 kernel launches
+                self._calls += 1
+                if self._calls == 1:
+                    self._launch_all(st)
+                else:
+                    if self._graph is None:
+                        torch.cuda.synchronize(eng.device)
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                            self._launch_all(_lib.stream_ptr(eng.device))
+                        self._graph = g
+                    self._graph.replay()
+        return self.flat
+
+    def _launch_all(self, st):
+        eng = self.eng
+        det = eng.model.model[-1]
+        if True:
             self.flat.zero_()
             if self.prof is None:
                 for _, step in self.steps:

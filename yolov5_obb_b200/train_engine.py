@@ -188,6 +188,10 @@ class TrainEngine:
         self.out_slices = out
         self._bwd, self._pack, self._pack_has_bwd = None, None, False
         self.prof = None  # set to {} to collect per-kernel-kind device times (ms) during forward()
+        import os
+        self.use_graph = os.environ.get("Y5OBB_NO_GRAPH", "0") != "1"
+        self._graphs = {}
+        self._nbt = [lay.mod.bn.num_batches_tracked for lay in self.layers if not isinstance(lay, tuple)]
         cmax = max([lay.z.C for lay in self.layers if not isinstance(lay, tuple)] + [det.na * 256])
         self.scratch = torch.zeros(int(L.y5obb_bn_scratch_floats(cmax)), dtype=torch.float32, device=device)  # reductions
 
@@ -220,11 +224,40 @@ class TrainEngine:
             self._pack_has_bwd = self._bwd is not None
         self._pack.run()
 
-    def forward(self, x: torch.Tensor):
-        """x: [B,3,H,W] fp32 in [0,1] or uint8 -> list of 3 raw prediction tensors [B, na, H_i, W_i, no] fp32."""
+    def forward(self, x: torch.Tensor, refresh: bool = False):
+        """x: [B,3,H,W] fp32 in [0,1] or uint8 -> list of 3 raw prediction tensors [B, na, H_i, W_i, no] fp32.
+        refresh=True re-packs the weights from the current parameters first (after an optimizer step).
+
+        The launch sequence is fixed (same buffers every step), so from the third call on it is replayed as ONE CUDA
+        graph per input dtype: ~330 launches collapse into a single cudaGraphLaunch (Y5OBB_NO_GRAPH=1 disables)."""
         _lib.require_cuda(x, "x")
         if tuple(x.shape) != (self.B, 3, self.H, self.W):
             raise RuntimeError(f"engine was planned for {(self.B, 3, self.H, self.W)}, got {tuple(x.shape)}")
+        if x.dtype != torch.uint8:
+            x = x.float()
+        if self.prof is not None or not self.use_graph:
+            return self._forward_eager(x.contiguous(), refresh)
+        slot = self._graphs.setdefault((x.dtype, refresh), dict(calls=0, graph=None, x=None))
+        slot["calls"] += 1
+        if slot["calls"] == 1:  # first call: eager (warm-up; plans and lazily built state settle)
+            return self._forward_eager(x.contiguous(), refresh)
+        if slot["graph"] is None:
+            if refresh and self._pack is None:
+                self.refresh_weights()  # builds the packing plan (allocates): not capturable
+            slot["x"] = torch.empty_like(x, memory_format=torch.contiguous_format)
+            slot["x"].copy_(x)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                self._forward_eager(slot["x"], refresh)
+            slot["graph"] = g
+        slot["x"].copy_(x)
+        slot["graph"].replay()
+        return self.det_out
+
+    def _forward_eager(self, x: torch.Tensor, refresh: bool = False):
+        if refresh:
+            self.refresh_weights()
         L, st = self._L, _lib.stream_ptr(self.device)
         evs = [] if self.prof is not None else None
 
@@ -240,10 +273,8 @@ class TrainEngine:
 
         with torch.cuda.device(self.device):
             if x.dtype == torch.uint8:
-                x = x.contiguous()
                 run("s2d", lambda: L.y5obb_stem_s2d_u8(x.data_ptr(), self.x_s2d.data_ptr(), self.B, self.H, self.W, 1, st))
             else:
-                x = x.contiguous().float()
                 run("s2d", lambda: L.y5obb_stem_s2d(x.data_ptr(), self.x_s2d.data_ptr(), self.B, self.H, self.W, 1, st))
             for lay in self.layers:
                 if isinstance(lay, tuple):
@@ -264,9 +295,9 @@ class TrainEngine:
                     z.ptr, z.pix_stride, npix, z.C, z.W, lay.scale.data_ptr(), lay.shift.data_ptr(), int(lay.act),
                     lay.res.ptr if lay.res else None, lay.res.pix_stride if lay.res else 0, y.ptr, y.pix_stride,
                     lay.y2x.ptr if lay.y2x else None, lay.y2x.pix_stride if lay.y2x else 0, st))
-                bn.num_batches_tracked += 1
             for cv in self.det_convs:
                 run("detect", lambda: L.y5obb_conv_run(cv._h, st))
+            torch._foreach_add_(self._nbt, 1)  # BatchNorm2d.num_batches_tracked of every layer
         if evs is not None:
             torch.cuda.synchronize()
             self.prof = {}
@@ -280,6 +311,7 @@ class TrainEngine:
         if self._bwd is None:
             from .train_backward import BackwardPlan
             self._bwd = BackwardPlan(self)     # packs its data-gradient weights from the current parameters
-            self._pack = None                  # the next refresh_weights() covers them too
+            self._pack = None                  # the next refresh_weights() covers them too ...
+            self._graphs = {}                  # ... so captured forward graphs (old packing plan) are dropped
         self._bwd.run(grads)
         return self._bwd

@@ -173,7 +173,7 @@ class _TrainFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, eng, x, *params):
-        outs = eng.forward(x)
+        outs = eng.forward(x, getattr(eng, "_refresh_next", False))
         ctx.eng, ctx.params = eng, params
         return tuple(o.detach() for o in outs)
 
@@ -273,13 +273,13 @@ class Model(nn.Module):
             from .train_engine import TrainEngine
             key = ("train", tuple(x.shape), x.device.index)
             eng = self._engines.get(key)
+            refresh = eng is not None          # an existing plan re-packs the (possibly updated) parameters first
             if eng is None:
                 eng = self._engines[key] = TrainEngine(self, x.shape[0], x.shape[2], x.shape[3], x.device)
-            else:
-                eng.refresh_weights()
+            eng._refresh_next = refresh
             self._last_train_engine = eng
             if not torch.is_grad_enabled():
-                return eng.forward(x)
+                return eng.forward(x, refresh)
             params = [p for p in self.parameters() if p.requires_grad]
             return list(_TrainFn.apply(eng, x, *params))
         from .engine import InferenceEngine
