@@ -353,8 +353,10 @@ def run_ours(args):
     conv_handles = {c._h.value for c in eng.convs}
 
     def step_device():
+        """pre-process + forward + NMS of one resident batch; the result stays on the device as the packed
+        ([B, max_det, 7], rows per image) pair, so consecutive steps queue back to back (no host read per step)."""
         pred, _ = model(x_dev)
-        return non_max_suppression_obb(pred, CONF, IOU, multi_label=True, max_det=MAX_DET)
+        return non_max_suppression_obb(pred, CONF, IOU, multi_label=True, max_det=MAX_DET, return_packed="async")
 
     from yolov5_obb_b200.pipeline import DetectPipeline
     pipe = DetectPipeline(model, CONF, IOU, MAX_DET, multi_label=True, device=dev)
@@ -391,10 +393,16 @@ def run_ours(args):
     # nvidia-smi takes ~100 ms to start: launch it before the warm-up so that it is sampling (every 100 ms) while
     # the timed region runs; warm-up and timed steps are the same load
     sampler = ClockSampler(local) if rank == 0 else None
+    # one blocking call first: it sizes the candidate capacity for this workload (sticky hint, general._CAP_HINT)
+    non_max_suppression_obb(model(x_dev)[0], CONF, IOU, multi_label=True, max_det=MAX_DET)
     for _ in range(max(args.warmup, 3)):
         dets = step_device()
     ms_total, dets = timed(step_device, args.steps)
     clocks = sampler.stop() if sampler else None
+    rows = dets[1].tolist()
+    if rows[B] > dets[2] or min(rows[:B]) < 0:
+        raise RuntimeError("NMS candidate capacity exceeded in the timed steps: the measurement would be invalid")
+    det_per_img = float(sum(rows[:B])) / B
     ms_step = ms_total / args.steps
     value = world * B / (ms_step / 1e3)
 
@@ -463,10 +471,10 @@ def run_ours(args):
         "config": workload_config(args),
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(x_host.numel()),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps,
-                "api": "yolov5_obb_b200.pipeline.DetectPipeline (pinned host uint8 in, host detections out; H2D of batch "
-                       "i+1 overlapped with compute of batch i)"},
+                "api": "yolov5_obb_b200.pipeline.DetectPipeline (pinned host uint8 in, per-image host detections out; "
+                       "two-deep software pipeline: H2D of batch i+1 and host read-out of batch i-1 overlap batch i)"},
         "gpu_launches": (1 + len(eng.ops) + 10) * args.steps,
-        "detections_per_image": float(sum(d.shape[0] for d in dets)) / B,
+        "detections_per_image": det_per_img,
         "clocks": clocks, "roofline": roof,
     }
     if not args.no_cpu_baseline and world == 1:

@@ -1,0 +1,41 @@
+"""GPU test of the host-to-host detection pipeline (pipeline.DetectPipeline = the loop of detect.py:104-122 /
+val.py:183-207): the two-deep software pipeline (async H2D / async D2H) must yield, batch by batch, exactly what the
+blocking calls model(x) + non_max_suppression_obb(pred) give; and the packed / async return forms of
+non_max_suppression_obb are the same rows as the list form."""
+import pytest
+import torch
+
+from tests.modelgen import build_mirror
+from tests.tilegen import synth_tiles
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def test_pipeline_equals_blocking_calls():
+    from yolov5_obb_b200.general import non_max_suppression_obb
+    from yolov5_obb_b200.pipeline import DetectPipeline
+    m = build_mirror("n", nc=15, seed=0, obj_bias=1.0, cls_bias=-1.0, det_gain=6.0).to(DEV)
+    batches = [synth_tiles(2, 256, seed=s).pin_memory() for s in (1, 2, 3, 4, 5)]
+    kw = dict(conf_thres=0.25, iou_thres=0.45, multi_label=True, max_det=300)
+    want = []
+    for xb in batches:
+        pred, _ = m(xb.to(DEV))
+        dets = non_max_suppression_obb(pred, **kw)
+        packed, counts = non_max_suppression_obb(pred, return_packed=True, **kw)
+        out, cdev, cap = non_max_suppression_obb(pred, return_packed="async", **kw)
+        c = cdev.tolist()
+        assert c[2] <= cap, (c, cap)
+        assert c[:2] == counts == [d.shape[0] for d in dets], (c, counts, [d.shape[0] for d in dets])
+        for b in range(2):
+            assert torch.equal(packed[b, :counts[b]], dets[b]) and torch.equal(out[b, :counts[b]], dets[b])
+        want.append([d.cpu() for d in dets])
+    pipe = DetectPipeline(m, 0.25, 0.45, 300, multi_label=True, device=DEV)
+    got = list(pipe(iter(batches)))
+    assert len(got) == len(want)
+    assert sum(d.shape[0] for w in want for d in w) > 0
+    for g, w in zip(got, want):
+        assert len(g) == len(w)
+        for a, b in zip(g, w):
+            assert not a.is_cuda and torch.equal(a, b)
+    assert pipe.h2d_bytes == sum(x.numel() for x in batches)

@@ -188,7 +188,13 @@ __global__ void k_bn_finalize(const float* __restrict__ sum, const float* __rest
   }
 }
 
-__device__ __forceinline__ float silu_f(float u) { return u / (1.0f + __expf(-u)); }
+// sigmoid through the hardware tanh (one MUFU op, |rel err| ~ 2^-11: far below the bf16 the results are stored in)
+__device__ __forceinline__ float sigmoid_tanh(float u) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * u));
+  return fmaf(0.5f, t, 0.5f);
+}
+__device__ __forceinline__ float silu_f(float u) { return u * sigmoid_tanh(u); }
 
 // Column-persistent element-wise kernels: a thread keeps ONE 8-channel vector column (its per-channel coefficients live
 // in registers) and walks over pixels; `cols` threads side by side cover a pixel's vectors (coalesced), 256 / cols pixels
@@ -256,8 +262,8 @@ __global__ void __launch_bounds__(256) k_bn_silu_apply(const __nv_bfloat16* __re
 
 
 __device__ __forceinline__ float silu_grad(float u) {
-  const float sg = 1.0f / (1.0f + __expf(-u));
-  return sg * (1.0f + u * (1.0f - sg));
+  const float sg = sigmoid_tanh(u);
+  return fmaf(u * sg, 1.0f - sg, sg);
 }
 
 // per-channel sum(du) and sum(du * xhat), du = dy * act'(u), u = z*scale + shift, xhat = (z - mean) * invstd
@@ -280,16 +286,15 @@ __global__ void __launch_bounds__(STAT_THREADS) k_bn_bwd_reduce(const __nv_bfloa
     const bool active = cv < vecs && lane < lanes;
     float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (active) {
-      float sc[8], sh[8], mu[8], is[8];
+      float sc[8], sh[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         sc[k] = scale[cv * 8 + k];
         sh[k] = shift[cv * 8 + k];
-        mu[k] = mean[cv * 8 + k];
-        is[k] = invstd[cv * 8 + k];
       }
       const __nv_bfloat16* zb = z + cv * 8;
       const __nv_bfloat16* db = dy + cv * 8;
+      // q accumulates sum(du * z); sum(du * xhat) = invstd * (sum(du * z) - mean * sum(du)) is formed once per block
       long long p = p0 + lane;
       for (; p + lanes < p1; p += 2LL * lanes) {  // two pixels (four 16-byte loads) in flight
         const uint4 z0 = *reinterpret_cast<const uint4*>(zb + p * z_stride);
@@ -303,7 +308,7 @@ __global__ void __launch_bounds__(STAT_THREADS) k_bn_bwd_reduce(const __nv_bfloa
         for (int k = 0; k < 8; ++k) {
           const float du = act ? df[k] * silu_grad(fmaf(zf[k], sc[k], sh[k])) : df[k];
           s[k] += du;
-          q[k] = fmaf(du, (zf[k] - mu[k]) * is[k], q[k]);
+          q[k] = fmaf(du, zf[k], q[k]);
         }
         unpack8(z1, zf);
         unpack8(d1, df);
@@ -311,7 +316,7 @@ __global__ void __launch_bounds__(STAT_THREADS) k_bn_bwd_reduce(const __nv_bfloa
         for (int k = 0; k < 8; ++k) {
           const float du = act ? df[k] * silu_grad(fmaf(zf[k], sc[k], sh[k])) : df[k];
           s[k] += du;
-          q[k] = fmaf(du, (zf[k] - mu[k]) * is[k], q[k]);
+          q[k] = fmaf(du, zf[k], q[k]);
         }
       }
       for (; p < p1; p += lanes) {
@@ -322,9 +327,11 @@ __global__ void __launch_bounds__(STAT_THREADS) k_bn_bwd_reduce(const __nv_bfloa
         for (int k = 0; k < 8; ++k) {
           const float du = act ? df[k] * silu_grad(fmaf(zf[k], sc[k], sh[k])) : df[k];
           s[k] += du;
-          q[k] = fmaf(du, (zf[k] - mu[k]) * is[k], q[k]);
+          q[k] = fmaf(du, zf[k], q[k]);
         }
       }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) q[k] = invstd[cv * 8 + k] * (q[k] - mean[cv * 8 + k] * s[k]);
     }
     block_partials(s, q, red, cols, lanes, col_in, lane, active, cv, C, partial);
   }
@@ -551,8 +558,8 @@ __global__ void k_detect_grad_pack1(const float* __restrict__ g, __nv_bfloat16* 
   }
 }
 
-int stat_blocks_max() { return sm_count() * 2; }
-// blocks of the two-stage reductions: >= 16 pixels per thread, at most 2 blocks per SM (every block adds a partial row)
+int stat_blocks_max() { return sm_count() * 4; }
+// blocks of the two-stage reductions: >= 16 pixels per thread, at most 4 blocks per SM (every block adds a partial row)
 int stat_blocks(long long npix, int C) {
   const int vecs = C / 8;
   const int cols = std::min(vecs, STAT_THREADS);

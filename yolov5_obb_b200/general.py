@@ -42,27 +42,44 @@ def non_max_suppression_obb(prediction: torch.Tensor, conf_thres: float = 0.25, 
         mask = 0
         for c in classes:
             mask |= 1 << int(c)
-    L = _lib.lib()
-    out = torch.empty((B, max_det, 7), dtype=torch.float32, device=dev)
-    counts = torch.empty(B + 1, dtype=torch.int64, device=dev)
     worst = B * A * (nc if (multi_label and nc > 1) else 1)
     # optimistic capacity (every kernel of the pipeline runs over `cap` slots); grown on overflow below
-    cap = min(worst, max(B * 8192, 1 << 16))
+    cap = min(worst, max(B * 8192, 1 << 16, int(_CAP_HINT.get((B, A, nc), 0))))
+    args = (pred, B, A, no, nc, conf_thres, iou_thres, mask, agnostic, multi_label, max_det)
+    if return_packed == "async":
+        # no host read at all: (device [B, max_det, 7], device int64 [B + 1] = rows per image + total candidates, cap).
+        # The caller checks counts[B] <= cap when it reads the counts (pipeline.DetectPipeline does, and re-runs).
+        out, counts = _launch(args, cap)
+        return out, counts, cap
     while True:
-        with torch.cuda.device(dev):
-            nbytes = L.y5obb_nms_obb_workspace_bytes(B, A, cap, MAX_NMS)
-            ws = _lib.workspace(nbytes, dev, "nms_obb")
-            rc = L.y5obb_nms_obb_f32(pred.data_ptr(), B, A, no, nc, float(conf_thres), float(iou_thres), mask,
-                                     int(bool(agnostic)), int(bool(multi_label)), int(max_det), MAX_NMS, float(MAX_WH),
-                                     _lib.NMS_STRICT_GT, cap, out.data_ptr(), counts.data_ptr(), ws.data_ptr(),
-                                     ws.numel(), _lib.stream_ptr(dev))
-        _lib.check(rc, "y5obb_nms_obb_f32")
+        out, counts = _launch(args, cap)
         c = counts.tolist()  # the one host read: rows per image (+ total candidates)
         if c[B] <= cap:
             break
         cap = min(worst, max(c[B], cap * 4))  # rare: more candidates than the optimistic capacity
+        _CAP_HINT[(B, A, nc)] = cap
     if any(k < 0 for k in c[:B]):
         raise RuntimeError("y5obb_nms_obb_f32: internal capacity error")
     if return_packed:  # (device [B, max_det, 7], per-image row counts) — one buffer for a single D2H copy
         return out, c[:B]
     return [out[b, :c[b]] for b in range(B)]
+
+
+_CAP_HINT = {}  # (B, anchors, nc) -> candidate capacity that was needed once (sticky: avoids repeated overflow re-runs)
+
+
+def _launch(args, cap):
+    pred, B, A, no, nc, conf_thres, iou_thres, mask, agnostic, multi_label, max_det = args
+    L = _lib.lib()
+    dev = pred.device
+    out = torch.empty((B, max_det, 7), dtype=torch.float32, device=dev)
+    counts = torch.empty(B + 1, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        nbytes = L.y5obb_nms_obb_workspace_bytes(B, A, cap, MAX_NMS)
+        ws = _lib.workspace(nbytes, dev, "nms_obb")
+        rc = L.y5obb_nms_obb_f32(pred.data_ptr(), B, A, no, nc, float(conf_thres), float(iou_thres), mask,
+                                 int(bool(agnostic)), int(bool(multi_label)), int(max_det), MAX_NMS, float(MAX_WH),
+                                 _lib.NMS_STRICT_GT, cap, out.data_ptr(), counts.data_ptr(), ws.data_ptr(),
+                                 ws.numel(), _lib.stream_ptr(dev))
+    _lib.check(rc, "y5obb_nms_obb_f32")
+    return out, counts

@@ -1,6 +1,8 @@
 """End-to-end detection pipeline from HOST images: the loop of /root/reference/detect.py:104-122 and
-val.py:183-207 (pre-process, inference, NMS) with the host->device copy of batch i+1 overlapped with the
-compute of batch i on a second stream (two device input buffers, event-ordered)."""
+val.py:183-207 (pre-process, inference, NMS), software-pipelined two deep: the host->device copy of batch i+1 runs on
+a second stream while batch i computes (two device input buffers, event-ordered), and the device->host copy of batch
+i's detections is asynchronous, so the host turns batch i-1 into per-image tensors while the GPU works on batch i
+(the stream is never drained inside the loop)."""
 from typing import Iterable, Iterator, List
 
 import torch
@@ -24,11 +26,12 @@ class DetectPipeline:
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
-    def _host_out(self, B, max_det):
-        h = getattr(self, "_hout", None)
-        if h is None or h.shape[0] != B or h.shape[1] != max_det:
-            self._hout = torch.empty((B, max_det, 7), dtype=torch.float32).pin_memory()
-        return self._hout
+    def _host_slot(self, slot, B, max_det):
+        hs = getattr(self, "_hslots", None)
+        if hs is None or hs[0][0].shape[0] != B or hs[0][0].shape[1] != max_det:
+            self._hslots = hs = [(torch.empty((B, max_det, 7), dtype=torch.float32).pin_memory(),
+                                  torch.empty(B + 1, dtype=torch.int64).pin_memory(), torch.cuda.Event()) for _ in range(2)]
+        return hs[slot]
 
     def _upload(self, slot: int, x_host: torch.Tensor, first_use: bool) -> None:
         if self._bufs[slot] is None or self._bufs[slot].shape != x_host.shape or self._bufs[slot].dtype != x_host.dtype:
@@ -52,6 +55,7 @@ class DetectPipeline:
         self._upload(0, cur, True)
         used[0] = True
         i = 0
+        pending = None
         compute = torch.cuda.current_stream(self.device)
         while cur is not None:
             slot = i & 1
@@ -62,13 +66,28 @@ class DetectPipeline:
             compute.wait_event(self._copied[slot])
             pred, _ = self.model(self._bufs[slot])
             self._consumed[slot].record(compute)  # the first kernel has consumed the input by now (stream order)
-            packed, counts = non_max_suppression_obb(pred, return_packed=True, **self.kw)
-            kmax = max(counts) if counts else 0
-            host = self._host_out(packed.shape[0], packed.shape[1])
-            if kmax:
-                host[:, :kmax].copy_(packed[:, :kmax], non_blocking=True)  # D2H of this batch's result, one copy
-                compute.synchronize()
-            self.d2h_bytes += packed.shape[0] * kmax * 7 * 4
-            yield [host[b, :k].clone() for b, k in enumerate(counts)]
+            packed, counts, cap = non_max_suppression_obb(pred, return_packed="async", **self.kw)
+            hout, hcnt, ev = self._host_slot(slot, packed.shape[0], packed.shape[1])
+            hout.copy_(packed, non_blocking=True)   # D2H of this batch's result, one copy; nobody waits for it here
+            hcnt.copy_(counts, non_blocking=True)
+            ev.record(compute)
+            self.d2h_bytes += packed.numel() * 4 + counts.numel() * 8
+            if pending is not None:
+                yield self._finish(pending)
+            pending = (hout, hcnt, ev, cap, cur)
             cur = nxt
             i += 1
+        if pending is not None:
+            yield self._finish(pending)
+
+    def _finish(self, pending):
+        hout, hcnt, ev, cap, x_host = pending
+        ev.synchronize()
+        c = hcnt.tolist()
+        B = len(c) - 1
+        if c[B] > cap or any(k < 0 for k in c[:B]):  # rare: more candidates than the optimistic capacity -> re-run, blocking
+            pred, _ = self.model(x_host.to(self.device))
+            packed, counts = non_max_suppression_obb(pred, return_packed=True, **self.kw)
+            host = packed.cpu()
+            return [host[b, :k].clone() for b, k in enumerate(counts)]
+        return [hout[b, :k].clone() for b, k in enumerate(c[:B])]
