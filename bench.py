@@ -445,8 +445,14 @@ def run_ours(args):
     conv_ms = [sum(evs[s][i][0].elapsed_time(evs[s][i][1]) for s in range(steps_r)) / steps_r for i in range(n_conv)]
     tot_conv_ms = sum(conv_ms)
     ach_tflops = sum(conv_flops) / (tot_conv_ms / 1e3) / 1e12
+    traffic, traffic_src = None, None
+    tp = ROOT / "profiles" / "r1_conv_traffic.json"   # dram__bytes_read+write per launch from one `ncu --set full` capture
+    if tp.exists() and args.model == MODEL and B == BATCH:
+        tj = json.loads(tp.read_text())
+        traffic, traffic_src = tj["dram_bytes_per_launch_mean"], tj["source"]
     roof = {"bound": "tensor", "kernel": "conv_tc_kernel", "achieved": ach_tflops, "peak": pk["tflops"],
-            "unit": "TFLOP/s", "frac": ach_tflops / pk["tflops"], "traffic": None, "peak_source": pk["src"],
+            "unit": "TFLOP/s", "frac": ach_tflops / pk["tflops"], "traffic": traffic, "traffic_source": traffic_src,
+            "algorithmic_bytes_per_launch": eng.hbm_bytes / n_conv, "peak_source": pk["src"],
             "launches_per_step": n_conv, "flops_per_launch": sum(conv_flops) / n_conv,
             "mean_launch_us": tot_conv_ms / n_conv * 1e3, "conv_share_of_step": tot_conv_ms / ms_step,
             "hbm_view": {"algorithmic_GB_per_step": eng.hbm_bytes / 1e9,

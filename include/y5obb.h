@@ -199,6 +199,10 @@ int y5obb_gaussian_label(const double* angle_deg, float* csl_out, int64_t n, int
 int64_t y5obb_bn_scratch_floats(int C);  /* scratch (fp32 elements) the two reductions below need for C channels */
 int y5obb_bn_stats(const void* z, int64_t z_pix_stride, int64_t npix, int C, float* sum, float* sumsq, float* scratch,
                    int64_t scratch_floats, void* stream);
+/* y5obb_bn_stats + y5obb_bn_finalize in two launches (block partials; ordered reduction + finalisation) */
+int y5obb_bn_batch_stats(const void* z, int64_t z_pix_stride, int64_t npix, int C, const float* gamma, const float* beta,
+                         float eps, float momentum, float* running_mean, float* running_var, float* scale, float* shift,
+                         float* mean_out, float* invstd_out, float* scratch, int64_t scratch_floats, void* stream);
 int y5obb_bn_finalize(const float* sum, const float* sumsq, int64_t npix, int C, const float* gamma, const float* beta,
                       float eps, float momentum, float* running_mean, float* running_var, float* scale, float* shift,
                       float* mean_out, float* invstd_out, void* stream);

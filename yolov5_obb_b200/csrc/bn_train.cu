@@ -164,6 +164,50 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict
   }
 }
 
+// k_reduce_partials + k_bn_finalize in one launch: thread (seg, col) adds rows seg, seg + 32, ... of BOTH statistics of
+// channel c, thread (0, col) adds the 32 segment sums in order and finalises the channel.
+__global__ void __launch_bounds__(256) k_reduce_finalize(const float* __restrict__ partial, int blocks, long long npix, int C,
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                         float eps, float momentum, float* __restrict__ running_mean,
+                                                         float* __restrict__ running_var, float* __restrict__ scale,
+                                                         float* __restrict__ shift, float* __restrict__ mean_out,
+                                                         float* __restrict__ invstd_out) {
+  __shared__ float red[2][32][8];
+  const int col = threadIdx.x & 7, seg = threadIdx.x >> 3;
+  const int c = blockIdx.x * 8 + col;
+  float a = 0.f, b = 0.f;
+  if (c < C)
+    for (int r = seg; r < blocks; r += 32) {
+      a += partial[(long long)r * 2 * C + c];
+      b += partial[(long long)r * 2 * C + C + c];
+    }
+  red[0][seg][col] = a;
+  red[1][seg][col] = b;
+  __syncthreads();
+  if (seg != 0 || c >= C) return;
+  float sum = red[0][0][col], sumsq = red[1][0][col];
+#pragma unroll
+  for (int s2 = 1; s2 < 32; ++s2) {
+    sum += red[0][s2][col];
+    sumsq += red[1][s2][col];
+  }
+  const double n = (double)npix;
+  const double m = (double)sum / n;
+  double var = (double)sumsq / n - m * m;
+  if (var < 0) var = 0;
+  const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float sc = gamma[c] * invstd;
+  scale[c] = sc;
+  shift[c] = beta[c] - (float)m * sc;
+  mean_out[c] = (float)m;
+  invstd_out[c] = invstd;
+  if (running_mean) {
+    const double unbiased = n > 1 ? var * n / (n - 1.0) : var;
+    running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * (float)m;
+    running_var[c] = (1.0f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
 __global__ void k_bn_finalize(const float* __restrict__ sum, const float* __restrict__ sumsq, long long npix, int C,
                               const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
                               float* __restrict__ running_mean, float* __restrict__ running_var,
@@ -588,6 +632,26 @@ int y5obb_bn_stats(const void* z, int64_t z_pix_stride, int64_t npix, int C, flo
   k_bn_stats<<<blocks, STAT_THREADS, 0, st>>>(static_cast<const __nv_bfloat16*>(z), z_pix_stride, npix, C, chunk, scratch);
   Y5_LAUNCH_CHECK();
   k_reduce_partials<<<(2 * C + 7) / 8, 256, 0, st>>>(scratch, blocks, C, sum, sumsq, nullptr, nullptr, 0);
+  Y5_LAUNCH_CHECK();
+  return Y5OBB_OK;
+}
+
+int y5obb_bn_batch_stats(const void* z, int64_t z_pix_stride, int64_t npix, int C, const float* gamma, const float* beta,
+                         float eps, float momentum, float* running_mean, float* running_var, float* scale, float* shift,
+                         float* mean_out, float* invstd_out, float* scratch, int64_t scratch_floats, void* stream) {
+  if (!z || !gamma || !beta || !scale || !shift || !mean_out || !invstd_out || !scratch || npix <= 0 || C <= 0 || (C & 7) ||
+      (z_pix_stride & 7))
+    return Y5OBB_EINVAL;
+  if ((running_mean == nullptr) != (running_var == nullptr)) return Y5OBB_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(scratch)) & 15) return Y5OBB_EINVAL;
+  const int blocks = stat_blocks(npix, C);
+  if (scratch_floats < (int64_t)blocks * 2 * C) return Y5OBB_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long chunk = (npix + blocks - 1) / blocks;
+  k_bn_stats<<<blocks, STAT_THREADS, 0, st>>>(static_cast<const __nv_bfloat16*>(z), z_pix_stride, npix, C, chunk, scratch);
+  Y5_LAUNCH_CHECK();
+  k_reduce_finalize<<<(C + 7) / 8, 256, 0, st>>>(scratch, blocks, npix, C, gamma, beta, eps, momentum, running_mean,
+                                                 running_var, scale, shift, mean_out, invstd_out);
   Y5_LAUNCH_CHECK();
   return Y5OBB_OK;
 }

@@ -59,6 +59,9 @@ class InferenceEngine:
             raise RuntimeError(f"image size {H}x{W} must be a multiple of the max stride {smax}")
         self.device, self.B, self.H, self.W = device, B, H, W
         self.ops = []          # (callable taking stream ptr)
+        import os
+        self._calls, self._graph = 0, None
+        self._use_graph = os.environ.get("Y5OBB_NO_GRAPH", "0") != "1"
         self.convs: List[ConvOp] = []
         self.keep = []         # buffers
         self.flops = 0.0
@@ -245,8 +248,23 @@ class InferenceEngine:
                 x = x.contiguous().float()
                 _lib.check(L.y5obb_stem_s2d(x.data_ptr(), self.x_s2d.data_ptr(), self.B, self.H, self.W, 1, st),
                            "y5obb_stem_s2d")
-            for op in self.ops:
-                rc = op(st)
-                if rc:
-                    _lib.check(rc, "engine op")
+            # the layer sequence is fixed (same buffers every call): from the third call on it is replayed as one CUDA
+            # graph - the layout pass above stays outside because it reads the caller's tensor (Y5OBB_NO_GRAPH=1 disables)
+            self._calls += 1
+            if self._use_graph and self._calls > 2:
+                if self._graph is None:
+                    torch.cuda.synchronize(self.device)
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                        self._run_ops(_lib.stream_ptr(self.device))
+                    self._graph = g
+                self._graph.replay()
+            else:
+                self._run_ops(st)
         return self.pred
+
+    def _run_ops(self, st):
+        for op in self.ops:
+            rc = op(st)
+            if rc:
+                _lib.check(rc, "engine op")

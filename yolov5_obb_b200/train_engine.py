@@ -285,12 +285,10 @@ class TrainEngine:
                 z, y = lay.z, lay.y
                 npix = z.B * z.H * z.W
                 bn = lay.mod.bn
-                run("bn_stats", lambda: L.y5obb_bn_stats(z.ptr, z.pix_stride, npix, z.C, lay.sum.data_ptr(), lay.sumsq.data_ptr(),
-                                                         self.scratch.data_ptr(), self.scratch.numel(), st))
-                run("bn_finalize", lambda: L.y5obb_bn_finalize(
-                    lay.sum.data_ptr(), lay.sumsq.data_ptr(), npix, z.C, bn.weight.data_ptr(), bn.bias.data_ptr(),
-                    float(bn.eps), float(bn.momentum), bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
-                    lay.scale.data_ptr(), lay.shift.data_ptr(), lay.mean.data_ptr(), lay.invstd.data_ptr(), st))
+                run("bn_stats", lambda: L.y5obb_bn_batch_stats(
+                    z.ptr, z.pix_stride, npix, z.C, bn.weight.data_ptr(), bn.bias.data_ptr(), float(bn.eps), float(bn.momentum),
+                    bn.running_mean.data_ptr(), bn.running_var.data_ptr(), lay.scale.data_ptr(), lay.shift.data_ptr(),
+                    lay.mean.data_ptr(), lay.invstd.data_ptr(), self.scratch.data_ptr(), self.scratch.numel(), st))
                 run("bn_apply", lambda: L.y5obb_bn_silu_apply(
                     z.ptr, z.pix_stride, npix, z.C, z.W, lay.scale.data_ptr(), lay.shift.data_ptr(), int(lay.act),
                     lay.res.ptr if lay.res else None, lay.res.pix_stride if lay.res else 0, y.ptr, y.pix_stride,
