@@ -400,7 +400,7 @@ def run_ours(args):
     ms_total, dets = timed(step_device, args.steps)
     clocks = sampler.stop() if sampler else None
     rows = dets[1].tolist()
-    if rows[B] > dets[2] or min(rows[:B]) < 0:
+    if rows[B] > dets[2] or min(rows) < 0:
         raise RuntimeError("NMS candidate capacity exceeded in the timed steps: the measurement would be invalid")
     det_per_img = float(sum(rows[:B])) / B
     ms_step = ms_total / args.steps

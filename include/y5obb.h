@@ -39,6 +39,12 @@ const char* y5obb_build_info(void);     /* "sm_100a nvcc <ver> <date>" */
 #define Y5OBB_NMS_STRICT_GT 1   /* suppress if IoU >  thr (reference CUDA, nms_rotated_cuda.cu:60); else */
                                 /* suppress if IoU >= thr (reference CPU, nms_rotated_cpu.cpp:55)         */
 #define Y5OBB_NMS_DROP_SMALL 2  /* boxes with min(w,h) < 0.001 never enter NMS (nms_rotated_wrapper.py:32) */
+#define Y5OBB_NMS_NO_CLASS_SPLIT 4  /* y5obb_nms_obb_f32 only: run ONE greedy pass per image over the class-offset boxes
+                                       exactly as general.py:849-853 does, instead of independent (image, class)
+                                       passes.  The split is the default when classes are offset (not agnostic); it
+                                       gives the same rows whenever boxes of different classes cannot overlap, which
+                                       the kernel verifies per box (r + max(|cx|,|cy|) < max_wh/2 - 8); if the test
+                                       fails counts[batch] comes back as -2 and the caller re-runs with this flag */
 
 /* Workspace needed for n_total boxes over n_images images with at most max_per_image boxes in any one
  * image (pass n_total if unknown). */

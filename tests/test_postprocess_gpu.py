@@ -66,3 +66,33 @@ def test_edge_cases():
         non_max_suppression_obb(torch.from_numpy(pred), 0.25, 0.45)
     with pytest.raises(AssertionError):
         non_max_suppression_obb(torch.from_numpy(pred).to(DEV), 1.5, 0.45)
+
+
+def test_class_split_equals_single_pass_and_falls_back():
+    """The (image, class) decomposition of the greedy pass gives exactly the rows of the reference's one pass over the
+    class-offset boxes; a box large enough to reach another class's offset copy makes the kernel report -2 and the
+    wrapper re-run in the one-pass form (still equal to the CPU restatement)."""
+    import yolov5_obb_b200.general as G
+    from yolov5_obb_b200 import _lib
+    pred = synth_pred(3, 20000, 15, 21, frac_obj=0.05)
+    kw = dict(conf_thres=0.25, iou_thres=0.45, multi_label=True, max_det=1500)
+    G._NO_SPLIT.clear()
+    split = _run(pred, **kw)
+    assert not G._NO_SPLIT                                     # synthetic DOTA-sized boxes: the shortcut applied
+    G._NO_SPLIT[(3, 20000, 15)] = True
+    single = _run(pred, **kw)
+    G._NO_SPLIT.clear()
+    for a, b in zip(split, single):
+        assert torch.equal(a, b)
+    # a 6000-px box among the candidates: classes are no longer separated by the 4096 offset
+    far = pred.copy()
+    far[0, 0, :4] = (500.0, 500.0, 6000.0, 50.0)
+    far[0, 0, 4] = 0.99
+    far[0, 0, 5:20] = 0.9
+    got = _run(far, **kw)
+    assert G._NO_SPLIT.get((3, 20000, 15)) is True             # the wrapper saw -2 and re-ran
+    exp = oracle_nms(torch.from_numpy(far), nms_mode=1, **kw)
+    G._NO_SPLIT.clear()
+    for b in range(3):
+        g, e = got[b].cpu().numpy(), exp[b].numpy()
+        assert g.shape == e.shape and (g == e).all(1).mean() > 0.995

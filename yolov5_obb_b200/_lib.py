@@ -75,6 +75,7 @@ PROTOTYPES = {
 
 NMS_STRICT_GT = 1
 NMS_DROP_SMALL = 2
+NMS_NO_CLASS_SPLIT = 4
 
 
 def lib() -> ctypes.CDLL:

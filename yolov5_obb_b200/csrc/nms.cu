@@ -499,6 +499,7 @@ struct PPArgs {
   int multi_label, agnostic;
   unsigned long long class_mask;  // bit j set = class j allowed
   float max_wh;
+  int* far_flag;  // set when a box is so large / far out that boxes of different classes could touch despite the offset
 };
 
 __global__ void k_pp_count(PPArgs a, int* __restrict__ cnt) {
@@ -580,6 +581,10 @@ __global__ void k_pp_emit(PPArgs a, const int* __restrict__ cnt, const int* __re
   const float cx = p[0], cy = p[1], w = p[2], h = p[3];
   const int img = (int)(row / a.A);
   long long base = off[row];
+  // class-split NMS is exact only if boxes of different classes cannot overlap: with r + max(|cx|, |cy|) < max_wh / 2
+  // for every box, two offset centres are further apart than the two circumradii (NaN fails the test)
+  if (lane == 0 && a.far_flag && !(0.5f * sqrtf(w * w + h * h) + fmaxf(fabsf(cx), fabsf(cy)) < 0.5f * a.max_wh - 8.0f))
+    atomicOr(a.far_flag, 1);
 
   auto put = [&](long long slot, int cls, float sc) {
     if (slot >= capacity) return;
@@ -641,19 +646,97 @@ __global__ void k_pp_emit(PPArgs a, const int* __restrict__ cnt, const int* __re
 __global__ void k_pp_gather(const float* __restrict__ out7, const int64_t* __restrict__ keep,
                             const int64_t* __restrict__ n_keep, const int64_t* __restrict__ seg_off, int n_images,
                             int max_det, float* __restrict__ dst, int64_t* __restrict__ counts,
-                            const int64_t* __restrict__ n_valid) {
+                            const int64_t* __restrict__ n_valid, const int* __restrict__ far_flag) {
   const int b = blockIdx.y;
   const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long nk = n_keep[b];
   if (k == 0) {
     counts[b] = nk;
-    if (b == 0) counts[n_images] = n_valid[1];  // total candidates before the capacity clamp
+    // total candidates before the capacity clamp; -2 = the class-split shortcut was not applicable (a box large or far
+    // enough to reach another class's offset copy): the caller re-runs with Y5OBB_NMS_NO_CLASS_SPLIT
+    if (b == 0) counts[n_images] = (far_flag && *far_flag) ? -2 : n_valid[1];
   }
   if (k >= nk || k >= max_det) return;
   const float* s = out7 + keep[seg_off[b] + k] * 7;
   float* d = dst + ((long long)b * max_det + k) * 7;
 #pragma unroll
   for (int e = 0; e < 7; ++e) d[e] = s[e];
+}
+
+// ---- class-split NMS (the reference separates classes by adding cls * max_wh to the centres, general.py:849-851:
+// boxes of different classes never overlap, so the greedy pass decomposes into independent (image, class) problems:
+// sum_c n_c^2 pair tests instead of (sum_c n_c)^2) ---------------------------------------------------------------
+// key2 of the candidate at score-sorted position pos: ((image * nc + cls) << 32), or the dump segment when the image's
+// top-max_nms clamp (general.py:845-846) or the dump image excludes it.  A stable sort on these bits keeps the score order.
+__global__ void k_class_keys(const uint64_t* __restrict__ keys1, const uint32_t* __restrict__ order1,
+                             const int32_t* __restrict__ seg1_start, const float* __restrict__ out7, int64_t n,
+                             int n_images, int nc, int max_nms, uint64_t* __restrict__ keys2) {
+  const int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= n) return;
+  const int img = (int)(keys1[pos] >> 32);
+  uint32_t seg = (uint32_t)(n_images * nc);
+  if (img < n_images) {
+    const long long r = pos - seg1_start[img];
+    if (max_nms <= 0 || r < max_nms) {
+      int cls = (int)out7[(long long)order1[pos] * 7 + 6];
+      cls = min(max(cls, 0), nc - 1);
+      seg = (uint32_t)(img * nc + cls);
+    }
+  }
+  keys2[pos] = (uint64_t)seg << 32;
+}
+
+__global__ void k_flag_kept(const int64_t* __restrict__ keep, const int64_t* __restrict__ n_keep,
+                            const int64_t* __restrict__ seg_off, uint8_t* __restrict__ flag) {
+  const int s = blockIdx.y;
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n_keep[s]) flag[keep[seg_off[s] + k]] = 1;
+}
+
+// one CTA per image: the kept candidates of all its classes, in the image's score order, first max_det of them
+__global__ void __launch_bounds__(1024) k_merge_classes(const uint32_t* __restrict__ order1,
+                                                        const int32_t* __restrict__ seg1_start,
+                                                        const uint8_t* __restrict__ flag, const NmsCtrl* __restrict__ ctrl,
+                                                        int n_images, int max_nms, long long max_keep,
+                                                        int64_t* __restrict__ keep_out, int64_t* __restrict__ n_keep_out,
+                                                        int64_t* __restrict__ seg_off_out) {
+  __shared__ int s_warp[32];
+  __shared__ long long s_count;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const long long off = seg1_start[b];
+  long long nb = (long long)seg1_start[b + 1] - off;
+  if (max_nms > 0 && nb > max_nms) nb = max_nms;
+  if (tid == 0) {
+    seg_off_out[b] = off;
+    if (b == 0) seg_off_out[n_images] = seg1_start[n_images];
+    s_count = 0;
+  }
+  if (ctrl->err) {
+    if (tid == 0) n_keep_out[b] = -1;
+    return;
+  }
+  __syncthreads();
+  for (long long base = 0; base < nb; base += 1024) {
+    const long long p = base + tid;
+    const uint32_t cand = p < nb ? order1[off + p] : 0u;
+    const bool kept = p < nb && flag[cand];
+    const unsigned bal = __ballot_sync(0xffffffffu, kept);
+    if (lane == 0) s_warp[wid] = __popc(bal);
+    __syncthreads();
+    long long before = s_count;
+    for (int w2 = 0; w2 < wid; ++w2) before += s_warp[w2];
+    const long long idx = before + __popc(bal & ((1u << lane) - 1u));
+    if (kept && (max_keep <= 0 || idx < max_keep)) keep_out[off + idx] = (int64_t)cand;
+    __syncthreads();
+    if (tid == 0) {
+      long long t = s_count;
+      for (int w2 = 0; w2 < 32; ++w2) t += s_warp[w2];
+      s_count = t;
+    }
+    __syncthreads();
+    if (max_keep > 0 && s_count >= max_keep) break;
+  }
+  if (tid == 0) n_keep_out[b] = (max_keep > 0 && s_count > max_keep) ? max_keep : s_count;
 }
 
 struct PPWs {
@@ -665,6 +748,13 @@ struct PPWs {
   int64_t *n_valid, *keep, *n_keep, *seg_off;
   void* nms_ws;
   size_t nms_bytes;
+  // class-split path
+  uint64_t *keys2_a, *keys2_b;
+  uint32_t *vals2_a, *order2;
+  int32_t* seg1_start;
+  uint8_t* keepflag;
+  int64_t *keepC, *n_keepC, *seg_offC;
+  int* far_flag;
   size_t total;
 };
 
@@ -678,7 +768,7 @@ size_t scan_bytes_for(long long rows) {
   return bytes;
 }
 
-PPWs carve_pp(void* base, long long rows, int n_images, long long capacity, int max_nms) {
+PPWs carve_pp(void* base, long long rows, int n_images, long long capacity, int max_nms, int nc) {
   PPWs w;
   Carver c(base);
   w.cnt = c.take<int>(rows);
@@ -694,11 +784,90 @@ PPWs carve_pp(void* base, long long rows, int n_images, long long capacity, int 
   w.n_keep = c.take<int64_t>(n_images);
   w.seg_off = c.take<int64_t>(n_images + 1);
   long long mpi = max_nms > 0 && max_nms < capacity ? max_nms : capacity;
-  NmsWs nw = carve_nms(nullptr, capacity, n_images, mpi);
+  const long long n_seg = (long long)n_images * nc;
+  NmsWs nw = carve_nms(nullptr, capacity, n_seg, mpi);  // the (image, class) segmentation needs the larger tables
   w.nms_bytes = nw.total + 256;
   w.nms_ws = c.take<char>(w.nms_bytes);
+  w.keys2_a = c.take<uint64_t>(capacity);
+  w.keys2_b = c.take<uint64_t>(capacity);
+  w.vals2_a = c.take<uint32_t>(capacity);
+  w.order2 = c.take<uint32_t>(capacity);
+  w.seg1_start = c.take<int32_t>(n_images + 2);
+  w.keepflag = c.take<uint8_t>(capacity);
+  w.keepC = c.take<int64_t>(capacity);
+  w.n_keepC = c.take<int64_t>(n_seg + 1);
+  w.seg_offC = c.take<int64_t>(n_seg + 2);
+  w.far_flag = c.take<int>(4);
   w.total = c.used();
   return w;
+}
+
+// Class-split variant of nms_impl for the post-process path (every candidate carries its class in out7[6]).
+// Same outputs as nms_impl: keep_out[seg_off_out[b] + k], k < n_keep_out[b], in descending score order per image.
+int nms_classes(const PPWs& w, const float* out7, int64_t n, int n_images, int nc, int64_t max_per_image, float thr, int flags,
+                int64_t max_keep, int max_nms, cudaStream_t st) {
+  const int n_seg = n_images * nc;
+  if (n_seg < 1 || n_seg >= MAX_IMAGES) return Y5OBB_EINVAL;
+  if (max_per_image <= 0 || max_per_image > n) max_per_image = n;
+  NmsWs ws = carve_nms(w.nms_ws, n, n_seg, max_per_image);
+  if (ws.total > w.nms_bytes) return Y5OBB_EWORKSPACE;
+  const unsigned g = (unsigned)((n + 255) / 256);
+  // 1. every image's candidates by descending score (ties: lower index), as the reference's argsort
+  k_make_keys<<<g, 256, 0, st>>>(w.dets5, w.scores, w.image_ids, n, n_images, flags, w.n_valid, ws.keys_a, ws.vals_a);
+  Y5_LAUNCH_CHECK();
+  int img_bits = 1;
+  while ((1ll << img_bits) <= n_images) ++img_bits;
+  size_t cub_bytes = ws.cub_bytes;
+  Y5_CUDA(cub::DeviceRadixSort::SortPairs(ws.cub_tmp, cub_bytes, ws.keys_a, ws.keys_b, ws.vals_a, ws.vals_b, (int)n, 0,
+                                          32 + img_bits, st));
+  k_segments<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(ws.keys_b, n, n_images, w.seg1_start);
+  Y5_LAUNCH_CHECK();
+  // 2. stable re-grouping by (image, class) of the top-max_nms of every image: score order survives inside a class
+  k_class_keys<<<g, 256, 0, st>>>(ws.keys_b, ws.vals_b, w.seg1_start, out7, n, n_images, nc, max_nms, w.keys2_a);
+  Y5_LAUNCH_CHECK();
+  int seg_bits = 1;
+  while ((1ll << seg_bits) <= n_seg) ++seg_bits;
+  cub_bytes = ws.cub_bytes;
+  Y5_CUDA(cub::DeviceRadixSort::SortPairs(ws.cub_tmp, cub_bytes, w.keys2_a, w.keys2_b, ws.vals_b, w.order2, (int)n, 32,
+                                          32 + seg_bits, st));
+  Y5_CUDA(cudaMemsetAsync(ws.rowflag, 0, (size_t)n, st));
+  Y5_CUDA(cudaMemsetAsync(w.keepflag, 0, (size_t)n, st));
+  k_segments<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(w.keys2_b, n, n_seg, ws.seg_start);
+  Y5_LAUNCH_CHECK();
+  k_plan<<<1, 32, 0, st>>>(ws.seg_start, n_seg, ws.mask_words, 0, ws.seg, ws.ctrl);
+  Y5_LAUNCH_CHECK();
+  k_prep<<<g, 256, 0, st>>>(w.dets5, w.order2, n, ws.pre);
+  Y5_LAUNCH_CHECK();
+  // 3. independent greedy passes per (image, class)
+  long long grid = (long long)sm_count() * 8;
+  {
+    const long long nb = (max_per_image + TB - 1) / TB;
+    const long long max_units = units_for(nb) * (n / max_per_image + 1) + n_seg;
+    if (grid > max_units) grid = max_units;
+    if (grid < 1) grid = 1;
+  }
+  k_tiles<<<(unsigned)grid, TILE_THREADS, 0, st>>>(ws.pre, ws.seg, n_seg, ws.ctrl, ws.mask, ws.rowflag, thr,
+                                                   (flags & Y5OBB_NMS_STRICT_GT) ? 1 : 0);
+  Y5_LAUNCH_CHECK();
+  const size_t smem = (size_t)((max_per_image + TB - 1) / TB) * sizeof(unsigned long long);
+  if (smem > 200 * 1024) return Y5OBB_EINVAL;
+  static size_t smem_set = 0;
+  if (smem > 32 * 1024 && smem > smem_set) {
+    Y5_CUDA(cudaFuncSetAttribute(k_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+    smem_set = 200 * 1024;
+  }
+  k_reduce<<<(unsigned)n_seg, REDUCE_THREADS, smem, st>>>(ws.seg, ws.ctrl, ws.mask, ws.rowflag, w.order2, (long long)max_keep,
+                                                         n_seg, w.keepC, w.n_keepC, w.seg_offC);
+  Y5_LAUNCH_CHECK();
+  // 4. merge: kept flags, then every image's keepers in its own score order, first max_keep of them
+  const long long per_seg = max_keep > 0 ? max_keep : max_per_image;
+  dim3 gf((unsigned)((per_seg + 255) / 256), (unsigned)n_seg);
+  k_flag_kept<<<gf, 256, 0, st>>>(w.keepC, w.n_keepC, w.seg_offC, w.keepflag);
+  Y5_LAUNCH_CHECK();
+  k_merge_classes<<<(unsigned)n_images, 1024, 0, st>>>(ws.vals_b, w.seg1_start, w.keepflag, ws.ctrl, n_images, max_nms,
+                                                      (long long)max_keep, w.keep, w.n_keep, w.seg_off);
+  Y5_LAUNCH_CHECK();
+  return Y5OBB_OK;
 }
 
 }  // namespace
@@ -744,7 +913,7 @@ int y5obb_nms_rotated_batched_f32(const float* dets5, const float* scores, const
 
 size_t y5obb_nms_obb_workspace_bytes(int64_t batch, int64_t anchors, int64_t max_candidates, int64_t max_nms) {
   if (batch <= 0 || anchors <= 0 || max_candidates <= 0) return 256;
-  PPWs w = carve_pp(nullptr, batch * anchors, (int)batch, max_candidates, (int)max_nms);
+  PPWs w = carve_pp(nullptr, batch * anchors, (int)batch, max_candidates, (int)max_nms, 64);
   return w.total + 256;
 }
 
@@ -758,7 +927,7 @@ int y5obb_nms_obb_f32(const float* pred, int64_t batch, int64_t anchors, int no,
   const long long rows = batch * anchors;
   if (rows > 0x7FFFFFF0ll || max_candidates > 0x7FFFFFF0ll) return Y5OBB_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
-  PPWs w = carve_pp(workspace, rows, (int)batch, max_candidates, max_nms);
+  PPWs w = carve_pp(workspace, rows, (int)batch, max_candidates, max_nms, nc);
   if (w.total > workspace_bytes) return Y5OBB_EWORKSPACE;
   PPArgs a;
   a.pred = pred;
@@ -771,6 +940,10 @@ int y5obb_nms_obb_f32(const float* pred, int64_t batch, int64_t anchors, int no,
   a.agnostic = agnostic;
   a.class_mask = class_mask;
   a.max_wh = max_wh;
+  // class-split NMS when the class offset separates the classes (not agnostic, > 1 class) and the caller did not veto it
+  const bool split = !agnostic && nc > 1 && !(flags & Y5OBB_NMS_NO_CLASS_SPLIT) && batch * (long long)nc < (1 << 16);
+  a.far_flag = split ? w.far_flag : nullptr;
+  if (split) Y5_CUDA(cudaMemsetAsync(w.far_flag, 0, sizeof(int), st));
   const unsigned g = (unsigned)((rows * 32 + 255) / 256);
   k_pp_count<<<g, 256, 0, st>>>(a, w.cnt);
   Y5_LAUNCH_CHECK();
@@ -779,12 +952,16 @@ int y5obb_nms_obb_f32(const float* pred, int64_t batch, int64_t anchors, int no,
   k_pp_emit<<<g, 256, 0, st>>>(a, w.cnt, w.off, max_candidates, w.dets5, w.scores, w.image_ids, w.out7, w.n_valid);
   Y5_LAUNCH_CHECK();
   long long mpi = max_nms > 0 && max_nms < max_candidates ? max_nms : max_candidates;
-  int rc = nms_impl(w.dets5, w.scores, w.image_ids, max_candidates, batch, mpi, iou_thres,
-                    flags | Y5OBB_NMS_DROP_SMALL, max_det, w.keep, w.n_keep, w.seg_off, w.nms_ws, w.nms_bytes, st,
-                    w.n_valid, max_nms);
+  int rc;
+  if (split)
+    rc = nms_classes(w, w.out7, max_candidates, (int)batch, nc, mpi, iou_thres, flags | Y5OBB_NMS_DROP_SMALL, max_det, max_nms, st);
+  else
+    rc = nms_impl(w.dets5, w.scores, w.image_ids, max_candidates, batch, mpi, iou_thres, flags | Y5OBB_NMS_DROP_SMALL,
+                  max_det, w.keep, w.n_keep, w.seg_off, w.nms_ws, w.nms_bytes, st, w.n_valid, max_nms);
   if (rc) return rc;
   dim3 gg((unsigned)((max_det + 127) / 128), (unsigned)batch);
-  k_pp_gather<<<gg, 128, 0, st>>>(w.out7, w.keep, w.n_keep, w.seg_off, (int)batch, max_det, out7, counts, w.n_valid);
+  k_pp_gather<<<gg, 128, 0, st>>>(w.out7, w.keep, w.n_keep, w.seg_off, (int)batch, max_det, out7, counts, w.n_valid,
+                                  split ? w.far_flag : nullptr);
   Y5_LAUNCH_CHECK();
   return Y5OBB_OK;
 }

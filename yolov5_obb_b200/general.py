@@ -45,7 +45,8 @@ def non_max_suppression_obb(prediction: torch.Tensor, conf_thres: float = 0.25, 
     worst = B * A * (nc if (multi_label and nc > 1) else 1)
     # optimistic capacity (every kernel of the pipeline runs over `cap` slots); grown on overflow below
     cap = min(worst, max(B * 8192, 1 << 16, int(_CAP_HINT.get((B, A, nc), 0))))
-    args = (pred, B, A, no, nc, conf_thres, iou_thres, mask, agnostic, multi_label, max_det)
+    nosplit = _NO_SPLIT.get((B, A, nc), False)
+    args = (pred, B, A, no, nc, conf_thres, iou_thres, mask, agnostic, multi_label, max_det, nosplit)
     if return_packed == "async":
         # no host read at all: (device [B, max_det, 7], device int64 [B + 1] = rows per image + total candidates, cap).
         # The caller checks counts[B] <= cap when it reads the counts (pipeline.DetectPipeline does, and re-runs).
@@ -54,6 +55,10 @@ def non_max_suppression_obb(prediction: torch.Tensor, conf_thres: float = 0.25, 
     while True:
         out, counts = _launch(args, cap)
         c = counts.tolist()  # the one host read: rows per image (+ total candidates)
+        if c[B] == -2:  # a box reaches another class's offset copy: the class-split shortcut is not exact here
+            _NO_SPLIT[(B, A, nc)] = True
+            args = args[:-1] + (True,)
+            continue
         if c[B] <= cap:
             break
         cap = min(worst, max(c[B], cap * 4))  # rare: more candidates than the optimistic capacity
@@ -65,11 +70,12 @@ def non_max_suppression_obb(prediction: torch.Tensor, conf_thres: float = 0.25, 
     return [out[b, :c[b]] for b in range(B)]
 
 
+_NO_SPLIT = {}  # (B, anchors, nc) -> True once a batch needed the one-pass-per-image form (sticky)
 _CAP_HINT = {}  # (B, anchors, nc) -> candidate capacity that was needed once (sticky: avoids repeated overflow re-runs)
 
 
 def _launch(args, cap):
-    pred, B, A, no, nc, conf_thres, iou_thres, mask, agnostic, multi_label, max_det = args
+    pred, B, A, no, nc, conf_thres, iou_thres, mask, agnostic, multi_label, max_det, nosplit = args
     L = _lib.lib()
     dev = pred.device
     out = torch.empty((B, max_det, 7), dtype=torch.float32, device=dev)
@@ -79,7 +85,8 @@ def _launch(args, cap):
         ws = _lib.workspace(nbytes, dev, "nms_obb")
         rc = L.y5obb_nms_obb_f32(pred.data_ptr(), B, A, no, nc, float(conf_thres), float(iou_thres), mask,
                                  int(bool(agnostic)), int(bool(multi_label)), int(max_det), MAX_NMS, float(MAX_WH),
-                                 _lib.NMS_STRICT_GT, cap, out.data_ptr(), counts.data_ptr(), ws.data_ptr(),
+                                 _lib.NMS_STRICT_GT | (_lib.NMS_NO_CLASS_SPLIT if nosplit else 0), cap, out.data_ptr(),
+                                 counts.data_ptr(), ws.data_ptr(),
                                  ws.numel(), _lib.stream_ptr(dev))
     _lib.check(rc, "y5obb_nms_obb_f32")
     return out, counts

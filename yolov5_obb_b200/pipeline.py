@@ -85,7 +85,7 @@ class DetectPipeline:
         ev.synchronize()
         c = hcnt.tolist()
         B = len(c) - 1
-        if c[B] > cap or any(k < 0 for k in c[:B]):  # rare: more candidates than the optimistic capacity -> re-run, blocking
+        if c[B] > cap or c[B] < 0 or any(k < 0 for k in c[:B]):  # rare: more candidates than the optimistic capacity -> re-run, blocking
             pred, _ = self.model(x_host.to(self.device))
             packed, counts = non_max_suppression_obb(pred, return_packed=True, **self.kw)
             host = packed.cpu()
