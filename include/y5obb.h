@@ -130,6 +130,12 @@ typedef struct {
   int det_decode;            /* 1: sigmoid + xy/wh decode (eval branch, yolo.py:71-74); 0: raw logits (train) */
   float det_stride;          /* level stride in pixels */
   float det_anchor[6];       /* anchor (w,h) in pixels for the 3 anchors of this level */
+  /* optional output geometry (MODE_CONV only; all 0 = derived / dense): the output has out_h x out_w pixels (rows and
+     columns of the input read beyond its extent are zero), and out / res pixels (b, h, w) live at
+     b * img_stride + h * row_stride + w * pix_stride (elements).  Used by the data gradient of stride-2 convolutions:
+     each output-pixel parity class is a 1- or 2-tap stride-1 convolution of dz written to every other pixel. */
+  int out_h, out_w;
+  int64_t out_row_stride, out_img_stride, res_row_stride, res_img_stride;
 } y5obb_conv_desc;
 
 int y5obb_conv_tiling(int cin, int cout, int mode, int det_no, int* block_k, int* block_n, int* cin_pad,
@@ -275,9 +281,12 @@ int y5obb_detect_grad_pack(const float* g, void* out_nhwc, int B, int na, int H,
  *   STEM          the 6x6/s2 stem as a 3x1 conv over the 48-channel space-to-depth window (KH=6,KW=6 in; 3 taps out)
  *   DETECT        rows grouped per anchor: group_real real rows padded to group_pad (models/yolo.py:49-65)
  *   DETECT_DGRAD  rows = Cin, cols grouped per anchor
- *   DETECT_BIAS   fp32 bias, grouped per anchor */
+ *   DETECT_BIAS   fp32 bias, grouped per anchor
+ *   DGRAD_S2      data gradient of a 3x3 / stride-2 / pad-1 conv for output-pixel parity (ph, pw) = (group_real >> 1,
+ *                 group_real & 1): rows = Cin, cols = Cout, (ph ? 2 : 1) x (pw ? 2 : 1) taps; tap t along an axis of parity 1
+ *                 is source tap (t == 0 ? 2 : 0), along an axis of parity 0 source tap 1 */
 enum { Y5OBB_PACK_FWD = 0, Y5OBB_PACK_DGRAD = 1, Y5OBB_PACK_STEM = 2, Y5OBB_PACK_DETECT = 3, Y5OBB_PACK_DETECT_DGRAD = 4,
-       Y5OBB_PACK_DETECT_BIAS = 5 };
+       Y5OBB_PACK_DETECT_BIAS = 5, Y5OBB_PACK_DGRAD_S2 = 6 };
 typedef struct y5obb_pack_plan y5obb_pack_plan_t;
 typedef struct {
   const float* src;

@@ -170,6 +170,14 @@ def test_pack_plan_matches_host_packing():
     for a in range(na):
         wT[:, a * bn:a * bn + no] = w.view(na, no, cin)[a].t()
     add(PACK_DETECT_DGRAD, w, pack_weights(wT.view(cin, na * bn, 1, 1), None)[0], no, bn)
+    from yolov5_obb_b200.train_ops import PACK_DGRAD_S2
+    w = torch.randn(96, 48, 3, 3, generator=g).to(DEV)          # stride-2 data gradient, one packing per output parity
+    for ph in range(2):
+        for pw in range(2):
+            kh = [2, 0] if ph else [1]
+            kw = [2, 0] if pw else [1]
+            sub = w[:, :, kh][:, :, :, kw]                       # [Cout, Cin, KH', KW'] in tap order
+            add(PACK_DGRAD_S2, w, pack_weights(sub.permute(1, 0, 2, 3).contiguous(), None)[0], ph * 2 + pw, 0)
     PackPlan(ent, DEV).run()
     torch.cuda.synchronize()
     for (kind, src, dst, _, _), ref in zip(ent, want):

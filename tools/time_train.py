@@ -58,6 +58,11 @@ wg = eng._bwd.prof["wgrad"][3:]   # first three are Detect levels
 top = sorted(zip(wg, parts), key=lambda t: -t[0])[:8]
 print("slowest wgrads:", "; ".join(f"{t*1e3:.0f}us {desc(p['lay'])} ({p['lay'].conv.info()['flops']/t/1e9:.0f} TF/s)" for t, p in top))
 dg = eng._bwd.prof["dgrad"][3:]
-dparts = [p for p in parts if "dgrad_wp" in p]
-top = sorted(zip(dg, dparts), key=lambda t: -t[0])[:8]
+dl = []
+for p in parts:  # stride-2 layers launch four parity-class convs
+    n = 1 if "dgrad_wp" in p else (4 if "dgrad_s2" in p else 0)
+    if n:
+        dl.append((sum(dg[:n]), p))
+        dg = dg[n:]
+top = sorted(dl, key=lambda t: -t[0])[:8]
 print("slowest dgrads:", "; ".join(f"{t*1e3:.0f}us {desc(p['lay'])} ({p['lay'].conv.info()['flops']/t/1e9:.0f} TF/s)" for t, p in top))

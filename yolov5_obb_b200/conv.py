@@ -28,6 +28,8 @@ class ConvDesc(ctypes.Structure):
         ("out2x", c_void_p), ("out2x_pix_stride", c_int64),
         ("det_out", c_void_p), ("det_rows_per_image", c_int64), ("det_row_off", c_int64),
         ("det_no", c_int), ("det_decode", c_int), ("det_stride", c_float), ("det_anchor", c_float * 6),
+        ("out_h", c_int), ("out_w", c_int), ("out_row_stride", c_int64), ("out_img_stride", c_int64),
+        ("res_row_stride", c_int64), ("res_img_stride", c_int64),
     ]
 
 
@@ -125,7 +127,10 @@ class Conv:
 
     def __init__(self, x, w_packed: torch.Tensor, bias_pad: torch.Tensor, cout: int, k, stride: int,
                  pad, act: bool, out: Optional[Slice] = None, res: Optional[Slice] = None,
-                 out2x: Optional[Slice] = None, det: Optional[dict] = None, flags: int = 0):
+                 out2x: Optional[Slice] = None, det: Optional[dict] = None, flags: int = 0,
+                 out_geom: Optional[dict] = None):
+        """out_geom (optional): dict(h, w, off, pix, row, img) - the output (and the residual, which must then be the same
+        slice) has h x w pixels at element offset `off` of the slice with pixel / row / image strides in elements."""
         _lib.require_cuda(x.buf, "conv input")
         kh, kw = (k, k) if isinstance(k, int) else k
         ph, pw = (pad, pad) if isinstance(pad, int) else pad
@@ -145,6 +150,14 @@ class Conv:
             d.out, d.out_pix_stride = out.ptr, out.pix_stride
         if res is not None:
             d.res, d.res_pix_stride = res.ptr, res.pix_stride
+        if out_geom is not None:
+            g = out_geom
+            d.out, d.out_pix_stride = out.ptr + 2 * g["off"], g["pix"]
+            d.out_h, d.out_w, d.out_row_stride, d.out_img_stride = g["h"], g["w"], g["row"], g["img"]
+            if res is not None:
+                assert res.ptr == out.ptr, "a strided residual must be the output slice itself (in-place accumulation)"
+                d.res, d.res_pix_stride = res.ptr + 2 * g["off"], g["pix"]
+                d.res_row_stride, d.res_img_stride = g["row"], g["img"]
         if out2x is not None:
             d.out2x, d.out2x_pix_stride = out2x.ptr, out2x.pix_stride
         if det:

@@ -90,7 +90,7 @@ struct ConvK {
   __nv_bfloat16* out;
   long long out_pix_stride;
   const __nv_bfloat16* res;
-  long long res_pix_stride;
+  long long res_pix_stride, res_row_stride, res_img_stride;
   __nv_bfloat16* out2x;
   long long out2x_pix_stride;
   // detect
@@ -458,7 +458,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       const uint32_t taddr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(q * 32) << 16);
 
       if (p.mode == MODE_CONV) {
-        const __nv_bfloat16* rrow = p.res ? p.res + pix * p.res_pix_stride + c.n0 : nullptr;
+        const __nv_bfloat16* rrow =
+            p.res ? p.res + (long long)c.b * p.res_img_stride + (long long)h * p.res_row_stride + (long long)w * p.res_pix_stride + c.n0
+                  : nullptr;
         __nv_bfloat16* urow = nullptr;
         if (p.out2x) urow = p.out2x + (((long long)c.b * 2 * p.Hout + 2 * h) * (2 * p.Wout) + 2 * w) * p.out2x_pix_stride + c.n0;
         const int nvalid = min(p.BN, p.Cout - c.n0);
@@ -644,8 +646,15 @@ int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
   ConvObj* o = new ConvObj();
   ConvK& k = o->k;
   memset(&k, 0, sizeof(k));
-  const int Hout = (d->Hin + 2 * d->pad_h - d->KH) / d->stride + 1;
-  const int Wout = (d->Win + 2 * d->pad_w - d->KW) / d->stride + 1;
+  const bool geom = d->out_h > 0 || d->out_w > 0 || d->out_row_stride || d->out_img_stride || d->res_row_stride || d->res_img_stride;
+  if (geom && (d->mode != MODE_CONV || d->out2x || d->out_h <= 0 || d->out_w <= 0 || !d->out_row_stride || !d->out_img_stride ||
+               (d->res && (!d->res_row_stride || !d->res_img_stride)) || (d->out_row_stride & 7) || (d->out_img_stride & 7) ||
+               (d->res_row_stride & 7) || (d->res_img_stride & 7))) {
+    delete o;
+    return Y5OBB_EINVAL;
+  }
+  const int Hout = geom ? d->out_h : (d->Hin + 2 * d->pad_h - d->KH) / d->stride + 1;
+  const int Wout = geom ? d->out_w : (d->Win + 2 * d->pad_w - d->KW) / d->stride + 1;
   k.B = d->B;
   k.Hout = Hout;
   k.Wout = Wout;
@@ -735,6 +744,8 @@ int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
   k.out_pix_stride = d->out_pix_stride;
   k.res = static_cast<const __nv_bfloat16*>(d->res);
   k.res_pix_stride = d->res_pix_stride;
+  k.res_row_stride = geom ? d->res_row_stride : d->res_pix_stride * Wout;
+  k.res_img_stride = geom ? d->res_img_stride : d->res_pix_stride * Wout * Hout;
   k.out2x = static_cast<__nv_bfloat16*>(d->out2x);
   k.out2x_pix_stride = d->out2x_pix_stride;
   k.det_out = d->det_out;
@@ -801,6 +812,10 @@ int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
     cuuint64_t dims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)Wout, (cuuint64_t)Hout, (cuuint64_t)d->B};
     cuuint64_t strides[3] = {(cuuint64_t)d->out_pix_stride * 2, (cuuint64_t)d->out_pix_stride * 2 * Wout,
                              (cuuint64_t)d->out_pix_stride * 2 * Wout * Hout};
+    if (geom) {
+      strides[1] = (cuuint64_t)d->out_row_stride * 2;
+      strides[2] = (cuuint64_t)d->out_img_stride * 2;
+    }
     cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)(32 / bw), 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = enc(&k.tmO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, d->out, dims, strides, box, es,

@@ -39,6 +39,14 @@ __device__ __forceinline__ float pack_value(const PackEntryK& e, int tap, int ro
       if (row >= e.Cin || col >= e.Cout) return 0.f;
       return e.src[(((long long)col * e.Cin + row) * e.KH + (e.KH - 1 - kh)) * e.KW + (e.KW - 1 - kw)];
     }
+    case Y5OBB_PACK_DGRAD_S2: {  // tap = th * KW' + tw of the parity class (ph, pw) = (g_real >> 1, g_real & 1)
+      if (row >= e.Cin || col >= e.Cout) return 0.f;
+      const int ph = e.g_real >> 1, pw = e.g_real & 1;
+      const int kwp = pw ? 2 : 1;
+      const int th = tap / kwp, tw = tap - th * kwp;
+      const int skh = ph ? (th == 0 ? 2 : 0) : 1, skw = pw ? (tw == 0 ? 2 : 0) : 1;
+      return e.src[(((long long)col * e.Cin + row) * e.KH + skh) * e.KW + skw];
+    }
     case Y5OBB_PACK_STEM: {  // 6x6/s2 stem as a 3x1 conv over the 48-channel window of the space-to-depth image
       // tap = ty (KH = 3, KW = 1 here), col = tx * 16 + (dy * 2 + dx) * 3 + c -> w[row][c][2ty+dy][2tx+dx]
       if (row >= e.Cout || col >= 48) return 0.f;
@@ -102,9 +110,10 @@ int y5obb_pack_plan_create(const y5obb_pack_entry* entries, int n, y5obb_pack_pl
   for (int i = 0; i < n; ++i) {
     const y5obb_pack_entry& e = entries[i];
     if (!e.src || !e.dst || e.Cout <= 0 || e.Cin <= 0 || e.KH <= 0 || e.KW <= 0 || e.rows_pad <= 0 || e.cols_pad <= 0 ||
-        e.kind < Y5OBB_PACK_FWD || e.kind > Y5OBB_PACK_DETECT_BIAS)
+        e.kind < Y5OBB_PACK_FWD || e.kind > Y5OBB_PACK_DGRAD_S2)
       return Y5OBB_EINVAL;
-    const bool grouped = e.kind >= Y5OBB_PACK_DETECT;
+    if (e.kind == Y5OBB_PACK_DGRAD_S2 && (e.KH != 3 || e.KW != 3 || e.group_real < 0 || e.group_real > 3)) return Y5OBB_EINVAL;
+    const bool grouped = e.kind >= Y5OBB_PACK_DETECT && e.kind <= Y5OBB_PACK_DETECT_BIAS;
     if (grouped && (e.group_real <= 0 || e.group_pad < e.group_real)) return Y5OBB_EINVAL;
     PackEntryK& k = h[(size_t)i];
     k.src = e.src;
@@ -119,7 +128,10 @@ int y5obb_pack_plan_create(const y5obb_pack_entry* entries, int n, y5obb_pack_pl
     k.cols_pad = e.cols_pad;
     k.g_real = e.group_real;
     k.g_pad = e.group_pad;
-    const long long taps = e.kind == Y5OBB_PACK_STEM ? 3 : (e.kind == Y5OBB_PACK_DETECT_BIAS ? 1 : (long long)e.KH * e.KW);
+    long long taps = (long long)e.KH * e.KW;
+    if (e.kind == Y5OBB_PACK_STEM) taps = 3;
+    if (e.kind == Y5OBB_PACK_DETECT_BIAS) taps = 1;
+    if (e.kind == Y5OBB_PACK_DGRAD_S2) taps = ((e.group_real >> 1) ? 2 : 1) * ((e.group_real & 1) ? 2 : 1);
     total += taps * e.rows_pad * e.cols_pad;
   }
   PackPlan* p = new PackPlan();

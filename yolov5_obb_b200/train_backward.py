@@ -11,6 +11,7 @@ statically when the plan is built (first writer of a channel range overwrites).
 Parameter gradients land in views of ONE flat fp32 buffer owned by the plan (run() returns it); the autograd
 Function in yolo.py hands them to autograd, which accumulates into `.grad` (so GradScaler / DDP hooks see them).
 """
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -243,23 +244,46 @@ class BackwardPlan:
                 part["w_d"] = w_d
                 if s == 1:
                     op, wp = add_dgrad(Slice.full(dz), w_d, k, k - 1 - p, gx, "dgrad")
+                    part["dgrad_wp"] = wp
+                    self.keep.append(op)
+                elif k == 3 and p == 1 and x.H % 2 == 0 and x.W % 2 == 0 and os.environ.get("Y5OBB_DGRAD_S2", "phase") == "phase":
+                    # Output pixels of parity (ph, pw) only see the taps of matching parity: four 1- / 2-tap stride-1
+                    # convolutions of dz, each written to every other pixel of gx - 9 tap-GEMMs per 4 outputs instead of
+                    # the 36 of the zero-stuffed form.
+                    acc = written.contribute(gx)
+                    ps = gx.pix_stride
+                    part["dgrad_s2"] = []
+                    for ph in range(2):
+                        for pw in range(2):
+                            kh2, kw2 = (2 if ph else 1), (2 if pw else 1)
+                            wp, bp = pack_weights(torch.zeros((x.C, Cout, kh2, kw2), device=dev), None)
+                            geom = dict(h=Hh, w=Ww, off=(ph * x.W + pw) * ps, pix=2 * ps, row=2 * x.W * ps, img=x.H * x.W * ps)
+                            op = ConvOp(Slice.full(dz), wp, bp, x.C, (kh2, kw2), 1, (0, 0), False, out=gx,
+                                        res=gx if acc else None, out_geom=geom)
+                            self.flops += op.info()["flops"]
+                            add("dgrad", lambda st, h=op._h: _lib.check(L.y5obb_conv_run(h, st), "dgrad s2 phase"))
+                            part["dgrad_s2"].append((ph * 2 + pw, wp))
+                            self.keep.append(op)
                 else:
                     dzup = bf(B, x.H, x.W, Cout)
                     add("zero_stuff", lambda st, dz=dz, dzup=dzup, npix=npix, C=Cout, W=Ww:
                                       _lib.check(L.y5obb_zero_stuff2x(dz.data_ptr(), C, dzup.data_ptr(), C, npix, C, W, st), "zero_stuff"))
                     op, wp = add_dgrad(Slice.full(dzup), w_d, k, k - 1 - p, gx, "dgrad s2")
-                part["dgrad_wp"] = wp
-                self.keep.append(op)
+                    part["dgrad_wp"] = wp
+                    self.keep.append(op)
         self.refresh()
 
     # ------------------------------------------------------------------------------------------
     def pack_entries(self):
         """(kind, fp32 parameter, packed bf16 buffer, group_real, group_pad) of every data-gradient weight buffer."""
-        from .train_ops import PACK_DGRAD, PACK_DETECT_DGRAD
+        from .train_ops import PACK_DGRAD, PACK_DETECT_DGRAD, PACK_DGRAD_S2
         det = self.eng.model.model[-1]
         ent = [(PACK_DETECT_DGRAD, part["mi"].weight.data, part["dgrad_wp"], det.no, part["bn"]) for part in self.det_parts]
         ent += [(PACK_DGRAD, part["lay"].mod.conv.weight.data, part["dgrad_wp"], 0, 0) for part in self.conv_parts
                 if "dgrad_wp" in part]
+        for part in self.conv_parts:
+            for phase, wp in part.get("dgrad_s2", ()):
+                ent.append((PACK_DGRAD_S2, part["lay"].mod.conv.weight.data, wp, phase, 0))
         return ent
 
     def refresh(self):

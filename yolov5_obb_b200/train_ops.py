@@ -55,7 +55,7 @@ class Wgrad:
             self._h = None
 
 
-PACK_FWD, PACK_DGRAD, PACK_STEM, PACK_DETECT, PACK_DETECT_DGRAD, PACK_DETECT_BIAS = range(6)
+PACK_FWD, PACK_DGRAD, PACK_STEM, PACK_DETECT, PACK_DETECT_DGRAD, PACK_DETECT_BIAS, PACK_DGRAD_S2 = range(7)
 
 
 class PackEntry(ctypes.Structure):
@@ -81,7 +81,8 @@ class PackPlan:
                 cout, cin, kh, kw = src.shape
                 assert dst.dtype == torch.bfloat16 and dst.dim() == 3
                 rows_pad, cols_pad = dst.shape[1], dst.shape[2]
-                assert dst.shape[0] == (3 if kind == PACK_STEM else kh * kw)
+                taps = 3 if kind == PACK_STEM else ((2 if g_real >> 1 else 1) * (2 if g_real & 1 else 1) if kind == PACK_DGRAD_S2 else kh * kw)
+                assert dst.shape[0] == taps
             arr[i] = PackEntry(src.data_ptr(), dst.data_ptr(), kind, cout, cin, kh, kw, rows_pad, cols_pad, g_real, g_pad)
             self._keep.append((src, dst))
         self._h = c_void_p()
