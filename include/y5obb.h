@@ -196,6 +196,9 @@ int y5obb_loss_backward(const y5obb_loss_desc* desc, const float* grad_loss, voi
 int y5obb_rbox2poly_f32(const float* rboxes5, float* polys8, int64_t n, void* stream);
 int y5obb_poly2hbb_f32(const float* polys8, float* hbb4, int64_t n, void* stream);
 int y5obb_scale_polys_f32(float* polys8, int64_t n, float pad_x, float pad_y, float gain, void* stream);
+/* poly2rbox (utils/rboxs_utils.py:39-81, whose arithmetic is cv2.minAreaRect): [n,8] fp32 corner points ->
+ * [n,5] fp64 (cx, cy, long edge, short edge, theta); theta in [-pi/2, pi/2) with pi = 3.141592 (use_pi) or degrees in [0, 180) */
+int y5obb_poly2rbox(const float* polys8, double* rbox5, int64_t n, int use_pi, void* stream);
 int y5obb_gaussian_label(const double* angle_deg, float* csl_out, int64_t n, int num_class, double sigma,
                          void* stream);
 

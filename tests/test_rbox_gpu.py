@@ -8,6 +8,7 @@ import torch
 pytestmark = pytest.mark.gpu
 G = np.load(Path(__file__).resolve().parents[1] / "tests" / "golden" / "rbox_golden.npz")
 DEV = "cuda:0"
+ROOT = Path(__file__).resolve().parents[1]
 
 
 def test_rbox2poly_poly2hbb_scale_polys():
@@ -39,3 +40,36 @@ def test_gaussian_label_matches_reference_rows():
         got = gaussian_label(a, 180, 0, sig).cpu().numpy()
         np.testing.assert_allclose(got, G[key], rtol=1e-6, atol=1e-12)
         assert np.array_equal(got.argmax(1), G[key].argmax(1))
+
+
+def test_poly2rbox_matches_oracle_and_reference_outputs():
+    """k_poly2rbox (A8): identical to the float64 oracle restatement (same hull, same edge choice, <= 1e-9) and, through
+    it, to the REFERENCE poly2rbox outputs (cv2.minAreaRect 4.13.0) up to the ties cv2's float32 rounding decides
+    (tests/test_oracle_p2r.py states the tolerances)."""
+    import numpy as np
+    from oracle import rbox_ref
+    from tests.test_oracle_p2r import compare_p2r
+    from yolov5_obb_b200.rboxs_utils import poly2rbox
+    G = np.load(ROOT / "tests" / "golden" / "p2r_golden.npz")
+    P = G["polys"]
+    t = torch.from_numpy(P).to(DEV)
+    got = poly2rbox(t, use_pi=True)
+    assert got.dtype == torch.float64 and got.shape == (len(P), 5)
+    want = rbox_ref.poly2rbox(P, use_pi=True)
+    g = got.cpu().numpy()
+    assert np.abs(g[:, :4] - want[:, :4]).max() < 1e-9
+    d = np.abs(g[:, 4] - want[:, 4])
+    assert np.minimum(d, rbox_ref.PI_REF - d).max() < 1e-9        # (the wrap point -pi/2 == +pi/2)
+    ties = compare_p2r(g, G["rbox_pi"], P)
+    assert ties < 0.15 * len(P)
+    deg = poly2rbox(t, use_pi=False).cpu().numpy()
+    assert np.abs(deg[:, 4] - (g[:, 4] * 180 / rbox_ref.PI_REF + 90)).max() < 1e-9 and deg[:, 4].min() >= 0 and deg[:, 4].max() < 180 + 1e-9
+    # with CSL rows, as the dataloader asks (utils/datasets.py:639-641): rows of the REFERENCE for non-tie polygons
+    rb, csl = poly2rbox(t[:64], num_cls_thata=180, radius=2.0, use_pi=True, use_gaussian=True)
+    ref_rb, ref_csl = G["csl_rbox"], G["csl"]
+    same = np.abs(rb.cpu().numpy()[:, 4] - ref_rb[:, 4]) < 1e-4
+    assert same.mean() > 0.8 and csl.shape == (64, 180)
+    # the CSL peak bin follows the (float) angle: identical rows wherever the angle agrees to well within a bin
+    ang = (ref_rb[:, 4] * 180 / rbox_ref.PI_REF + 90)
+    safe = same & (np.abs(ang - np.round(ang)) > 1e-2)
+    assert np.abs(csl.cpu().numpy()[safe] - ref_csl[safe]).max() < 1e-6

@@ -59,3 +59,20 @@ def gaussian_label(angle_deg: torch.Tensor, num_class: int = 180, u=0, sig: floa
     _run(_lib.lib().y5obb_gaussian_label, "y5obb_gaussian_label", a.device, a.data_ptr(), out.data_ptr(), a.shape[0],
          int(num_class), float(sig))
     return out
+
+
+def poly2rbox(polys: torch.Tensor, num_cls_thata: int = 180, radius: float = 6.0, use_pi: bool = False,
+              use_gaussian: bool = False):
+    """utils/rboxs_utils.py:39-81 on the device: (num_gts, [x1 y1 x2 y2 x3 y3 x4 y4]) -> (num_gts, [cx cy l s theta]) fp64,
+    theta in [-pi/2, pi/2) (use_pi) or degrees in [0, 180); with use_gaussian also the (num_gts, num_cls_thata) CSL rows
+    (gaussian_label_cpu(label=angle_deg, u=0, sig=radius)).  The reference's arithmetic is cv2.minAreaRect; see
+    csrc/rbox_utils.cu k_poly2rbox for the restated algorithm and tests/test_rbox_gpu.py for the parity statement."""
+    _lib.require_cuda(polys, "polys")
+    assert polys.shape[-1] == 8
+    p = polys.reshape(-1, 8).float().contiguous()   # np.float32(poly), rboxs_utils.py:60
+    out = torch.empty((p.shape[0], 5), dtype=torch.float64, device=p.device)
+    _run(_lib.lib().y5obb_poly2rbox, "y5obb_poly2rbox", p.device, p.data_ptr(), out.data_ptr(), p.shape[0], int(bool(use_pi)))
+    if not use_gaussian:
+        return out
+    angle = out[:, 4] if not use_pi else out[:, 4] * 180 / pi + 90
+    return out, gaussian_label(angle, num_cls_thata, 0, radius)
