@@ -50,7 +50,10 @@ def non_max_suppression_obb(prediction: torch.Tensor, conf_thres: float = 0.25, 
     if return_packed == "async":
         # no host read at all: (device [B, max_det, 7], device int64 [B + 1] = rows per image + total candidates, cap).
         # The caller checks counts[B] <= cap when it reads the counts (pipeline.DetectPipeline does, and re-runs).
-        out, counts = _launch(args, cap)
+        # Every launch of the pipeline has a fixed geometry (sized by `cap`), so for a fixed input buffer the whole
+        # post-process is replayed as ONE CUDA graph from the third identical call on; the two returned tensors are
+        # then the graph's static outputs (valid until the next call with the same arguments).
+        out, counts = _launch_graphed(args, cap)
         return out, counts, cap
     while True:
         out, counts = _launch(args, cap)
@@ -74,7 +77,34 @@ _NO_SPLIT = {}  # (B, anchors, nc) -> True once a batch needed the one-pass-per-
 _CAP_HINT = {}  # (B, anchors, nc) -> candidate capacity that was needed once (sticky: avoids repeated overflow re-runs)
 
 
-def _launch(args, cap):
+_GRAPHS = {}
+
+
+def _launch_graphed(args, cap):
+    import os
+    pred = args[0]
+    if os.environ.get("Y5OBB_NO_GRAPH", "0") == "1":
+        return _launch(args, cap)
+    key = (pred.data_ptr(), pred.device.index, cap) + tuple(args[1:])
+    slot = _GRAPHS.get(key)
+    if slot is None:
+        if len(_GRAPHS) > 16:
+            _GRAPHS.clear()
+        slot = _GRAPHS[key] = dict(calls=0, graph=None, out=None, counts=None, ws=None)
+    slot["calls"] += 1
+    if slot["calls"] <= 2:
+        return _launch(args, cap)
+    if slot["graph"] is None:
+        torch.cuda.synchronize(pred.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            out, counts, ws = _launch(args, cap, keep_ws=True)
+        slot.update(graph=g, out=out, counts=counts, ws=ws)
+    slot["graph"].replay()
+    return slot["out"], slot["counts"]
+
+
+def _launch(args, cap, keep_ws=False):
     pred, B, A, no, nc, conf_thres, iou_thres, mask, agnostic, multi_label, max_det, nosplit = args
     L = _lib.lib()
     dev = pred.device
@@ -82,11 +112,12 @@ def _launch(args, cap):
     counts = torch.empty(B + 1, dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
         nbytes = L.y5obb_nms_obb_workspace_bytes(B, A, cap, MAX_NMS)
-        ws = _lib.workspace(nbytes, dev, "nms_obb")
+        # a captured graph owns its workspace (the shared grow-only buffer may be re-allocated later)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev) if keep_ws else _lib.workspace(nbytes, dev, "nms_obb")
         rc = L.y5obb_nms_obb_f32(pred.data_ptr(), B, A, no, nc, float(conf_thres), float(iou_thres), mask,
                                  int(bool(agnostic)), int(bool(multi_label)), int(max_det), MAX_NMS, float(MAX_WH),
                                  _lib.NMS_STRICT_GT | (_lib.NMS_NO_CLASS_SPLIT if nosplit else 0), cap, out.data_ptr(),
                                  counts.data_ptr(), ws.data_ptr(),
                                  ws.numel(), _lib.stream_ptr(dev))
     _lib.check(rc, "y5obb_nms_obb_f32")
-    return out, counts
+    return (out, counts, ws) if keep_ws else (out, counts)
