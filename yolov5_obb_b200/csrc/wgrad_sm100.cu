@@ -25,15 +25,16 @@ namespace {
 constexpr int WG_THREADS = 192;
 constexpr int WG_MAX_STAGES = 8;
 constexpr int WG_SMEM = 200 * 1024;
-constexpr int WG_BK = 64;                       // pixels per pipeline stage
-constexpr uint32_t WG_CHUNK = WG_BK * 128;      // one 64-channel chunk of a stage: [64 pixels][128 B]
+// a pixel block (= one TMA box per 64-channel chunk) has bk = 64, 128 or 256 pixels; a chunk is [bk pixels][128 B]
 
 struct WgradK {
   CUtensorMap tmA;  // dz NHWC slice: (Cout, Wo, Ho, B), box {64, kwp, khp, 1}
   CUtensorMap tmB;  // x NHWC slice: (Cin, Wi, Hi, B), box {64, kwp*s, khp*s, 1}, element strides {1, s, s, 1}
   int B, Ho, Wo, Cout, Cin;
   int KH, KW, stride, pad_h, pad_w;
-  int kwp, khp, BN;         // pixel block kwp x khp = WG_BK pixels; N tile (input channels, multiple of 16)
+  int kwp, khp, BN;         // pixel block kwp x khp = bk pixels; N tile (input channels, multiple of 16)
+  int bk;                   // pixels per block (64 / 128 / 256)
+  uint32_t chunk;           // bk * 128 bytes
   int tiles_w, tiles_h;     // pixel blocks per image
   int nblocks;              // B * tiles_h * tiles_w
   int T, ngroups;           // taps handled by one CTA (they share the dz tile), tap groups
@@ -49,11 +50,11 @@ struct WgradK {
 };
 
 // MN-major, 128B-swizzled operand: 64-channel chunks of [pixels][128 B]; 8-pixel groups 1024 B apart (SBO), chunks
-// WG_CHUNK bytes apart (LBO).  (cute/atom/mma_traits_sm100.hpp: Swizzle<3,4,3> o ((8,n),(8,k)):((1,LBO),(8,SBO)).)
-__device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr) {
+// `chunk` bytes apart (LBO).  (cute/atom/mma_traits_sm100.hpp: Swizzle<3,4,3> o ((8,n),(8,k)):((1,LBO),(8,SBO)).)
+__device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr, uint32_t chunk) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)(WG_CHUNK >> 4) << 16;   // LBO
+  d |= (uint64_t)(chunk >> 4) << 16;      // LBO
   d |= (uint64_t)(1024u >> 4) << 32;      // SBO
   d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
   d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
@@ -73,6 +74,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
   __shared__ uint32_t tmem_base_smem;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t WG_CHUNK = p.chunk;
   const uint32_t a_bytes = (uint32_t)p.a_chunks * WG_CHUNK, b_bytes = (uint32_t)p.b_chunks * WG_CHUNK;
   const uint32_t blk_bytes = a_bytes + (uint32_t)p.T * b_bytes;
 
@@ -151,7 +153,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      const uint64_t desc_hi = make_mnmajor_desc(0u);
+      const uint64_t desc_hi = make_mnmajor_desc(0u, WG_CHUNK);
+      const int nk = p.bk >> 4;
       const uint32_t ring = ptx::smem_u32(smem);
       uint32_t started = 0u;  // bit g: accumulator group g holds a partial sum already
       const int nchunks = ntap * p.b_chunks;  // the taps' x tiles are consecutive 64-channel chunks: ONE N axis
@@ -170,8 +173,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
               const uint32_t d_tmem = tmem_base + (uint32_t)(c0 * 64);
               const uint32_t idesc = p.idesc | ((uint32_t)(nn * 8) << 17);
               uint32_t accumulate = (started >> g) & 1u;
-#pragma unroll
-              for (int j = 0; j < WG_BK / 16; ++j) {  // 16 pixel rows = 2048 B per MMA
+#pragma unroll 4
+              for (int j = 0; j < nk; ++j) {  // 16 pixel rows = 2048 B per MMA
                 ptx::umma_bf16(d_tmem, da + (uint64_t)(128 * j), db + (uint64_t)(128 * j), idesc, accumulate);
                 accumulate = 1u;
               }
@@ -300,10 +303,42 @@ int y5obb_wgrad_create(const y5obb_wgrad_desc* d, y5obb_wgrad_t** out) {
   k.co_group = d->co_group;
   k.co_group_pad = d->co_group_pad;
   if (const char* e = getenv("Y5OBB_WGRAD_DBG")) k.dbg = atoi(e);
-  // pixel tile kwp x khp = 64 output pixels: the shape that covers the map with the fewest tiles (ties: widest rows)
+  k.ci_blks = (d->Cin + 255) / 256;
+  k.BN = ((d->Cin + k.ci_blks - 1) / k.ci_blks + 15) / 16 * 16;
+  k.b_chunks = (k.BN + 63) / 64;
+  k.co_blks = (d->Cout + 127) / 128;
+  k.a_chunks = d->Cout > 64 ? 2 : 1;
+  const int ntaps = d->KH * d->KW;
+  // Block size bk (pixels per TMA box) and taps per CTA T.  Every cp.async.bulk.tensor instruction costs the TMA unit a
+  // few hundred cycles whatever its size: measured on B200, 64-pixel boxes deliver ~12 B/clk/SM and 128-pixel boxes
+  // 1.3-1.8x that (48->48 3x3 at 256^2: 189 -> 106 us; 192->192 3x3 at 64^2: 80 -> 51 us), while trading taps per CTA for
+  // 256-pixel boxes loses again (the dz tile is re-read once per tap group).  So: 128-pixel blocks, as many taps per CTA
+  // as fit two pipeline stages and the 8 TMEM chunk slots.
+  const long long npx = (long long)d->B * d->Ho * d->Wo;
+  int best_bk = npx >= 512 ? 128 : 64;
+  int best_T = std::min(ntaps, 8 / k.b_chunks);
+  while (best_T > 1 && (uint32_t)(k.a_chunks + best_T * k.b_chunks) * (uint32_t)best_bk * 128 > WG_SMEM / 2) --best_T;
+  if ((uint32_t)(k.a_chunks + best_T * k.b_chunks) * (uint32_t)best_bk * 128 > WG_SMEM / 2) best_bk = 64;
+  if (const char* e = getenv("Y5OBB_WGRAD_BK")) {  // experiments
+    const int v = atoi(e);
+    if (v == 64 || v == 128 || v == 256) {
+      best_bk = v;
+      best_T = std::min(ntaps, 8 / k.b_chunks);
+      while (best_T > 1 && (uint32_t)(k.a_chunks + best_T * k.b_chunks) * (uint32_t)v * 128 > WG_SMEM / 2) --best_T;
+    }
+  }
+  if (const char* e = getenv("Y5OBB_WGRAD_T")) best_T = std::max(1, std::min(atoi(e), std::min(ntaps, 8 / k.b_chunks)));
+  if (best_bk == 0) {
+    delete o;
+    return Y5OBB_EINVAL;
+  }
+  k.bk = best_bk;
+  k.chunk = (uint32_t)best_bk * 128;
+  // pixel block kwp x khp = bk output pixels: the shape that covers the map with the fewest blocks (ties: widest rows)
   long long best = -1;
-  for (int kwp = 1; kwp <= WG_BK; kwp <<= 1) {
-    const int khp = WG_BK / kwp;
+  for (int kwp = 1; kwp <= std::min(k.bk, 256); kwp <<= 1) {
+    const int khp = k.bk / kwp;
+    if (khp * d->stride > 256 || kwp * d->stride > 256) continue;  // TMA box extents (input pixels) are at most 256
     const long long cost = (long long)((d->Wo + kwp - 1) / kwp) * ((d->Ho + khp - 1) / khp);
     if (best < 0 || cost <= best) {
       best = cost;
@@ -314,44 +349,34 @@ int y5obb_wgrad_create(const y5obb_wgrad_desc* d, y5obb_wgrad_t** out) {
   k.tiles_w = (d->Wo + k.kwp - 1) / k.kwp;
   k.tiles_h = (d->Ho + k.khp - 1) / k.khp;
   k.nblocks = d->B * k.tiles_w * k.tiles_h;
-  k.ci_blks = (d->Cin + 255) / 256;
-  k.BN = ((d->Cin + k.ci_blks - 1) / k.ci_blks + 15) / 16 * 16;
-  k.b_chunks = (k.BN + 63) / 64;
-  k.co_blks = (d->Cout + 127) / 128;
-  k.a_chunks = d->Cout > 64 ? 2 : 1;
-  const int ntaps = d->KH * d->KW;
-  // taps per CTA: as many accumulators as TMEM (512 columns) holds, while one pixel block still fits >= 3 stages
-  const uint32_t a_bytes = (uint32_t)k.a_chunks * WG_CHUNK, b_bytes = (uint32_t)k.b_chunks * WG_CHUNK;
-  int T = std::max(1, std::min(ntaps, 8 / k.b_chunks));  // 8 chunks of 64 fp32 columns = the 512 TMEM columns
-  while (T > 1 && a_bytes + (uint32_t)T * b_bytes > WG_SMEM / 3) --T;
-  k.ngroups = (ntaps + T - 1) / T;
+  const uint32_t a_bytes = (uint32_t)k.a_chunks * k.chunk, b_bytes = (uint32_t)k.b_chunks * k.chunk;
+  k.ngroups = (ntaps + best_T - 1) / best_T;
   k.T = (ntaps + k.ngroups - 1) / k.ngroups;  // balanced groups
   const uint32_t blk_bytes = a_bytes + (uint32_t)k.T * b_bytes;
   if (blk_bytes > WG_SMEM / 2) {
     delete o;
     return Y5OBB_EINVAL;
   }
-  // pixel blocks per stage: narrow layers move few bytes per block; keep >= 3 stages and at most 4 blocks
-  k.PB = std::max(1, std::min(4, (int)(WG_SMEM / 3 / blk_bytes)));
-  k.PB = std::min(k.PB, std::max(1, k.nblocks));
-  k.stage_bytes = (uint32_t)k.PB * blk_bytes;
+  k.PB = 1;
+  k.stage_bytes = blk_bytes;
   k.stages = (int)std::min<size_t>(WG_MAX_STAGES, WG_SMEM / k.stage_bytes);
-  k.steps = (k.nblocks + k.PB - 1) / k.PB;
+  k.steps = k.nblocks;
   const int items = k.ngroups * k.co_blks * k.ci_blks;
-  {  // split-K: minimise (waves) x (steps per CTA + the fixed cost of a CTA, ~8 steps: TMEM alloc, pipeline fill,
-     // fp32 atomic epilogue); 1 CTA per SM
+  {  // split-K: minimise (waves) x (steps per CTA + the fixed cost of a CTA: TMEM alloc, pipeline fill, fp32 atomic
+     // epilogue - about 512 pixels' worth of pipeline steps); 1 CTA per SM
     const int sms = sm_count();
-    long long best_cost = -1;
-    int best = 1;
+    const int fixed = std::max(1, 512 / k.bk);
+    long long best_cost2 = -1;
+    int bestk = 1;
     for (int ksp = 1; ksp <= std::min(k.steps, 4 * sms); ++ksp) {
       const long long waves = ((long long)items * ksp + sms - 1) / sms;
-      const long long cost = waves * ((k.steps + ksp - 1) / ksp + 8);
-      if (best_cost < 0 || cost < best_cost) {
-        best_cost = cost;
-        best = ksp;
+      const long long cost = waves * ((k.steps + ksp - 1) / ksp + fixed);
+      if (best_cost2 < 0 || cost < best_cost2) {
+        best_cost2 = cost;
+        bestk = ksp;
       }
     }
-    k.ksplit = best;
+    k.ksplit = bestk;
   }
   k.idesc = ptx::make_idesc_bf16(128, 0) | (1u << 15) | (1u << 16);  // A and B MN-major; N is set per instruction
   k.tmem_cols = 64;
