@@ -276,7 +276,9 @@ def run_train_leg(args, dev, world, rank, dist, pk):
     from yolov5_obb_b200.train_step import TrainStep
     size, TB = args.train_model, args.train_batch
     m = build_mirror(size, nc=NC, seed=0).train().to(dev)
-    ts = TrainStep(m, batch_size=TB * world, imgsz=IMG)
+    # configs[2] is a b64 job (8 tiles on each of 8 GPUs): nominal batch 64 -> the reference's `accumulate` is 1, i.e. every
+    # step ends with the optimizer + EMA update (a b8 single-GPU job would only step the optimizer every 8th batch)
+    ts = TrainStep(m, batch_size=64, imgsz=IMG)
     imgs_h, tg_h = train_inputs(TB, rank)
     imgs_h, tg_h = imgs_h.pin_memory(), tg_h.pin_memory()
     imgs_d, tg_d = imgs_h.to(dev), tg_h.to(dev)
