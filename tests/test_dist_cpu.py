@@ -73,6 +73,11 @@ def _grad_worker(rank, ws, port, q):
     dist.all_reduce = lambda t, op=dist.ReduceOp.SUM: (calls.append(t.numel()), orig(t, op=op))[1]
     ts._allreduce_grads()
     flat_calls = list(calls)
+    # gradient accumulation: .grad still views the first step's buffer while the engine already holds a newer one
+    net._last_train_engine.last_grad_flat = torch.zeros(n)
+    calls.clear()
+    ts._allreduce_grads()
+    flat_calls += list(calls)
     # gradients that are NOT views of the flat buffer fall back to one call per tensor
     for p in net.parameters():
         p.grad = p.grad.clone()
@@ -96,6 +101,6 @@ def test_two_rank_gradient_allreduce_is_one_call_and_a_sum():
         assert p.exitcode == 0
     n = len(res[0][1])
     for rank, flat, flat_calls, per_tensor_calls, last in res:
-        assert flat == [3.0 * i for i in range(n)]           # 1x + 2x
-        assert flat_calls == [n]                             # ONE collective over the whole buffer
+        assert flat == [6.0 * i for i in range(n)]           # (1x + 2x) = 3x on both ranks, summed once more through ._base
+        assert flat_calls == [n, n]                          # ONE collective over the whole buffer, both times
         assert per_tensor_calls == 6                         # fallback path: conv w/b, bn w/b, conv w/b

@@ -124,10 +124,14 @@ class TrainStep:
         tensors) are reduced one by one."""
         params = [p for p in self.model.parameters() if p.grad is not None]
         eng = getattr(self.model, "_last_train_engine", None)
-        flat = getattr(eng, "last_grad_flat", None)
-        if flat is not None:
+        cands = [getattr(eng, "last_grad_flat", None)]
+        if params and params[0].grad._base is not None:   # gradient accumulation: .grad still views the FIRST step's buffer
+            cands.append(params[0].grad._base)
+        for flat in cands:
+            if flat is None or flat.dim() != 1:
+                continue
             lo, hi = flat.data_ptr(), flat.data_ptr() + flat.numel() * flat.element_size()
-            if all(lo <= p.grad.data_ptr() < hi for p in params):
+            if all(lo <= p.grad.data_ptr() and p.grad.data_ptr() + p.grad.numel() * p.grad.element_size() <= hi for p in params):
                 dist.all_reduce(flat, op=dist.ReduceOp.SUM)
                 return
         for p in params:
