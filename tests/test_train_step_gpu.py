@@ -59,3 +59,32 @@ def test_steps_reduce_the_loss_and_follow_sgd_nesterov_and_ema():
     print("losses", [f"{v:.3f}" for v in losses])
     assert all(math.isfinite(v) for v in losses) and min(losses[-4:]) < losses[0] - 0.1
     assert items.shape == (4,) and torch.isfinite(items).all()
+
+
+def test_eval_after_training_uses_the_updated_weights():
+    """val after an epoch (train.py:352): the inference plan folds BatchNorm into packed weights when it is built, so it must
+    be rebuilt once optimizer steps / training forwards have changed parameters and running statistics."""
+    from oracle import model_ref
+    from yolov5_obb_b200.train_step import TrainStep
+    m = build_mirror("n", nc=15, seed=2).to(DEV)
+    x = synth_tiles(2, 128, seed=5).to(DEV)
+    xf = x.float() / 255
+    m.eval()
+    p0, _ = m(xf)
+    p0 = p0.clone()
+    eng0 = m._engines[(tuple(xf.shape), 0)]
+    m(xf)
+    assert m._engines[(tuple(xf.shape), 0)] is eng0          # nothing changed: the plan is reused
+    m.train()
+    ts = TrainStep(m, batch_size=64, imgsz=128, ema=False)
+    tg = torch.from_numpy(synth_targets(2, 20, 128, nc=15, seed=5)).to(DEV)
+    for _ in range(3):
+        ts.step(x, tg)
+    m.eval()
+    p1, _ = m(xf)
+    assert m._engines[(tuple(xf.shape), 0)] is not eng0      # weights / statistics moved: re-planned
+    ref_m = copy.deepcopy(m).cpu()
+    want, _ = model_ref.forward(ref_m, xf.cpu())
+    rel = ((p1.cpu() - want).norm() / want.norm()).item()
+    assert rel < 2e-2, rel
+    assert (p1 - p0).abs().max().item() > 1e-3               # and the output really changed

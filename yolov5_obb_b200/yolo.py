@@ -263,8 +263,25 @@ class Model(nn.Module):
         return self
 
     def invalidate(self):
-        """Call after changing parameters so that packed weights are rebuilt."""
+        """Drop every plan (packed weights, buffers, captured graphs); the next forward re-plans."""
         self._engines.clear()
+        self._sig_tensors = None
+
+    def __deepcopy__(self, memo):
+        """copy.deepcopy(model) (ModelEMA, checkpoints): parameters and buffers are copied, the device plans are not."""
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        skip = ("_engines", "_last_train_engine", "_sig_tensors", "_sig_nbt")
+        new.__dict__ = {k: deepcopy(v, memo) for k, v in self.__dict__.items() if k not in skip}
+        new._engines = {}
+        new._sig_tensors = None
+        return new
+
+    def _apply(self, fn, *args, **kwargs):  # .to() / .cuda() / .float(): the plans point at the old storages
+        if getattr(self, "_engines", None):
+            self._engines.clear()
+        self._sig_tensors = None
+        return super()._apply(fn, *args, **kwargs)
 
     def forward(self, x, augment=False, profile=False, visualize=False):
         if augment or profile or visualize:
@@ -285,6 +302,20 @@ class Model(nn.Module):
         from .engine import InferenceEngine
         key = (tuple(x.shape), x.device.index)
         eng = self._engines.get(key)
-        if eng is None:
+        # The inference plan folds BatchNorm into packed bf16 weights when it is built.  Parameters and statistics that
+        # were updated in place since then (optimizer / EMA steps, load_state_dict, a training forward) show up in the
+        # tensors' version counters or in num_batches_tracked: the plan is then rebuilt (val after every epoch, train.py:352).
+        sig = self._weights_signature()
+        if eng is None or eng._weights_sig != sig:
             eng = self._engines[key] = InferenceEngine(self, x.shape[0], x.shape[2], x.shape[3], x.device)
+            eng._weights_sig = sig
         return eng.forward(x), None
+
+    def _weights_signature(self):
+        tr = getattr(self, "_sig_tensors", None)
+        if tr is None:
+            tr = self._sig_tensors = list(self.parameters()) + [b for b in self.buffers() if b.dtype.is_floating_point]
+            self._sig_nbt = [b for n, b in self.named_buffers() if n.endswith("num_batches_tracked")]
+        # (the training kernels write running statistics through raw pointers: they bump num_batches_tracked, which a
+        # torch op increments, so the sum of its version counters moves with every training forward)
+        return (sum(t._version for t in tr), sum(t._version for t in self._sig_nbt), id(tr[0]) if tr else 0)
