@@ -59,3 +59,27 @@ def test_model_ema_matches_the_reference_formula():
         else:
             assert torch.equal(v, before[k])                    # integer buffers (num_batches_tracked) are not averaged
     assert ema.updates == 2 and not any(p.requires_grad for p in ema.ema.parameters())
+
+
+def test_model_deepcopy_and_weight_signature():
+    """copy.deepcopy(model) copies parameters but no device plans; the weight signature (what decides whether the inference
+    plan must be rebuilt) moves with in-place updates of parameters and of num_batches_tracked, and only then."""
+    import copy
+    from tests.modelgen import build_mirror
+    m = build_mirror("n", nc=15, seed=0)
+    m._engines["plan"] = object()            # stands for a device plan (holds ctypes handles: not copyable)
+    m._last_train_engine = object()
+    s0 = m._weights_signature()
+    assert m._weights_signature() == s0
+    c = copy.deepcopy(m)
+    assert c._engines == {} and not hasattr(c, "_last_train_engine")
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), c.state_dict().values()))
+    sc = c._weights_signature()
+    with torch.no_grad():
+        next(c.parameters()).add_(1.0)       # an optimizer / EMA step on the copy
+    assert c._weights_signature() != sc and m._weights_signature() == s0
+    bns = [b for b in m.modules() if isinstance(b, torch.nn.BatchNorm2d)]
+    torch._foreach_add_([b.num_batches_tracked for b in bns], 1)   # what a training forward does
+    assert m._weights_signature() != s0
+    m.invalidate()
+    assert m._engines == {}
