@@ -98,6 +98,45 @@ def build(force: bool = False) -> bool:
     return True
 
 
+POLY_SHIM = r'''
+// C shim around the reference's DOTA_devkit/polyiou.cpp (declared in polyiou.h:9): test infrastructure
+#include <vector>
+double iou_poly(std::vector<double> p, std::vector<double> q);
+extern "C" void ref_iou_poly_pairs(const double* p8, const double* q8, double* out, long n) {
+  for (long i = 0; i < n; ++i)
+    out[i] = iou_poly(std::vector<double>(p8 + 8 * i, p8 + 8 * i + 8), std::vector<double>(q8 + 8 * i, q8 + 8 * i + 8));
+}
+'''
+
+
+def build_polyiou(force: bool = False) -> bool:
+    """oracle/_ref/libref_polyiou.so = the reference's DOTA_devkit/polyiou.cpp (the polygon IoU behind the tile-merge NMS,
+    ResultMerge_multi_process.py:62-123) compiled in place with g++ plus the C shim above."""
+    so = OUT / "libref_polyiou.so"
+    if not REF.exists():
+        return so.exists()
+    if so.exists() and not force:
+        return True
+    OUT.mkdir(exist_ok=True)
+    work = OUT / "_build"
+    work.mkdir(exist_ok=True)
+    (work / "ref_polyiou_shim.cpp").write_text(POLY_SHIM)
+    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-ffp-contract=off", "-o", str(so),
+                           str(work / "ref_polyiou_shim.cpp"), str(REF / "DOTA_devkit" / "polyiou.cpp")])
+    return True
+
+
+def load_polyiou():
+    import ctypes
+    so = OUT / "libref_polyiou.so"
+    if not so.exists():
+        raise FileNotFoundError("oracle/_ref/libref_polyiou.so not built; run python oracle/build_ref.py")
+    lib = ctypes.CDLL(str(so))
+    lib.ref_iou_poly_pairs.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long]
+    lib.ref_iou_poly_pairs.restype = None
+    return lib
+
+
 def load_ref():
     """Import the prebuilt reference extension (tests only)."""
     import importlib.util
@@ -113,4 +152,5 @@ def load_ref():
 
 if __name__ == "__main__":
     ok = build(force="--force" in sys.argv)
-    print("oracle/_ref:", "ok" if ok else "unavailable")
+    ok2 = build_polyiou(force="--force" in sys.argv)
+    print("oracle/_ref:", "ok" if ok else "unavailable", "| polyiou:", "ok" if ok2 else "unavailable")
