@@ -300,6 +300,15 @@ int y5obb_pack_plan_create(const y5obb_pack_entry* entries, int n, y5obb_pack_pl
 int y5obb_pack_plan_run(const y5obb_pack_plan_t* plan, void* stream);
 void y5obb_pack_plan_destroy(y5obb_pack_plan_t* plan);
 
+/* ---- tile-merge polygon NMS of the DOTA devkit (EXPERIMENTAL in round 1: not yet validated on hardware) ----------
+ * DOTA_devkit/ResultMerge_multi_process.py:62-123 py_cpu_nms_poly_fast over DOTA_devkit/polyiou.cpp:106-128 iou_poly, in
+ * double precision without FMA contraction (bit-equal to the reference's g++ build by construction; oracle/poly_ref.py).
+ * dets9: [n][9] = x1 y1 x2 y2 x3 y3 x4 y4 score (device).  keep_out: indices in descending score order. */
+size_t y5obb_poly_nms_workspace_bytes(int64_t n);
+int y5obb_poly_nms_f64(const double* dets9, int64_t n, double thresh, int64_t* keep_out, int64_t* n_keep_out, void* workspace,
+                       size_t workspace_bytes, void* stream);
+int y5obb_poly_iou_pairs_f64(const double* p8, const double* q8, double* iou_out, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
