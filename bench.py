@@ -355,7 +355,9 @@ def run_ours(args):
 
     B = args.batch
     model = build_model(args.model, dev)
-    x_host = synth_batch(B, seed=rank).pin_memory()
+    # every replica processes the same seeded tile set: the NMS stage is data dependent (candidates per tile), and with four
+    # distinct tiles per batch a per-rank seed made rank 1's step 12 % longer than rank 0's - sample noise, not scaling
+    x_host = synth_batch(B, seed=0).pin_memory()
     x_dev = x_host.to(dev)
     model(x_dev)  # builds the plan
     eng = model._engines[(tuple(x_dev.shape), dev.index)]
