@@ -322,7 +322,7 @@ class BackwardPlan:
     def _launch_all(self, st):
         eng = self.eng
         det = eng.model.model[-1]
-        if True:
+        with torch.no_grad():
             self.flat.zero_()
             if self.prof is None:
                 for _, step in self.steps:
