@@ -300,6 +300,25 @@ int y5obb_pack_plan_create(const y5obb_pack_entry* entries, int n, y5obb_pack_pl
 int y5obb_pack_plan_run(const y5obb_pack_plan_t* plan, void* stream);
 void y5obb_pack_plan_destroy(y5obb_pack_plan_t* plan);
 
+/* ---- fused SGD-Nesterov + EMA step (EXPERIMENTAL in round 1: not yet validated on hardware) --------------------
+ * train.py:148-162,336-342 + utils/torch_utils.py:304-314 over every tensor in one launch.  group 0/1/2 index the per-step
+ * learning-rate table (BatchNorm weights / decayed weights / biases); group -1 = EMA only (floating-point buffers);
+ * ema may be NULL. */
+typedef struct y5obb_sgd_plan y5obb_sgd_plan_t;
+typedef struct {
+  float* p;          /* parameter (fp32 master weight), updated in place */
+  const float* g;    /* gradient */
+  float* mom;        /* momentum buffer */
+  float* ema;        /* EMA copy of p, or NULL */
+  int64_t n;
+  float weight_decay;
+  int group;
+} y5obb_sgd_entry;
+int y5obb_sgd_ema_plan_create(const y5obb_sgd_entry* entries, int n, y5obb_sgd_plan_t** out);
+int y5obb_sgd_ema_plan_run(const y5obb_sgd_plan_t* plan, const float* lr3, float momentum, float ema_decay, int first_step,
+                           void* stream);
+void y5obb_sgd_ema_plan_destroy(y5obb_sgd_plan_t* plan);
+
 /* ---- tile-merge polygon NMS of the DOTA devkit (EXPERIMENTAL in round 1: not yet validated on hardware) ----------
  * DOTA_devkit/ResultMerge_multi_process.py:62-123 py_cpu_nms_poly_fast over DOTA_devkit/polyiou.cpp:106-128 iou_poly, in
  * double precision without FMA contraction (bit-equal to the reference's g++ build by construction; oracle/poly_ref.py).

@@ -60,6 +60,9 @@ PROTOTYPES = {
     "y5obb_wgrad_create": (c_int, [c_void_p, ctypes.POINTER(c_void_p)]),
     "y5obb_wgrad_run": (c_int, [c_void_p, c_void_p]),
     "y5obb_wgrad_destroy": (None, [c_void_p]),
+    "y5obb_sgd_ema_plan_create": (c_int, [c_void_p, c_int, ctypes.POINTER(c_void_p)]),
+    "y5obb_sgd_ema_plan_run": (c_int, [c_void_p, c_void_p, c_float, c_float, c_int, c_void_p]),
+    "y5obb_sgd_ema_plan_destroy": (None, [c_void_p]),
     "y5obb_poly_nms_workspace_bytes": (c_size_t, [c_int64]),
     "y5obb_poly_nms_f64": (c_int, [c_void_p, c_int64, ctypes.c_double, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "y5obb_poly_iou_pairs_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),

@@ -104,3 +104,65 @@ class PackPlan:
             except Exception:
                 pass
             self._h = None
+
+
+class SgdEntry(ctypes.Structure):
+    """Mirror of y5obb_sgd_entry (include/y5obb.h)."""
+    _fields_ = [("p", c_void_p), ("g", c_void_p), ("mom", c_void_p), ("ema", c_void_p), ("n", c_int64),
+                ("weight_decay", ctypes.c_float), ("group", c_int)]
+
+
+class FusedSGDEMA:
+    """EXPERIMENTAL (not validated on hardware in round 1): optimizer.step() + ema.update() of train.py:336-342 as ONE launch.
+
+    groups: (g0, g1, g2) parameter lists as train.py:148-156 builds them; grads: {parameter: fp32 gradient tensor} with FIXED
+    storage (e.g. views of the backward plan's flat buffer); ema_model: a deep copy whose state_dict mirrors model's.
+    step(lr=(lr0, lr1, lr2), momentum, ema_decay) applies torch.optim.SGD(nesterov=True) arithmetic and the EMA rule."""
+
+    def __init__(self, model, groups, grads, ema_model=None, weight_decay: float = 0.0):
+        self.device = next(model.parameters()).device
+        ema_sd = dict(ema_model.state_dict()) if ema_model is not None else {}
+        name_of = {id(p): n for n, p in model.named_parameters()}
+        self.mom, ent, self._keep = {}, [], []
+        for gi, plist in enumerate(groups):
+            for p in plist:
+                g = grads[p]
+                assert p.dtype == torch.float32 and g.dtype == torch.float32 and p.is_contiguous() and g.is_contiguous()
+                m = torch.zeros_like(p)
+                self.mom[p] = m
+                e = ema_sd.get(name_of[id(p)])
+                ent.append(SgdEntry(p.data_ptr(), g.data_ptr(), m.data_ptr(), e.data_ptr() if e is not None else None, p.numel(),
+                                    float(weight_decay) if gi == 1 else 0.0, gi))
+                self._keep += [p, g, m, e]
+        if ema_model is not None:  # floating-point buffers (BatchNorm running statistics): EMA only
+            msd = dict(model.state_dict())
+            pnames = set(name_of.values())
+            for k, e in ema_sd.items():
+                if k in pnames or not e.dtype.is_floating_point:
+                    continue
+                v = msd[k]
+                ent.append(SgdEntry(v.data_ptr(), None, None, e.data_ptr(), v.numel(), 0.0, -1))
+                self._keep += [v, e]
+        arr = (SgdEntry * len(ent))(*ent)
+        self._h = c_void_p()
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().y5obb_sgd_ema_plan_create(arr, len(ent), ctypes.byref(self._h))
+        _lib.check(rc, "y5obb_sgd_ema_plan_create")
+        self.steps = 0
+
+    def step(self, lr, momentum: float, ema_decay: float = 0.0, stream=None):
+        lr3 = (ctypes.c_float * 3)(*[float(v) for v in lr])
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().y5obb_sgd_ema_plan_run(self._h, lr3, float(momentum), float(ema_decay), int(self.steps == 0),
+                                                   stream if stream is not None else _lib.stream_ptr(self.device))
+        _lib.check(rc, "y5obb_sgd_ema_plan_run")
+        self.steps += 1
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                _lib.lib().y5obb_sgd_ema_plan_destroy(h)
+            except Exception:
+                pass
+            self._h = None
