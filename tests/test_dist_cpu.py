@@ -104,3 +104,42 @@ def test_two_rank_gradient_allreduce_is_one_call_and_a_sum():
         assert flat == [6.0 * i for i in range(n)]           # (1x + 2x) = 3x on both ranks, summed once more through ._base
         assert flat_calls == [n, n]                          # ONE collective over the whole buffer, both times
         assert per_tensor_calls == 6                         # fallback path: conv w/b, bn w/b, conv w/b
+
+
+def _bcast_worker(rank, ws, port, q):
+    """Replicas seeded per rank (init_seeds(1 + RANK), train.py:100) must start from rank 0's weights and BatchNorm
+    statistics, as DDP's constructor broadcast guarantees (train.py:214): dist_util.broadcast_model_state, called by
+    TrainStep.__init__ before the optimizer and the EMA copy are built."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(ws))
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    from yolov5_obb_b200.dist_util import broadcast_model_state
+    torch.manual_seed(1 + rank)
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3), torch.nn.BatchNorm2d(4), torch.nn.Conv2d(4, 2, 1))
+    with torch.no_grad():
+        net[1].running_mean += rank + 0.5
+        net[1].num_batches_tracked += 7 * (rank + 1)
+    ptrs = [p.data_ptr() for p in net.parameters()]
+    before = torch.cat([p.detach().flatten() for p in net.parameters()]).clone()
+    n = broadcast_model_state(net, 0)
+    after = torch.cat([p.detach().flatten() for p in net.parameters()])
+    q.put((rank, n, before.tolist(), after.tolist(), net[1].running_mean.tolist(), int(net[1].num_batches_tracked),
+           ptrs == [p.data_ptr() for p in net.parameters()]))
+    dist.destroy_process_group()
+
+
+def test_two_rank_start_up_broadcast():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bcast_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    (_, n0, b0, a0, rm0, nbt0, same0), (_, n1, b1, a1, rm1, nbt1, same1) = res
+    assert b0 != b1                                   # the per-rank seeds really differ
+    assert a0 == b0 and a1 == b0                      # every rank now holds rank 0's parameters
+    assert rm0 == rm1 == [0.5] * 4 and nbt0 == nbt1 == 7
+    assert n0 == n1 == 6 + 3 and same0 and same1      # 6 parameters + 3 buffers, written in place (plans keep their pointers)

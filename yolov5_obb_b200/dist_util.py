@@ -37,3 +37,19 @@ def sum_over_ranks(value: float, device="cpu") -> float:
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return float(t.item())
+
+
+def broadcast_model_state(model, src: int = 0) -> int:
+    """What DistributedDataParallel does at construction (train.py:214 `DDP(model, ...)`): every parameter and every
+    buffer of rank `src` replaces the other ranks' copies, so replicas seeded per rank (init_seeds(1 + RANK),
+    train.py:100) start from identical weights and BatchNorm statistics.  In place (`.data.copy_`-free: the broadcast
+    writes the storages the device plans point at).  Returns the number of tensors sent."""
+    rank, ws = world()
+    if ws == 1:
+        return 0
+    n = 0
+    with torch.no_grad():
+        for t in list(model.parameters()) + list(model.buffers()):
+            dist.broadcast(t.data, src=src)
+            n += 1
+    return n

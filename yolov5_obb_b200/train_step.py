@@ -89,13 +89,21 @@ class TrainStep:
         self.hyp["label_smoothing"] = 0.0
         model.hyp = self.hyp
         model.nc = model.model[-1].nc
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        if self.world > 1:
+            # DDP broadcasts rank 0's parameters and buffers when it wraps the model (train.py:214); the reference seeds
+            # per rank (train.py:100), so without this the replicas would start from different weights.  Done BEFORE the
+            # optimizer and the EMA copy are built.
+            from .dist_util import broadcast_model_state
+            broadcast_model_state(model, 0)
+            if hasattr(model, "_bump_generation"):
+                model._bump_generation()
         g0, g1, g2 = param_groups(model)
         self.optimizer = torch.optim.SGD(g0, lr=self.hyp["lr0"], momentum=self.hyp["momentum"], nesterov=True, foreach=True)
         self.optimizer.add_param_group({"params": g1, "weight_decay": self.hyp["weight_decay"]})
         self.optimizer.add_param_group({"params": g2})
         self.ema = ModelEMA(model) if ema else None
         self.compute_loss = ComputeLoss(model)
-        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.ni = 0
         self._last_opt = -1
         self.optimizer.zero_grad(set_to_none=True)

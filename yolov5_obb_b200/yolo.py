@@ -231,6 +231,13 @@ class Model(nn.Module):
                 mod.momentum = 0.03
         self._engines = {}
         self._fused = False
+        self._generation = 0
+
+    def _bump_generation(self):
+        """Explicit staleness signal for the inference plans: called by everything that writes parameters or statistics
+        through raw pointers (training forwards, the fused optimizer step, a start-up broadcast), which tensor version
+        counters do not see."""
+        self._generation = getattr(self, "_generation", 0) + 1
 
     def _strides(self):
         s, out = [], {}
@@ -295,6 +302,7 @@ class Model(nn.Module):
                 eng = self._engines[key] = TrainEngine(self, x.shape[0], x.shape[2], x.shape[3], x.device)
             eng._refresh_next = refresh
             self._last_train_engine = eng
+            self._bump_generation()  # running statistics move (the captured graph bumps no version counter)
             if not torch.is_grad_enabled():
                 return eng.forward(x, refresh)
             params = [p for p in self.parameters() if p.requires_grad]
@@ -318,4 +326,5 @@ class Model(nn.Module):
             self._sig_nbt = [b for n, b in self.named_buffers() if n.endswith("num_batches_tracked")]
         # (the training kernels write running statistics through raw pointers: they bump num_batches_tracked, which a
         # torch op increments, so the sum of its version counters moves with every training forward)
-        return (sum(t._version for t in tr), sum(t._version for t in self._sig_nbt), id(tr[0]) if tr else 0)
+        return (sum(t._version for t in tr), sum(t._version for t in self._sig_nbt), id(tr[0]) if tr else 0,
+                getattr(self, "_generation", 0))
