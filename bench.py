@@ -57,6 +57,9 @@ def parse():
     ap.add_argument("--train-model", default=TRAIN_MODEL)
     ap.add_argument("--train-batch", type=int, default=TRAIN_BATCH)
     ap.add_argument("--train-steps", type=int, default=10)
+    ap.add_argument("--no-nms-sweep", action="store_true", help="skip the rotated-NMS boxes/s sweep (the `nms` object)")
+    ap.add_argument("--no-eager", action="store_true", help="skip the eager-PyTorch-on-this-GPU bar (`extra.eager_torch_b200`)")
+    ap.add_argument("--no-parity-gate", action="store_true", help="skip the engine-vs-oracle check of the benchmarked plan")
     return ap.parse_args()
 
 
@@ -173,10 +176,19 @@ def cpu_arm(size, batch, steps, warmup, budget_s=25.0, use_ref_nms=False):
         except Exception as e:  # pragma: no cover
             nms_note += f" [oracle/_ref unavailable: {type(e).__name__}]"
 
+    split = [0.0, 0.0, 0.0]  # the reference's three timers (val.py:183-207): pre-process, inference, NMS
+
     def step():
+        t = [time.perf_counter()]
         x = x8.float() / 255                      # pre-process (val.py:187-188)
+        t.append(time.perf_counter())
         pred, _ = model_ref.forward(m, x)         # inference
-        return cpu_nms(pred, CONF, IOU, multi_label=True, max_det=MAX_DET, nms_mode=0)  # NMS (CPU rule >=)
+        t.append(time.perf_counter())
+        r = cpu_nms(pred, CONF, IOU, multi_label=True, max_det=MAX_DET, nms_mode=0)  # NMS (CPU rule >=)
+        t.append(time.perf_counter())
+        for i in range(3):
+            split[i] = t[i + 1] - t[i]            # the last step's split is reported
+        return r
 
     t0 = time.perf_counter()
     step()                                   # warm-up (page-in, thread pools); a second one only if steps are short
@@ -194,6 +206,8 @@ def cpu_arm(size, batch, steps, warmup, budget_s=25.0, use_ref_nms=False):
             step()
         dt, cold = (time.perf_counter() - t0) / n, ""
     return dict(value=b / dt, unit="images/s", cores=cores, kind=kind, ms_per_step=dt * 1e3, steps=n,
+                split_ms={"pre": split[0] * 1e3, "inference": split[1] * 1e3, "nms": split[2] * 1e3},
+                value_without_nms=b / max(split[0] + split[1], 1e-9),
                 sample=f"yolov5{size} fp32 eager-torch restatement of the reference CPU path + {nms_note}, "
                        f"{n} steps of 1 tile 1024x1024 (of the b{batch} workload){cold}, torch {torch.__version__}, {cores} threads")
 
@@ -208,8 +222,11 @@ def run_reference(args):
         "steps": cb["steps"], "warmup": min(args.warmup, 2), "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args),
-        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "split_ms", "value_without_nms")},
         "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "split_ms shows where the CPU step goes: the reference's nms_rotated_cpu is single-threaded and quadratic in "
+                "the candidate count (SURVEY 2.3), so this arm's images/s is dominated by NMS on the synthetic tiles' "
+                "candidate load; value_without_nms is pre-process + inference alone",
     }
     if not args.no_train:  # the train-step leg of the metric on the same CPU arm (train.py --device cpu restated)
         tb = cpu_train_arm(args.train_model, budget_s=45.0)
@@ -336,6 +353,193 @@ def run_train_leg(args, dev, world, rank, dist, pk):
     return out
 
 
+
+# ------------------------------------------------------------------------------------------------
+# rotated-NMS leg of the metric (BASELINE configs[3]): boxes/s and pair-IoUs/s, 1k-200k candidates, 15 classes, IoU 0.4
+# ------------------------------------------------------------------------------------------------
+NMS_SIZES = (1000, 2000, 5000, 10000, 20000, 50000, 100000, 200000)
+NMS_THR, NMS_CLASSES = 0.4, 15
+
+
+def nms_sweep(dev, seeds=(0, 1, 2), cpu_budget_s=25.0):
+    """N candidates of 15 classes in one 1024^2 frame ("dense": realistic suppression) and in a 16384^2 frame
+    ("sparse": nothing suppressed, worst case for the pair count), unique scores, thr 0.4.  Per (layout, N), median over
+    the seeds:  ours through the reference-facing op nms_rotated(dets, scores, thr) on class-OFFSET boxes (the reference's
+    own mode, general.py:849-851) and through the segmented op on raw boxes; the reference's CUDA kernel K1
+    (nms_rotated_cuda.cu compiled from /root/reference into oracle/_ref) on the same GPU and inputs, keep lists compared;
+    the reference's CPU kernel for the sizes a time budget allows."""
+    import ctypes
+    import numpy as np
+    import torch
+    from tests.boxgen import rboxes
+    from yolov5_obb_b200 import _lib
+    from yolov5_obb_b200.nms_rotated import nms_rotated, nms_rotated_batched
+    L = _lib.lib()
+    ref = None
+    try:
+        from oracle.build_ref import load_ref
+        ref = load_ref()
+    except Exception as e:  # pragma: no cover
+        ref_err = f"{type(e).__name__}: {e}"
+
+    def wall(fn):
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        r = fn()
+        torch.cuda.synchronize(dev)
+        return (time.perf_counter() - t0) * 1e3, r
+
+    rows, cpu_left = [], cpu_budget_s
+    for layout, span in (("dense", 1024.0), ("sparse", 16384.0)):
+        for n in NMS_SIZES:
+            t_off, t_seg, t_ref, stages, kept, equal = [], [], [], [], [], []
+            pairs = 0
+            for seed in seeds:
+                d, sc, cls = rboxes(n, span, 1000 * seed + 17, n_classes=NMS_CLASSES, class_offset=False)
+                cnt = np.bincount(cls, minlength=NMS_CLASSES).astype(np.int64)
+                pairs = int((cnt * (cnt - 1) // 2).sum())
+                d_off = d.copy()
+                d_off[:, :2] += cls[:, None].astype(np.float32) * np.float32(4096)
+                td, to, ts_, tc = (torch.from_numpy(a).to(dev) for a in (d, d_off, sc, cls.astype(np.int32)))
+                nms_rotated(to, ts_, NMS_THR)                                   # warm-up (workspace growth, first launch)
+                L.y5obb_nms_debug_stage_timing(1)
+                ms, keep = wall(lambda: nms_rotated(to, ts_, NMS_THR))
+                st4 = (ctypes.c_float * 4)()
+                if L.y5obb_nms_debug_stage_ms(st4) == 0:
+                    stages.append([float(v) for v in st4])
+                L.y5obb_nms_debug_stage_timing(0)
+                t_off.append(ms)
+                kept.append(int(keep.numel()))
+                nms_rotated_batched(td, ts_, tc, NMS_CLASSES, NMS_THR)
+                ms2, (k2, c2, o2) = wall(lambda: nms_rotated_batched(td, ts_, tc, NMS_CLASSES, NMS_THR))
+                t_seg.append(ms2)
+                # the segmented result, merged back into one score-ordered list, is the offset-mode keep set
+                c2h, o2h = c2.tolist(), o2.tolist()
+                seg_keep = torch.cat([k2[o2h[g]:o2h[g] + c2h[g]] for g in range(NMS_CLASSES)])
+                seg_keep = seg_keep[torch.argsort(ts_[seg_keep], descending=True)]
+                same_seg = bool(torch.equal(seg_keep, keep))
+                if ref is not None:
+                    ref.nms_rotated_cuda(to[: min(n, 2000)], ts_[: min(n, 2000)], NMS_THR)
+                    ms3, kref = wall(lambda: ref.nms_rotated_cuda(to, ts_, NMS_THR))
+                    t_ref.append(ms3)
+                    equal.append(bool(torch.equal(kref, keep)) and same_seg)
+                else:
+                    equal.append(same_seg)
+            med = lambda v: float(np.median(v)) if v else None
+            stg = [float(np.median([s_[i] for s_ in stages])) for i in range(4)] if stages else None
+            row = {"layout": layout, "n": n, "pairs_algorithmic": pairs, "kept": int(np.median(kept)),
+                   "ms": med(t_off), "boxes_per_s": n / (med(t_off) / 1e3), "pair_ious_per_s": pairs / (med(t_off) / 1e3),
+                   "GBps_on_24B_per_box": 24.0 * n / (med(t_off) / 1e3) / 1e9,
+                   "stage_ms": dict(zip(("sort", "plan_prep", "k_tiles", "k_reduce"), stg)) if stg else None,
+                   "segmented_ms": med(t_seg), "segmented_boxes_per_s": n / (med(t_seg) / 1e3),
+                   "reference_k1_ms": med(t_ref), "speedup_vs_reference_k1": (med(t_ref) / med(t_off)) if t_ref else None,
+                   "keep_lists_equal": all(equal)}
+            # the reference's CPU kernel (single thread, quadratic): only while the time budget lasts
+            if ref is not None and n <= 10000 and cpu_left > 0:
+                est = 1.7e-6 * (n * n / 2 if layout == "sparse" else n * max(row["kept"], 1))
+                if est < cpu_left:
+                    d, sc, cls = rboxes(n, span, 17, n_classes=NMS_CLASSES, class_offset=True)
+                    t0 = time.perf_counter()
+                    kc = ref.nms_rotated_cpu(torch.from_numpy(d), torch.from_numpy(sc), NMS_THR)
+                    dt = time.perf_counter() - t0
+                    cpu_left -= dt
+                    row["reference_cpu_ms"] = dt * 1e3
+                    row["reference_cpu_kept"] = int(kc.numel())
+            rows.append(row)
+    big = [r for r in rows if r["n"] == 200000 and r["layout"] == "dense"][0]
+    return {"workload": "rotated-NMS + rotated-IoU sweep (BASELINE configs[3]): N candidate rboxes, 15 classes, IoU 0.4, unique "
+                        "scores, seeds 0-2 (median); dense = one 1024^2 frame, sparse = 16384^2 frame; class-offset boxes "
+                        "through nms_rotated (the reference's mode), raw boxes through the segmented op",
+            "metric": "rotated-NMS boxes/s", "value": big["boxes_per_s"], "unit": "boxes/s", "at": "dense, N = 200000",
+            "timing": "wall clock around the op with a device synchronize on both sides (the op returns a variable-length "
+                      "tensor: one 8-byte host read inside); stage_ms from CUDA events inside the op",
+            "reference_k1": "utils/nms_rotated/src/nms_rotated_cuda.cu compiled unmodified (oracle/_ref), same GPU, same "
+                            "inputs" if ref is not None else f"unavailable ({ref_err})",
+            "all_keep_lists_equal": all(r["keep_lists_equal"] for r in rows), "rows": rows}
+
+
+# ------------------------------------------------------------------------------------------------
+# parity gate of the benchmarked plan, and the eager-PyTorch bar on the same GPU
+# ------------------------------------------------------------------------------------------------
+def parity_gate(model_cpu, x_u8_dev, pred, sample=(0, -1), tol=3e-2):
+    """The exact plan the timing runs (b16 x 1024^2: its own tile geometry, stem padding, 16 images per grid) against the
+    fp32 oracle (oracle/model_ref on the host, test infrastructure) on sampled images of the batch: relative L2 of the
+    decoded prediction per Detect level, and agreement of the `obj > conf` candidate masks.  Raises if it fails."""
+    import torch
+    from oracle import model_ref
+    B = x_u8_dev.shape[0]
+    idx = sorted({i % B for i in sample})
+    x = x_u8_dev[idx].cpu().float() / 255
+    want, _ = model_ref.forward(model_cpu, x)
+    got = pred[idx].float().cpu()
+    det = model_cpu.model[-1]
+    H = x.shape[2]
+    rows = [det.na * (H // int(s)) ** 2 for s in det.stride.tolist()]
+    out, o = {"images": idx, "tolerance_rel_l2": tol, "levels": []}, 0
+    for l, r in enumerate(rows):
+        g, w = got[:, o:o + r], want[:, o:o + r]
+        rel = ((g - w).norm() / w.norm()).item()
+        out["levels"].append({"stride": int(det.stride[l]), "rel_l2": rel, "max_abs_box_px": (g[..., :4] - w[..., :4]).abs().max().item()})
+        o += r
+    cg, cw = got[..., 4] > CONF, want[..., 4] > CONF
+    inter, union = (cg & cw).sum().item(), (cg | cw).sum().item()
+    out["obj_candidate_mask_iou"] = inter / max(union, 1)
+    out["candidates_engine_vs_oracle"] = [int(cg.sum()), int(cw.sum())]
+    out["ok"] = all(lv["rel_l2"] < tol for lv in out["levels"]) and out["obj_candidate_mask_iou"] > 0.9
+    if not out["ok"]:
+        raise RuntimeError(f"parity gate failed: the benchmarked plan disagrees with the fp32 oracle: {out}")
+    return out
+
+
+def eager_torch_arm(model_cpu, x_u8_dev, steps, warmup):
+    """The reference's own GPU path restated (oracle/eager_ref.py: fused fp16 model through cuDNN with cudnn.benchmark, Detect,
+    the per-image non_max_suppression_obb loop over the reference's CUDA kernel K1) on this GPU, same tiles, same step
+    definition (pre-process + inference + NMS).  The bar SURVEY §2.3 L1 names - not the target."""
+    import torch
+    from oracle.eager_ref import EagerFusedModel
+    from oracle.postprocess import non_max_suppression_obb as loop_nms, ref_obb_nms_cuda
+    from oracle.build_ref import load_ref
+    dev = x_u8_dev.device
+    ref = load_ref()
+    nms_fn = ref_obb_nms_cuda(ref)
+    old = torch.backends.cudnn.benchmark
+    torch.backends.cudnn.benchmark = True
+    try:
+        em = EagerFusedModel(model_cpu, dev, half=True)
+
+        def step():
+            x = x_u8_dev.half() / 255                                   # val.py:187-188
+            pred = em.forward(x)                                        # val.py:191
+            return loop_nms(pred, CONF, IOU, multi_label=True, max_det=MAX_DET, nms_fn=nms_fn), pred
+
+        for _ in range(max(warmup, 3)):
+            step()
+        torch.cuda.synchronize(dev)
+        t_inf = t_nms = 0.0
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        t0 = time.perf_counter()
+        n_det = 0
+        for _ in range(steps):
+            e[0].record()
+            pred = em.forward(x_u8_dev.half() / 255)
+            e[1].record()
+            dets = loop_nms(pred, CONF, IOU, multi_label=True, max_det=MAX_DET, nms_fn=nms_fn)
+            e[2].record()
+            torch.cuda.synchronize(dev)
+            t_inf += e[0].elapsed_time(e[1])
+            t_nms += e[1].elapsed_time(e[2])
+            n_det = sum(d.shape[0] for d in dets)
+        dt = (time.perf_counter() - t0) / steps
+    finally:
+        torch.backends.cudnn.benchmark = old
+    B = x_u8_dev.shape[0]
+    return {"value": B / dt, "unit": "images/s", "ms_per_step": dt * 1e3, "inference_ms": t_inf / steps, "nms_ms": t_nms / steps,
+            "steps": steps, "detections_per_image": n_det / B, "dtype": "fp16 (model.half(), val.py:128,142)",
+            "what": "eager PyTorch " + torch.__version__ + " / cuDNN " + str(torch.backends.cudnn.version()) +
+                    ", cudnn.benchmark=True, NCHW, BatchNorm folded (Conv.forward_fuse); non_max_suppression_obb per-image loop "
+                    "with the reference's nms_rotated_cuda (K1 + N^2/8-byte mask D2H + host scan); same GPU, tiles and step "
+                    "definition; timed by wall clock with a synchronize per step (its NMS synchronises anyway)"}
+
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
@@ -354,13 +558,19 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     B = args.batch
-    model = build_model(args.model, dev)
+    import copy
+    model_cpu = build_model(args.model)
+    model = copy.deepcopy(model_cpu).to(dev)
     # every replica processes the same seeded tile set: the NMS stage is data dependent (candidates per tile), and with four
     # distinct tiles per batch a per-rank seed made rank 1's step 12 % longer than rank 0's - sample noise, not scaling
     x_host = synth_batch(B, seed=0).pin_memory()
     x_dev = x_host.to(dev)
-    model(x_dev)  # builds the plan
+    pred0, _ = model(x_dev)  # builds the plan
     eng = model._engines[(tuple(x_dev.shape), dev.index)]
+    # the number below is only worth reporting if THIS plan computes the right thing: compare it with the oracle first
+    parity = None
+    if not args.no_parity_gate and rank == 0:
+        parity = parity_gate(model_cpu, x_dev, pred0)
     conv_flops = [c.info()["flops"] for c in eng.convs]
     n_conv = len(eng.convs)
     st = _lib.stream_ptr(dev)
@@ -473,6 +683,16 @@ def run_ours(args):
             "hbm_view": {"algorithmic_GB_per_step": eng.hbm_bytes / 1e9,
                          "achieved_GBps": eng.hbm_bytes / (tot_conv_ms / 1e3) / 1e9, "peak_GBps": pk["hbm"]}}
 
+    # the other half of the metric (rotated-NMS boxes/s) and the eager-PyTorch bar: single-GPU runs only, rank 0
+    nms, eager = None, None
+    if world == 1 and not args.no_nms_sweep:
+        nms = nms_sweep(dev)
+    if world == 1 and not args.no_eager:
+        try:
+            eager = eager_torch_arm(model_cpu, x_dev, steps=min(args.steps, 10), warmup=3)
+        except Exception as e:  # the bar needs oracle/_ref (the reference's K1): report its absence, never fake it
+            eager = {"unavailable": f"{type(e).__name__}: {e}"}
+
     # train-step leg (all ranks take part: the gradient all-reduce is the path's one exchange step)
     train = None
     if not args.no_train:
@@ -498,9 +718,15 @@ def run_ours(args):
         "detections_per_image": det_per_img,
         "clocks": clocks, "roofline": roof,
     }
+    if parity is not None:
+        line["parity"] = parity
+    if nms is not None:
+        line["nms"] = nms
+    if eager is not None:
+        line["extra"] = {"eager_torch_b200": eager}
     if not args.no_cpu_baseline and world == 1:
         cb = cpu_arm(args.model, B, args.steps, args.warmup)
-        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "split_ms", "value_without_nms")}
     if train is not None:
         line["train"] = train
         if not args.no_cpu_baseline and world == 1:

@@ -68,6 +68,12 @@ int y5obb_nms_rotated_batched_f32(const float* dets5, const float* scores, const
                                   int64_t* keep_out, int64_t* n_keep_out, int64_t* seg_off_out,
                                   void* workspace, size_t workspace_bytes, void* stream);
 
+/* Profiling aid for the single-pass NMS (y5obb_nms_rotated[_batched]_f32): with timing on, CUDA events are recorded on the
+ * caller's stream between the stages; y5obb_nms_debug_stage_ms then returns {key+radix sort, segments/plan/prep, k_tiles
+ * (pairwise IoU bit matrix), k_reduce (greedy scan + compaction)} of the most recent call in milliseconds. */
+int y5obb_nms_debug_stage_timing(int on);
+int y5obb_nms_debug_stage_ms(float* ms4);
+
 /* Pairwise rotated IoU of n independent pairs (a[i], b[i]), each 5 floats.  Device restatement of
  * utils/nms_rotated/src/box_iou_rotated_utils.h:334-360 (single_box_iou_rotated<float>). */
 int y5obb_rbox_iou_pairs_f32(const float* a5, const float* b5, float* iou_out, int64_t n, void* stream);
@@ -105,6 +111,10 @@ typedef struct y5obb_conv y5obb_conv_t;
 #define Y5OBB_CONV_BIAS_HALVED 8    /* flags: REQUIRED when act = 1: `bias` holds 0.5 * b (SiLU is evaluated as h + h*tanh(h), h = x/2) */
 #define Y5OBB_CONV_NO_GROUP 16      /* flags: one (tap, K-chunk) unit per pipeline stage */
 #define Y5OBB_CONV_NO_PAIRW 4      /* flags: stride-2 convs use TMA element strides along W instead of the pixel-pair view */
+#define Y5OBB_CONV_NO_PDL 32       /* flags: plain stream-ordered launch (default: programmatic dependent launch - the kernel's
+                                      prologue overlaps the previous kernel's tail and it waits, griddepcontrol.wait, before its
+                                      first global-memory access; also switched off by the environment variable Y5OBB_NO_PDL=1) */
+#define Y5OBB_CONV_ACC2 64         /* flags: two TMEM accumulator stages only (A-B comparison; default: as many as 512 columns hold) */
 
 typedef struct {
   const void* in;            /* bf16 NHWC slice */
@@ -146,6 +156,9 @@ int y5obb_conv_run(const y5obb_conv_t* conv, void* stream);
 int y5obb_conv_info(const y5obb_conv_t* conv, double* flops, double* hbm_bytes, int* grid, int* block_n,
                     int* block_k, int* stages);
 void y5obb_conv_destroy(y5obb_conv_t* conv);
+/* Profiling aid: CTA 0 of every later run writes clock64() stamps of its producer / MMA / epilogue roles for its first 32
+ * tiles into dev_buf ([3][32][8] uint64, device memory; NULL switches it off).  Results are unaffected. */
+int y5obb_conv_debug_timestamps(y5obb_conv_t* conv, unsigned long long* dev_buf);
 
 /* ---- HBM-bound helpers around the conv stack -------------------------------------------------
  * y5obb_stem_s2d: NCHW fp32 image [B,3,H,W] -> 2x2 space-to-depth NHWC bf16 [B,H/2,W/2,16] (channel
@@ -300,7 +313,7 @@ int y5obb_pack_plan_create(const y5obb_pack_entry* entries, int n, y5obb_pack_pl
 int y5obb_pack_plan_run(const y5obb_pack_plan_t* plan, void* stream);
 void y5obb_pack_plan_destroy(y5obb_pack_plan_t* plan);
 
-/* ---- fused SGD-Nesterov + EMA step (EXPERIMENTAL in round 1: not yet validated on hardware) --------------------
+/* ---- fused SGD-Nesterov + EMA step -------------------------------------------------------------------------------
  * train.py:148-162,336-342 + utils/torch_utils.py:304-314 over every tensor in one launch.  group 0/1/2 index the per-step
  * learning-rate table (BatchNorm weights / decayed weights / biases); group -1 = EMA only (floating-point buffers);
  * ema may be NULL. */
@@ -319,7 +332,7 @@ int y5obb_sgd_ema_plan_run(const y5obb_sgd_plan_t* plan, const float* lr3, float
                            void* stream);
 void y5obb_sgd_ema_plan_destroy(y5obb_sgd_plan_t* plan);
 
-/* ---- tile-merge polygon NMS of the DOTA devkit (EXPERIMENTAL in round 1: not yet validated on hardware) ----------
+/* ---- tile-merge polygon NMS of the DOTA devkit (CPU form, double precision) ---------------------------------------
  * DOTA_devkit/ResultMerge_multi_process.py:62-123 py_cpu_nms_poly_fast over DOTA_devkit/polyiou.cpp:106-128 iou_poly, in
  * double precision without FMA contraction (bit-equal to the reference's g++ build by construction; oracle/poly_ref.py).
  * dets9: [n][9] = x1 y1 x2 y2 x3 y3 x4 y4 score (device).  keep_out: indices in descending score order. */

@@ -20,7 +20,7 @@ from tests.predgen import synth_pred  # noqa: E402
 
 
 
-from tests.golden_cfgs import PP_CFGS as CFGS, PP_ANCHORS as ANCHORS  # noqa: E402
+from tests.golden_cfgs import PP_CFGS as CFGS, PP_ANCHORS as ANCHORS, PP_OVERMAX  # noqa: E402
 
 
 def main():
@@ -43,6 +43,21 @@ def main():
         for b, r in enumerate(res):
             out[f"{name}/{b}"] = r.numpy()
         print(name, "seed", seed, [tuple(r.shape) for r in res])
+    # > 30 000 candidates per image, degenerate boxes inside the top 30 000 (the reference's clamp-then-drop order)
+    seed = 0
+    while True:
+        pred = torch.from_numpy(synth_pred(seed=seed, **PP_OVERMAX["pred"]))
+        res = non_max_suppression_obb(pred.clone(), **PP_OVERMAX["kw"])
+        o0 = oracle_nms(pred, nms_mode=0, **PP_OVERMAX["kw"])
+        o1 = oracle_nms(pred, nms_mode=1, **PP_OVERMAX["kw"])
+        if all(torch.equal(a, b) and torch.equal(a, c) for a, b, c in zip(res, o0, o1)):
+            break
+        seed += 1
+    out["overmax/seed"] = np.int64(seed)
+    for b, r in enumerate(res):
+        assert r.shape[0] < PP_OVERMAX["kw"]["max_det"]  # the lowest-ranked keepers must be visible
+        out[f"overmax/{b}"] = r.numpy()
+    print("overmax seed", seed, [tuple(r.shape) for r in res])
     np.savez_compressed(HERE / "postprocess_golden.npz", **out)
 
 

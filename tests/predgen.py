@@ -4,12 +4,12 @@ to store the reference function's OUTPUT."""
 import numpy as np
 
 
-def synth_pred(B=2, A=3000, nc=15, seed=0, frac_obj=0.3, span=1024.0):
+def synth_pred(B=2, A=3000, nc=15, seed=0, frac_obj=0.3, span=1024.0, clusters=None, n_tiny=0):
     rng = np.random.default_rng(seed)
     no = nc + 185
     p = np.zeros((B, A, no), np.float32)
     for b in range(B):
-        K = max(A // 8, 1)
+        K = clusters if clusters else max(A // 8, 1)
         oc = rng.uniform(0, span, (K, 2))
         ol = np.exp(rng.uniform(np.log(8), np.log(300), K))
         os_ = ol * rng.uniform(0.15, 1.0, K)
@@ -35,4 +35,10 @@ def synth_pred(B=2, A=3000, nc=15, seed=0, frac_obj=0.3, span=1024.0):
     # a few degenerate rows: tiny boxes (dropped by obb_nms), exact duplicates
     p[:, 0, 2] = 1e-4
     p[:, 1, :] = p[:, 2, :]
+    if n_tiny:  # degenerate boxes with high scores: they rank inside the top-max_nms and are dropped only afterwards
+        r2 = np.random.default_rng(seed + 1000)
+        for b in range(B):
+            rows = r2.choice(A, n_tiny, replace=False)
+            p[b, rows, 2 + r2.integers(0, 2, n_tiny)] = 1e-4
+            p[b, rows, 4] = r2.uniform(0.8, 1.0, n_tiny)
     return p

@@ -21,3 +21,20 @@ def test_postprocess_oracle_matches_reference_output(name):
         res = non_max_suppression_obb(pred, nms_mode=mode, **PP_CFGS[name])
         for b, r in enumerate(res):
             assert np.array_equal(r.numpy(), G[f"{name}/{b}"]), (name, mode, b)
+
+
+def test_postprocess_oracle_over_max_nms_order():
+    """> 30 000 candidates per image with degenerate boxes ranked inside the top 30 000: the reference clamps by score
+    first (general.py:845-846) and drops min(w,h) < 0.001 afterwards (nms_rotated_wrapper.py:32-39)."""
+    from tests.golden_cfgs import PP_OVERMAX
+    G = np.load(ROOT / "tests" / "golden" / "postprocess_golden.npz")
+    pred = torch.from_numpy(synth_pred(seed=int(G["overmax/seed"]), **PP_OVERMAX["pred"]))
+    res = non_max_suppression_obb(pred, nms_mode=1, **PP_OVERMAX["kw"])
+    for b, r in enumerate(res):
+        assert np.array_equal(r.numpy(), G[f"overmax/{b}"]), b
+    # the other order (drop first, clamp second) gives a different answer on this input: the case discriminates
+    tiny = pred[..., 2:4].min(-1)[0] < 0.001
+    other = pred.clone()
+    other[..., 4] = torch.where(tiny, torch.zeros(()), other[..., 4])
+    res2 = non_max_suppression_obb(other, nms_mode=1, **PP_OVERMAX["kw"])
+    assert any(a.shape != b.shape for a, b in zip(res, res2))

@@ -1,6 +1,5 @@
-"""GPU parity of the EXPERIMENTAL tile-merge polygon NMS (csrc/poly_nms.cu) against the reference's polyiou.cpp outputs
-(tests/golden/poly_golden.npz): IoU bit-equal, keep lists equal.  Skipped unless Y5OBB_EXPERIMENTAL=1: the kernels have
-not been validated on hardware in round 1 (no GPU budget was left when they were written)."""
+"""GPU parity of the tile-merge polygon NMS (csrc/poly_nms.cu) against the reference's polyiou.cpp outputs
+(tests/golden/poly_golden.npz): IoU bit-equal, keep lists equal."""
 import os
 from pathlib import Path
 
@@ -8,8 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("Y5OBB_EXPERIMENTAL") != "1", reason="experimental kernels: set Y5OBB_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parents[1]
 DEV = "cuda:0"
 

@@ -96,3 +96,25 @@ def test_class_split_equals_single_pass_and_falls_back():
     for b in range(3):
         g, e = got[b].cpu().numpy(), exp[b].numpy()
         assert g.shape == e.shape and (g == e).all(1).mean() > 0.995
+
+
+@pytest.mark.parametrize("nosplit", [False, True])
+def test_over_max_nms_reference_order(nosplit):
+    """More than max_nms = 30 000 candidates per image, degenerate boxes among the top 30 000: rows bit-exact against the
+    REFERENCE function's output (clamp by score first, general.py:845-846; too-small filter second,
+    nms_rotated_wrapper.py:32-39), on the class-split path and on the one-pass path."""
+    import yolov5_obb_b200.general as G
+    from tests.golden_cfgs import PP_OVERMAX
+    gold = np.load(ROOT / "tests" / "golden" / "postprocess_golden.npz")
+    cfg = PP_OVERMAX["pred"]
+    pred = synth_pred(seed=int(gold["overmax/seed"]), **cfg)
+    key = (cfg["B"], cfg["A"], cfg["nc"])
+    G._NO_SPLIT.clear()
+    if nosplit:
+        G._NO_SPLIT[key] = True
+    try:
+        res = _run(pred, **PP_OVERMAX["kw"])
+    finally:
+        G._NO_SPLIT.clear()
+    for b, r in enumerate(res):
+        assert np.array_equal(r.cpu().numpy(), gold[f"overmax/{b}"]), (b, r.shape, gold[f"overmax/{b}"].shape)

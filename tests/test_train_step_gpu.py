@@ -88,3 +88,58 @@ def test_eval_after_training_uses_the_updated_weights():
     rel = ((p1.cpu() - want).norm() / want.norm()).item()
     assert rel < 2e-2, rel
     assert (p1 - p0).abs().max().item() > 1e-3               # and the output really changed
+
+
+def _oracle_trajectory(m, imgs_u8, tg, steps, imgsz, emulate_bf16):
+    """train.py:296-342 restated on the CPU in fp32 (oracle/model_ref + loss_ref + torch.optim.SGD with the reference's three
+    parameter groups): the loss of every step on one repeated batch."""
+    from oracle import model_ref, loss_ref
+    from yolov5_obb_b200.train_step import HYP_FINETUNE_DOTA, param_groups
+    m = copy.deepcopy(m).cpu().train()
+    det = m.model[-1]
+    hyp = loss_ref.scaled_hyp({k: HYP_FINETUNE_DOTA.get(k, v) for k, v in loss_ref.DEFAULT_HYP.items()}, det.nl, det.nc, imgsz)
+    g0, g1, g2 = param_groups(m)
+    opt = torch.optim.SGD(g0, lr=HYP_FINETUNE_DOTA["lr0"], momentum=HYP_FINETUNE_DOTA["momentum"], nesterov=True)
+    opt.add_param_group({"params": g1, "weight_decay": HYP_FINETUNE_DOTA["weight_decay"]})   # batch 64, accumulate 1
+    opt.add_param_group({"params": g2})
+    x = imgs_u8.float().cpu() / 255
+    out = []
+    for _ in range(steps):
+        with torch.enable_grad():
+            pred = model_ref.forward_with_grad(m, x, training=True, emulate_bf16=emulate_bf16)
+            loss, _ = loss_ref.compute_loss(pred, tg.cpu(), det.anchors, det.stride, hyp, det.nc)
+            loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        out.append(loss.item())
+    return out
+
+
+def test_loss_trajectory_against_the_cpu_oracle():
+    """30 optimisation steps of yolov5n at 128^2 on one repeated batch: the device's loss curve beside the fp32 CPU oracle's.
+    The yardstick is measured, not assumed: the oracle run with bf16 storage emulated gives the distance two CORRECT
+    implementations with this storage precision reach (the network is chaotic at random init, test_train_backward_gpu).
+    Step 0 (same weights) must agree to 1e-3 relative; afterwards the device must stay within 3x the emulation's own drift
+    (+2 % of the loss); and the curves must end lower than they start together."""
+    from yolov5_obb_b200.train_step import TrainStep
+    B, S, N = 4, 128, 30
+    m0 = build_mirror("n", nc=15, seed=1).train()
+    imgs = synth_tiles(B, S, seed=3)
+    tg = torch.from_numpy(synth_targets(B, 40, S, nc=15, seed=3))
+    ref = _oracle_trajectory(m0, imgs, tg, N, S, emulate_bf16=False)
+    emu = _oracle_trajectory(m0, imgs, tg, N, S, emulate_bf16=True)
+    md = copy.deepcopy(m0).to(DEV)
+    ts = TrainStep(md, batch_size=64, imgsz=S)
+    dev = []
+    for _ in range(N):
+        l, _ = ts.step(imgs.to(DEV), tg.to(DEV))
+        dev.append(l.item())
+    print("oracle fp32 ", [f"{v:.3f}" for v in ref])
+    print("oracle bf16 ", [f"{v:.3f}" for v in emu])
+    print("device      ", [f"{v:.3f}" for v in dev])
+    assert abs(dev[0] - ref[0]) < 1e-3 * abs(ref[0]) + 2e-2 * abs(emu[0] - ref[0]) + 1e-3
+    run_max = 0.0
+    for i in range(N):
+        run_max = max(run_max, abs(emu[i] - ref[i]))      # the emulation's drift so far (running maximum: drift is not monotone)
+        assert abs(dev[i] - ref[i]) < 3.0 * run_max + 0.02 * abs(ref[i]) + 1e-3, (i, dev[i], ref[i], emu[i])
+    assert min(ref[-4:]) < ref[0] and min(dev[-4:]) < dev[0]

@@ -27,6 +27,8 @@ PROTOTYPES = {
     "y5obb_nms_rotated_batched_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_float,
                                               c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                               c_void_p]),
+    "y5obb_nms_debug_stage_timing": (c_int, [c_int]),
+    "y5obb_nms_debug_stage_ms": (c_int, [ctypes.POINTER(c_float)]),
     "y5obb_rbox_iou_pairs_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "y5obb_nms_obb_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64]),
     "y5obb_nms_obb_f32": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_float, c_float, ctypes.c_uint64, c_int,
@@ -38,6 +40,7 @@ PROTOTYPES = {
     "y5obb_conv_info": (c_int, [c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
                         + [ctypes.POINTER(c_int)] * 4),
     "y5obb_conv_destroy": (None, [c_void_p]),
+    "y5obb_conv_debug_timestamps": (c_int, [c_void_p, c_void_p]),
     "y5obb_loss_workspace_bytes": (c_size_t, [c_void_p]),
     "y5obb_loss_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "y5obb_loss_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

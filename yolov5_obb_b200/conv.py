@@ -128,7 +128,7 @@ class Conv:
     def __init__(self, x, w_packed: torch.Tensor, bias_pad: torch.Tensor, cout: int, k, stride: int,
                  pad, act: bool, out: Optional[Slice] = None, res: Optional[Slice] = None,
                  out2x: Optional[Slice] = None, det: Optional[dict] = None, flags: int = 0,
-                 out_geom: Optional[dict] = None):
+                 out_geom: Optional[dict] = None, bias_prehalved: bool = False):
         """out_geom (optional): dict(h, w, off, pix, row, img) - the output (and the residual, which must then be the same
         slice) has h x w pixels at element offset `off` of the slice with pixel / row / image strides in elements."""
         _lib.require_cuda(x.buf, "conv input")
@@ -141,7 +141,8 @@ class Conv:
         d.B, d.Hin, d.Win, d.Cin = x.B, x.H, x.W, x.C
         if act and not det:
             # the SiLU epilogue evaluates h + h*tanh(h) with h = 0.5*acc + 0.5*bias: hand it 0.5*bias
-            bias_pad = (bias_pad * 0.5).contiguous()
+            if not bias_prehalved:
+                bias_pad = (bias_pad * 0.5).contiguous()
             flags |= BIAS_HALVED
         d.w, d.bias = w_packed.data_ptr(), bias_pad.data_ptr()
         d.Cout, d.KH, d.KW, d.stride, d.pad_h, d.pad_w = cout, kh, kw, stride, ph, pw

@@ -35,6 +35,7 @@ namespace {
 
 constexpr int BM = 128;  // output pixels per tile == TMEM lanes
 constexpr int MAX_STAGES = 16;
+constexpr int MAX_ACC = 8;                // TMEM accumulator stages: 512 columns / accumulator stride
 constexpr int NUM_THREADS = 320;          // TMA producer, MMA issuer, 8 epilogue warps
 constexpr int EPI_WARPS = 8;
 constexpr int EPI_STAGE_CONV = 32 * 64;    // 32 pixels x 32 bf16 channels, 64-byte swizzled
@@ -71,6 +72,8 @@ struct ConvK {
   int Cout, cout_pad;
   int Cin, kchunks, KH, KW, stride, pad_h, pad_w;
   int stages;
+  int n_acc, acc_shift, acc_stride;  // TMEM accumulator stages (power of two), log2, columns between them
+  int pdl;             // launched with programmatic stream serialisation: griddepcontrol.wait before the first global access
   int dbg;             // timing experiments only (results are garbage): 1 = no TMA loads, 2 = no MMAs, 4 = no epilogue work
   int pairw;           // 1: stride-2 conv whose input is viewed as horizontal pixel PAIRS (2*pix_stride channels per
                        // position): the column phase of a tap is a channel offset, so TMA reads contiguous rows
@@ -99,7 +102,13 @@ struct ConvK {
   int det_no, det_decode;
   float det_stride;
   float det_anchor[6];
+  unsigned long long* ts;  // debug: clock64 stamps of CTA 0, [role 3][tile 32][slot 8] (y5obb_conv_debug_timestamps)
 };
+
+#define Y5_TS(role, it, slot)                                                                  \
+  do {                                                                                         \
+    if (p.ts && blockIdx.x == 0 && (it) < 32) p.ts[((role)*32 + (it)) * 8 + (slot)] = clock64(); \
+  } while (0)
 
 struct TileCoord {
   int b, h0, w0, n0, nt;
@@ -156,6 +165,7 @@ struct EpiTile {
   uint32_t stage_bytes;
   uint32_t swz;       // (lane >> 1) & 3
   int lane;
+  bool leader;        // the warp's elected thread (elect.sync once per kernel): issues and tracks the TMA stores
   const float* bias;  // + n0; holds 0.5 * bias when the layer has SiLU (Y5OBB_CONV_BIAS_HALVED)
   const __nv_bfloat16* rrow;  // residual row of this thread's pixel (+ n0) or null
   __nv_bfloat16* urow;        // up-sampled destination of this thread's pixel (+ n0) or null
@@ -183,7 +193,7 @@ __device__ __forceinline__ void conv_epi_tile(const EpiTile& e, int& sbuf) {
     for (int g = 0; g < 8; ++g) bv[g] = __ldg(b4 + g);
     ptx::tmem_ld_wait();
     // the staging buffer about to be overwritten must have been read by its TMA store
-    if (e.lane == 0) ptx::tma_store_wait_read<1>();
+    if (e.leader) ptx::tma_store_wait_read<1>();
     __syncwarp();
     uint8_t* sb = e.stage + sbuf * e.stage_bytes + e.lane * 64;
 #pragma unroll
@@ -229,7 +239,7 @@ __device__ __forceinline__ void conv_epi_tile(const EpiTile& e, int& sbuf) {
     }
     ptx::fence_proxy_async();
     __syncwarp();
-    if (e.lane == 0) {
+    if (e.leader) {
       // rows beyond the image and channels beyond Cout are clipped by the tensor map
       ptx::tma_store_4d(e.tm, e.stage + sbuf * e.stage_bytes, e.cn0 + c0, e.cw, e.chh, e.cb);
       ptx::tma_store_commit();
@@ -242,8 +252,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
-  __shared__ __align__(8) uint64_t tmem_full[2];
-  __shared__ __align__(8) uint64_t tmem_empty[2];
+  __shared__ __align__(8) uint64_t tmem_full[MAX_ACC];
+  __shared__ __align__(8) uint64_t tmem_empty[MAX_ACC];
   __shared__ __align__(8) uint64_t wres_bar;
   __shared__ uint32_t tmem_base_smem;
 
@@ -266,7 +276,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < p.n_acc; ++a) {
       ptx::mbar_init(&tmem_full[a], 1);
       ptx::mbar_init(&tmem_empty[a], p.epi_tile_split ? 128 : EPI_WARPS * 32);
     }
@@ -281,10 +291,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  // Programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's
+  // tail; from here on global memory is touched, so the previous grid must have completed and flushed.  Only then may the
+  // NEXT kernel start its own prologue (its pre-wait phase never touches memory, and it finds kernel N-1's inputs final).
+  if (p.pdl) {
+    ptx::griddep_wait();
+    ptx::griddep_launch_dependents();
+  }
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // elect.sync (not `lane == 0`): ptxas then knows a single thread runs the region and issues UTMALDG / UTCHMMA straight from
+    // uniform registers; under a lane test every such instruction is wrapped in a per-lane serialisation loop (~60 cycles each)
+    if (ptx::elect_one()) {
       if (p.b_resident) {  // all weight tiles, once: tile (tap, kc) at smem_res + (tap * kchunks + kc) * b_stage_bytes
         const int ntile = p.KH * p.KW * p.kchunks;
         ptx::mbar_expect_tx(&wres_bar, (uint32_t)ntile * p.b_bytes);
@@ -296,12 +315,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       int s = 0;
       uint32_t ph = 0;
       const uint32_t unit_tx = p.a_tx_bytes + (uint32_t)p.b_per_stage * p.b_bytes;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int pit = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++pit) {
         const TileCoord c = decode_tile(p, t);
-        int tap_outer = 0, kc = 0;  // unit = (tap_outer, kc), kc fastest; rowshift: tap_outer = kw, else kh * KW + kw
+        int kh = 0, kw = 0, kc = 0;  // unit = (tap, kc), kc fastest; rowshift: taps = kw only (kh stays 0), else kh * KW + kw
         for (int u0 = 0; u0 < p.n_units; u0 += p.group) {
           const int ng = min(p.group, p.n_units - u0);
+          if (u0 == 0) Y5_TS(0, pit, 0);
           ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
+          if (u0 == 0) Y5_TS(0, pit, 1);
           uint8_t* sbase = smem + (size_t)s * stage_bytes;
           if (p.dbg & 1) {
             ptx::mbar_arrive(&full_bar[s]);
@@ -309,8 +331,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             ptx::mbar_expect_tx(&full_bar[s], unit_tx * (uint32_t)ng);
           }
           for (int g = 0; g < ng; ++g) {
-            const int kh = p.rowshift ? 0 : tap_outer / p.KW;
-            const int kw = p.rowshift ? tap_outer : tap_outer - kh * p.KW;
             int wi = c.w0 * p.stride + kw - p.pad_w;
             const int hi = c.h0 * p.stride + kh - p.pad_h;
             int cbase = 0;
@@ -332,7 +352,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             }
             if (++kc == p.kchunks) {
               kc = 0;
-              ++tap_outer;
+              if (++kw == p.KW) {
+                kw = 0;
+                ++kh;
+              }
             }
           }
           if (++s == p.stages) {
@@ -340,11 +363,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             ph ^= 1u;
           }
         }
+        Y5_TS(0, pit, 2);
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
@@ -361,17 +385,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       const uint32_t a_step = p.row_shift_bytes >> 4;
       const uint32_t b_step = (p.b_resident ? (uint32_t)(p.KW * p.kchunks) * p.b_stage_bytes : p.b_stage_bytes) >> 4;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+        const int acc = it & (p.n_acc - 1);
+        const uint32_t acc_ph = (uint32_t)(it >> p.acc_shift) & 1u;
+        Y5_TS(1, it, 0);
         ptx::mbar_wait(&tmem_empty[acc], acc_ph ^ 1u);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+        Y5_TS(1, it, 1);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
         uint32_t accumulate = 0u;
         int tap_outer = 0, kc = 0;
         for (int u0 = 0; u0 < p.n_units; u0 += p.group) {
           const int ng = min(p.group, p.n_units - u0);
           ptx::mbar_wait(&full_bar[s], ph);
           ptx::tc_fence_after();
+          if (u0 == 0) Y5_TS(1, it, 2);
           const uint32_t sbase = ring_u32 + (uint32_t)s * stage_bytes;
           for (int g = 0; g < ng; ++g) {
             // K sub-blocks of 16 that hold real channels (the zero-filled tail of a ragged chunk is skipped)
@@ -418,7 +445,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             ph ^= 1u;
           }
         }
+        Y5_TS(1, it, 3);
         ptx::umma_commit(&tmem_full[acc]);
+        Y5_TS(1, it, 4);
       }
     }
   } else {
@@ -426,6 +455,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     // warp e = warp - 2; TMEM lane quarter q = warp & 3 (hardware rule: a warp reads lanes 32*(warp%4)..+31);
     // the two warps sharing a quarter split the columns: 32-column chunks with (chunk & 1) == half.
     const int e = warp - 2;
+    const bool leader = ptx::elect_one();  // one fixed thread per warp owns the bulk-store groups (per-thread state)
     const int q = warp & 3;
     const int half = e >> 2;
     const int row = q * 32 + lane;
@@ -440,22 +470,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     const int col_first = p.epi_tile_split ? 0 : half * 32;  // first 32-column chunk of this warp
     const int col_step = p.epi_tile_split ? 32 : 64;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-      const int acc = it & 1;
-      if (p.epi_tile_split && acc != half) continue;  // the other warp group owns this tile
+      const int acc = it & (p.n_acc - 1);
+      if (p.epi_tile_split && (it & 1) != half) continue;  // the other warp group owns this tile
       const TileCoord c = decode_tile(p, t);
-      const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+      const uint32_t acc_ph = (uint32_t)(it >> p.acc_shift) & 1u;
       const int h = c.h0 + hl, w = c.w0 + wl;
       const bool valid = (h < p.Hout) && (w < p.Wout);
       const long long pix = ((long long)c.b * p.Hout + h) * p.Wout + w;
 
+      const bool ts_on = leader && (e & 3) == 0 && (p.epi_tile_split || e == 0);
+      if (ts_on) Y5_TS(2, it, 0);
       ptx::mbar_wait(&tmem_full[acc], acc_ph);
       ptx::tc_fence_after();
+      if (ts_on) Y5_TS(2, it, 1);
       if (p.dbg & 4) {
         ptx::tc_fence_before();
         ptx::mbar_arrive(&tmem_empty[acc]);
         continue;
       }
-      const uint32_t taddr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(q * 32) << 16);
+      const uint32_t taddr = tmem_base + (uint32_t)(acc * p.acc_stride) + ((uint32_t)(q * 32) << 16);
 
       if (p.mode == MODE_CONV) {
         const __nv_bfloat16* rrow =
@@ -470,6 +503,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         et.stage_bytes = p.epi_stage_bytes;
         et.swz = (uint32_t)((lane >> 1) & 3);
         et.lane = lane;
+        et.leader = leader;
         et.bias = p.bias + c.n0;
         et.rrow = valid ? rrow : nullptr;
         et.urow = valid ? urow : nullptr;
@@ -505,7 +539,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
           uint32_t r[32];
           ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)c0, r);
           ptx::tmem_ld_wait();
-          if (lane == 0) ptx::tma_store_wait_read<1>();
+          if (leader) ptx::tma_store_wait_read<1>();
           __syncwarp();
           uint8_t* sb = stage + sbuf * p.epi_stage_bytes;
           const float4* b4 = reinterpret_cast<const float4*>(p.bias + c.n0 + c0);
@@ -532,17 +566,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
           }
           ptx::fence_proxy_async();
           __syncwarp();
-          if (lane == 0) {
+          if (leader) {
             ptx::tma_store_5d(&p.tmO, sb, c0, c.w0 + box_w0, c.h0 + box_h0, a, c.b);
             ptx::tma_store_commit();
           }
           sbuf ^= 1;
         }
       }
+      if (ts_on) Y5_TS(2, it, 2);
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tmem_empty[acc]);
+      if (ts_on) Y5_TS(2, it, 3);
     }
-    if (lane == 0) ptx::tma_store_wait_all();
+    if (leader) ptx::tma_store_wait_all();
   }
 
   ptx::tc_fence_before();
@@ -732,6 +768,16 @@ int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
     delete o;
     return Y5OBB_EINVAL;
   }
+  // TMEM accumulator stages: the MMA issuer may run that many tiles ahead of the epilogue warps
+  k.acc_stride = bn <= 32 ? 32 : (bn <= 64 ? 64 : (bn <= 128 ? 128 : 256));
+  k.n_acc = std::min(MAX_ACC, 512 / k.acc_stride);
+  if (d->flags & Y5OBB_CONV_ACC2) k.n_acc = 2;
+  k.acc_shift = 0;
+  while ((1 << k.acc_shift) < k.n_acc) ++k.acc_shift;
+  {
+    const char* e = getenv("Y5OBB_NO_PDL");
+    k.pdl = ((d->flags & Y5OBB_CONV_NO_PDL) || (e && e[0] == '1')) ? 0 : 1;
+  }
   k.fd_ntn = make_fastdiv((uint32_t)k.n_tiles_n);
   k.fd_per_img = make_fastdiv((uint32_t)(k.tiles_h * k.tiles_w));
   k.fd_tiles_w = make_fastdiv((uint32_t)k.tiles_w);
@@ -874,6 +920,22 @@ int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
 int y5obb_conv_run(const y5obb_conv_t* conv, void* stream) {
   if (!conv) return Y5OBB_EINVAL;
   const ConvObj* o = reinterpret_cast<const ConvObj*>(conv);
+  if (o->k.pdl) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)o->grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = o->smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel, o->k);
+    if (e != cudaSuccess) return cuda_fail(e);
+    return Y5OBB_OK;
+  }
   conv_tc_kernel<<<o->grid, NUM_THREADS, o->smem, (cudaStream_t)stream>>>(o->k);
   Y5_LAUNCH_CHECK();
   return Y5OBB_OK;
@@ -893,5 +955,11 @@ int y5obb_conv_info(const y5obb_conv_t* conv, double* flops, double* hbm_bytes, 
 }
 
 void y5obb_conv_destroy(y5obb_conv_t* conv) { delete reinterpret_cast<ConvObj*>(conv); }
+
+int y5obb_conv_debug_timestamps(y5obb_conv_t* conv, unsigned long long* dev_buf_768) {
+  if (!conv) return Y5OBB_EINVAL;
+  reinterpret_cast<ConvObj*>(conv)->k.ts = dev_buf_768;
+  return Y5OBB_OK;
+}
 
 }  // extern "C"

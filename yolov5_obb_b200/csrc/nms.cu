@@ -283,7 +283,8 @@ __global__ void __launch_bounds__(REDUCE_THREADS)
 k_reduce(const NmsSeg* __restrict__ seg, const NmsCtrl* __restrict__ ctrl,
          const unsigned long long* __restrict__ mask, const uint8_t* __restrict__ rowflag,
          const uint32_t* __restrict__ order, long long max_keep, int n_images,
-         int64_t* __restrict__ keep_out, int64_t* __restrict__ n_keep_out, int64_t* __restrict__ seg_off_out) {
+         int64_t* __restrict__ keep_out, int64_t* __restrict__ n_keep_out, int64_t* __restrict__ seg_off_out,
+         const PreBox* __restrict__ pre, int late_drop_small) {
   extern __shared__ unsigned long long remv[];
   __shared__ unsigned long long s_diag[TB];
   __shared__ int s_orrows[TB];
@@ -304,6 +305,15 @@ k_reduce(const NmsSeg* __restrict__ seg, const NmsCtrl* __restrict__ ctrl,
   for (int w = tid; w < S.nblk; w += REDUCE_THREADS) remv[w] = 0ull;
   if (tid == 0) s_nor = 0;
   __syncthreads();
+  if (late_drop_small) {
+    // Reference order (general.py:845-846 then nms_rotated_wrapper.py:32-39): the top-max_nms clamp counts degenerate
+    // boxes, obb_nms drops them afterwards.  They start out "removed": never kept, their mask rows never applied.
+    for (int i = tid; i < S.n; i += REDUCE_THREADS) {
+      const PreBox& q = pre[S.off + i];
+      if (fminf(q.w, q.h) < 0.001f) atomicOr(&remv[i >> 6], 1ull << (i & 63));
+    }
+    __syncthreads();
+  }
 
   long long count = 0;
   const unsigned long long* M = mask + S.mask_off;
@@ -420,6 +430,17 @@ NmsWs carve_nms(void* base, int64_t n, int64_t n_images, int64_t max_per_image) 
   return w;
 }
 
+// profiling aid (y5obb_nms_debug_stage_timing): CUDA events between the stages of nms_impl on the caller's stream
+struct StageTimer {
+  cudaEvent_t ev[5];
+  bool made = false, on = false;
+  int n = 0;
+};
+StageTimer g_stage;
+inline void stage_mark(cudaStream_t st) {
+  if (g_stage.on && g_stage.n < 5) cudaEventRecord(g_stage.ev[g_stage.n++], st);
+}
+
 int nms_impl(const float* dets, const float* scores, const int32_t* image_ids, int64_t n, int64_t n_images,
              int64_t max_per_image, float thr, int flags, int64_t max_keep, int64_t* keep_out, int64_t* n_keep_out,
              int64_t* seg_off_out, void* workspace, size_t ws_bytes, cudaStream_t st,
@@ -437,13 +458,19 @@ int nms_impl(const float* dets, const float* scores, const int32_t* image_ids, i
   if (w.total > ws_bytes) return Y5OBB_EWORKSPACE;
 
   const unsigned g = (unsigned)((n + 255) / 256);
-  k_make_keys<<<g, 256, 0, st>>>(dets, scores, image_ids, n, (int)n_images, flags, n_valid_dev, w.keys_a, w.vals_a);
+  g_stage.n = 0;
+  stage_mark(st);
+  // with a top-k clamp the degenerate boxes keep their rank (reference order: clamp first, too-small filter second)
+  const int late_drop = ((flags & Y5OBB_NMS_DROP_SMALL) && per_image_clamp > 0) ? 1 : 0;
+  k_make_keys<<<g, 256, 0, st>>>(dets, scores, image_ids, n, (int)n_images, late_drop ? (flags & ~Y5OBB_NMS_DROP_SMALL) : flags,
+                                 n_valid_dev, w.keys_a, w.vals_a);
   Y5_LAUNCH_CHECK();
   int img_bits = 1;
   while ((1ll << img_bits) <= n_images) ++img_bits;
   size_t cub_bytes = w.cub_bytes;
   Y5_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, cub_bytes, w.keys_a, w.keys_b, w.vals_a, w.vals_b, (int)n, 0,
                                           32 + img_bits, st));
+  stage_mark(st);
   Y5_CUDA(cudaMemsetAsync(w.rowflag, 0, (size_t)n, st));
   k_segments<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(w.keys_b, n, (int)n_images, w.seg_start);
   Y5_LAUNCH_CHECK();
@@ -462,9 +489,11 @@ int nms_impl(const float* dets, const float* scores, const int32_t* image_ids, i
   long long grid = (long long)sm_count() * 8;
   if (grid > max_units) grid = max_units;
   if (grid < 1) grid = 1;
+  stage_mark(st);
   k_tiles<<<(unsigned)grid, TILE_THREADS, 0, st>>>(w.pre, w.seg, (int)n_images, w.ctrl, w.mask, w.rowflag, thr,
                                                    (flags & Y5OBB_NMS_STRICT_GT) ? 1 : 0);
   Y5_LAUNCH_CHECK();
+  stage_mark(st);
 
   const size_t smem = (size_t)((max_per_image + TB - 1) / TB) * sizeof(unsigned long long);
   if (smem > 200 * 1024) return Y5OBB_EINVAL;  // > 1.6 M boxes in one image
@@ -475,8 +504,9 @@ int nms_impl(const float* dets, const float* scores, const int32_t* image_ids, i
   }
   k_reduce<<<(unsigned)n_images, REDUCE_THREADS, smem, st>>>(w.seg, w.ctrl, w.mask, w.rowflag, w.vals_b,
                                                             (long long)max_keep, (int)n_images, keep_out, n_keep_out,
-                                                            seg_off_out);
+                                                            seg_off_out, w.pre, late_drop);
   Y5_LAUNCH_CHECK();
+  stage_mark(st);
   return Y5OBB_OK;
 }
 
@@ -670,7 +700,7 @@ __global__ void k_pp_gather(const float* __restrict__ out7, const int64_t* __res
 // top-max_nms clamp (general.py:845-846) or the dump image excludes it.  A stable sort on these bits keeps the score order.
 __global__ void k_class_keys(const uint64_t* __restrict__ keys1, const uint32_t* __restrict__ order1,
                              const int32_t* __restrict__ seg1_start, const float* __restrict__ out7, int64_t n,
-                             int n_images, int nc, int max_nms, uint64_t* __restrict__ keys2) {
+                             int n_images, int nc, int max_nms, int drop_small, uint64_t* __restrict__ keys2) {
   const int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (pos >= n) return;
   const int img = (int)(keys1[pos] >> 32);
@@ -678,9 +708,12 @@ __global__ void k_class_keys(const uint64_t* __restrict__ keys1, const uint32_t*
   if (img < n_images) {
     const long long r = pos - seg1_start[img];
     if (max_nms <= 0 || r < max_nms) {
-      int cls = (int)out7[(long long)order1[pos] * 7 + 6];
+      const float* o = out7 + (long long)order1[pos] * 7;
+      int cls = (int)o[6];
       cls = min(max(cls, 0), nc - 1);
-      seg = (uint32_t)(img * nc + cls);
+      // reference order: the top-max_nms clamp above counted this box; obb_nms then drops it if it is degenerate
+      // (nms_rotated_wrapper.py:32-39)
+      if (!(drop_small && fminf(o[2], o[3]) < 0.001f)) seg = (uint32_t)(img * nc + cls);
     }
   }
   keys2[pos] = (uint64_t)seg << 32;
@@ -813,7 +846,8 @@ int nms_classes(const PPWs& w, const float* out7, int64_t n, int n_images, int n
   if (ws.total > w.nms_bytes) return Y5OBB_EWORKSPACE;
   const unsigned g = (unsigned)((n + 255) / 256);
   // 1. every image's candidates by descending score (ties: lower index), as the reference's argsort
-  k_make_keys<<<g, 256, 0, st>>>(w.dets5, w.scores, w.image_ids, n, n_images, flags, w.n_valid, ws.keys_a, ws.vals_a);
+  k_make_keys<<<g, 256, 0, st>>>(w.dets5, w.scores, w.image_ids, n, n_images, flags & ~Y5OBB_NMS_DROP_SMALL, w.n_valid,
+                                 ws.keys_a, ws.vals_a);
   Y5_LAUNCH_CHECK();
   int img_bits = 1;
   while ((1ll << img_bits) <= n_images) ++img_bits;
@@ -823,7 +857,8 @@ int nms_classes(const PPWs& w, const float* out7, int64_t n, int n_images, int n
   k_segments<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(ws.keys_b, n, n_images, w.seg1_start);
   Y5_LAUNCH_CHECK();
   // 2. stable re-grouping by (image, class) of the top-max_nms of every image: score order survives inside a class
-  k_class_keys<<<g, 256, 0, st>>>(ws.keys_b, ws.vals_b, w.seg1_start, out7, n, n_images, nc, max_nms, w.keys2_a);
+  k_class_keys<<<g, 256, 0, st>>>(ws.keys_b, ws.vals_b, w.seg1_start, out7, n, n_images, nc, max_nms,
+                                  (flags & Y5OBB_NMS_DROP_SMALL) ? 1 : 0, w.keys2_a);
   Y5_LAUNCH_CHECK();
   int seg_bits = 1;
   while ((1ll << seg_bits) <= n_seg) ++seg_bits;
@@ -857,7 +892,7 @@ int nms_classes(const PPWs& w, const float* out7, int64_t n, int n_images, int n
     smem_set = 200 * 1024;
   }
   k_reduce<<<(unsigned)n_seg, REDUCE_THREADS, smem, st>>>(ws.seg, ws.ctrl, ws.mask, ws.rowflag, w.order2, (long long)max_keep,
-                                                         n_seg, w.keepC, w.n_keepC, w.seg_offC);
+                                                         n_seg, w.keepC, w.n_keepC, w.seg_offC, ws.pre, 0);
   Y5_LAUNCH_CHECK();
   // 4. merge: kept flags, then every image's keepers in its own score order, first max_keep of them
   const long long per_seg = max_keep > 0 ? max_keep : max_per_image;
@@ -963,6 +998,23 @@ int y5obb_nms_obb_f32(const float* pred, int64_t batch, int64_t anchors, int no,
   k_pp_gather<<<gg, 128, 0, st>>>(w.out7, w.keep, w.n_keep, w.seg_off, (int)batch, max_det, out7, counts, w.n_valid,
                                   split ? w.far_flag : nullptr);
   Y5_LAUNCH_CHECK();
+  return Y5OBB_OK;
+}
+
+int y5obb_nms_debug_stage_timing(int on) {
+  if (on && !g_stage.made) {
+    for (int i = 0; i < 5; ++i) Y5_CUDA(cudaEventCreate(&g_stage.ev[i]));
+    g_stage.made = true;
+  }
+  g_stage.on = on != 0;
+  g_stage.n = 0;
+  return Y5OBB_OK;
+}
+
+int y5obb_nms_debug_stage_ms(float* ms4) {
+  if (!ms4 || !g_stage.on || g_stage.n != 5) return Y5OBB_EINVAL;
+  Y5_CUDA(cudaEventSynchronize(g_stage.ev[4]));
+  for (int i = 0; i < 4; ++i) Y5_CUDA(cudaEventElapsedTime(&ms4[i], g_stage.ev[i], g_stage.ev[i + 1]));
   return Y5OBB_OK;
 }
 

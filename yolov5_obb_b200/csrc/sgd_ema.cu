@@ -3,8 +3,8 @@
 //   torch.optim.SGD(nesterov=True, dampening=0):  g' = g + wd * p;  buf = g' (first step) | momentum * buf + g';
 //                                                 p -= lr * (g' + momentum * buf)
 //   utils/torch_utils.py:304-314                  ema = d * ema + (1 - d) * p  for every floating-point state_dict entry
-// EXPERIMENTAL in round 1: not yet run on hardware (tests/test_sgd_ema_gpu.py is skipped unless Y5OBB_EXPERIMENTAL=1);
-// train_step.TrainStep uses torch.optim.SGD + torch._foreach EMA (about 60 launches, 0.6 ms per step) by default.
+// tests/test_sgd_ema_gpu.py: equal to torch.optim.SGD + ModelEMA over three steps; train_step.TrainStep uses it whenever every
+// batch ends with an optimizer step (it replaces about 60 multi-tensor launches, 0.6 ms per yolov5m step).
 // HBM-bound: 16 B read + 12 B written per parameter element.
 #include <algorithm>
 #include <vector>

@@ -1,8 +1,7 @@
 """Host-side mirror of the DOTA devkit's tile-merge NMS (DOTA_devkit/ResultMerge_multi_process.py:62-123
 py_cpu_nms_poly_fast over polyiou.iou_poly), backed by csrc/poly_nms.cu.
 
-EXPERIMENTAL in round 1: the kernels were written against the bit-equal CPU restatement (oracle/poly_ref.py) but have not
-run on hardware yet; tests/test_poly_gpu.py is skipped unless Y5OBB_EXPERIMENTAL=1.  Nothing on the measured paths uses it."""
+tests/test_poly_gpu.py: IoU bit-equal to the reference's polyiou.cpp, keep lists equal (fp64, no FMA contraction)."""
 import torch
 
 from . import _lib

@@ -25,13 +25,15 @@ from . import yolo as Y
 
 
 def fold_bn(conv: torch.nn.Conv2d, bn: Optional[torch.nn.BatchNorm2d]):
-    """W' = diag(gamma / sqrt(var + eps)) W ; b' = beta - gamma * mean / sqrt(var + eps)  (+ conv bias)."""
-    w = conv.weight.detach().float()
-    b = conv.bias.detach().float() if conv.bias is not None else torch.zeros(w.shape[0], device=w.device)
+    """W' = diag(gamma / sqrt(var + eps)) W ; b' = beta - gamma * mean / sqrt(var + eps)  (+ conv bias).
+    Host-side plan building: the arithmetic runs on CPU copies of the parameters (one D2H copy per tensor, no device
+    kernels), the packed bf16 operands are uploaded once by the caller."""
+    w = conv.weight.detach().float().cpu()
+    b = conv.bias.detach().float().cpu() if conv.bias is not None else torch.zeros(w.shape[0])
     if bn is None:
         return w, b
-    scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
-    return w * scale.view(-1, 1, 1, 1), (b - bn.running_mean.detach().float()) * scale + bn.bias.detach().float()
+    scale = bn.weight.detach().float().cpu() / torch.sqrt(bn.running_var.detach().float().cpu() + bn.eps)
+    return w * scale.view(-1, 1, 1, 1), (b - bn.running_mean.detach().float().cpu()) * scale + bn.bias.detach().float().cpu()
 
 
 def _conv_params(m):
@@ -95,11 +97,20 @@ class InferenceEngine:
                 ch[i], hw[i] = sum(ch[f] for f in fs), in_hw
                 assert all(hw[f] == in_hw for f in fs)
 
+        arena = {"buf": None, "used": 0}
+
         def new(h, w, c):
             # zeros, once: the pixel-pair view of stride-2 convs may read channels of a buffer before their
-            # producer ran (they meet zero weights, but must be finite)
-            t = torch.zeros((B, h, w, c), dtype=torch.bfloat16, device=device)
-            self.keep.append(t)
+            # producer ran (they meet zero weights, but must be finite).  Carved from a few large zeroed chunks
+            # (one fill each) instead of one allocation + fill per tensor.
+            n = B * h * w * c
+            n_al = (n + 127) // 128 * 128   # 256-byte aligned starts (TMA wants 16)
+            if arena["buf"] is None or arena["used"] + n_al > arena["buf"].numel():
+                arena["buf"] = torch.zeros(max(n_al, 128 << 20), dtype=torch.bfloat16, device=device)
+                arena["used"] = 0
+                self.keep.append(arena["buf"])
+            t = arena["buf"][arena["used"]:arena["used"] + n].view(B, h, w, c)
+            arena["used"] += n_al
             return t
 
         # ---- pass 2: who feeds a concat
@@ -144,9 +155,11 @@ class InferenceEngine:
         def add_conv(x, w, b, k, s, p, act, dst: Optional[Slice] = None, res=None, out2x=None, detd=None):
             if dbg_no_res:
                 res = None
-            wp, bp = pack_weights(w, b, MODE_DETECT if detd else 0, detd["no"] if detd else 0)
-            op = ConvOp(x, wp, bp, w.shape[0], k, s, p, act, out=dst, res=res, out2x=out2x, det=detd,
-                        flags=conv_flags)
+            wp, bp = pack_weights(w.cpu(), b.cpu(), MODE_DETECT if detd else 0, detd["no"] if detd else 0)   # packed on the host
+            if act and not detd:
+                bp = bp * 0.5   # the SiLU epilogue wants 0.5 * bias (Y5OBB_CONV_BIAS_HALVED)
+            op = ConvOp(x, wp.to(device), bp.to(device), w.shape[0], k, s, p, act, out=dst, res=res, out2x=out2x, det=detd,
+                        flags=conv_flags, bias_prehalved=True)
             self.convs.append(op)
             info = op.info()
             self.flops += info["flops"]
@@ -172,7 +185,7 @@ class InferenceEngine:
                     if (k, s, p, w.shape[1]) != (6, 2, 2, 3):
                         raise RuntimeError("layer 0 must be the v6.0 stem Conv(3, c, 6, 2, 2)")
                     # w2[co, (dy*2+dx)*3 + c, ty, tx] = w[co, c, 2*ty+dy, 2*tx+dx]   (3x3/s1/p1 over the s2d image)
-                    w2 = torch.zeros((w.shape[0], 16, 3, 3), device=w.device)
+                    w2 = torch.zeros((w.shape[0], 16, 3, 3))
                     for dy in range(2):
                         for dx in range(2):
                             w2[:, (dy * 2 + dx) * 3:(dy * 2 + dx) * 3 + 3] = w[:, :, dy::2, dx::2]
@@ -224,7 +237,7 @@ class InferenceEngine:
             mi = det.m[l]
             stride = float(det.stride[l])
             anchors_px = (det.anchors[l].detach().float().cpu() * stride).flatten().tolist()
-            add_conv(out[f], mi.weight.detach().float(), mi.bias.detach().float(), 1, 1, 0, False,
+            add_conv(out[f], mi.weight.detach().float().cpu(), mi.bias.detach().float().cpu(), 1, 1, 0, False,
                      detd=dict(out=self.pred, rows_per_image=self.rows_total, row_off=row_off, no=det.no, decode=True,
                                stride=stride, anchors_px=anchors_px))
             row_off += rows[l]

@@ -45,6 +45,34 @@ def nms_rotated(dets: torch.Tensor, scores: torch.Tensor, iou_threshold: float, 
     return keep[:k]
 
 
+def nms_rotated_batched(dets: torch.Tensor, scores: torch.Tensor, group_ids: torch.Tensor, n_groups: int,
+                        iou_threshold: float, strict_gt: bool = True, max_per_group: int = 0, max_keep: int = 0):
+    """Segmented form of nms_rotated: boxes only compete inside their group (image, or class — what the reference obtains
+    by adding cls * 4096 to the centres, utils/general.py:849-851, here without touching the coordinates).
+    group_ids: int32 [N] in [0, n_groups).  Returns device tensors (keep int64 [N], n_keep int64 [n_groups],
+    seg_off int64 [n_groups + 1]): group g's keepers are keep[seg_off[g] : seg_off[g] + n_keep[g]], indices into the
+    caller's order, by descending score.  No host synchronisation."""
+    _lib.require_cuda(dets, "dets")
+    n = dets.size(0)
+    d = dets.detach().contiguous().float()
+    s = scores.detach().contiguous().float()
+    g = group_ids.detach().contiguous().to(torch.int32)
+    dev = dets.device
+    keep = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    cnt = torch.empty(n_groups, dtype=torch.int64, device=dev)
+    off = torch.empty(n_groups + 1, dtype=torch.int64, device=dev)
+    mpg = int(max_per_group) if max_per_group > 0 else n
+    L = _lib.lib()
+    flags = _lib.NMS_STRICT_GT if strict_gt else 0
+    with torch.cuda.device(dev):
+        ws = _lib.workspace(L.y5obb_nms_workspace_bytes(n, n_groups, mpg), dev, "nms")
+        rc = L.y5obb_nms_rotated_batched_f32(_lib.ptr(d), _lib.ptr(s), _lib.ptr(g), n, n_groups, mpg, float(iou_threshold),
+                                             flags, int(max_keep), _lib.ptr(keep), _lib.ptr(cnt), _lib.ptr(off),
+                                             _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev))
+    _lib.check(rc, "y5obb_nms_rotated_batched_f32")
+    return keep, cnt, off
+
+
 def nms_poly(dets: torch.Tensor, iou_threshold: float) -> torch.Tensor:
     """nms_rotated_ext.nms_poly: polygon NMS (reference kernel K2 cannot build on torch >= 1.11)."""
     raise RuntimeError("nms_poly: polygon-input NMS is not part of this round's hot path (SURVEY §8 A14)")

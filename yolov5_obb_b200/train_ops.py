@@ -113,13 +113,14 @@ class SgdEntry(ctypes.Structure):
 
 
 class FusedSGDEMA:
-    """EXPERIMENTAL (not validated on hardware in round 1): optimizer.step() + ema.update() of train.py:336-342 as ONE launch.
+    """optimizer.step() + ema.update() of train.py:336-342 as ONE launch (tests/test_sgd_ema_gpu.py: equal to torch.optim.SGD
+    with the reference's parameter groups + ModelEMA within 1e-5 relative over three steps).
 
     groups: (g0, g1, g2) parameter lists as train.py:148-156 builds them; grads: {parameter: fp32 gradient tensor} with FIXED
     storage (e.g. views of the backward plan's flat buffer); ema_model: a deep copy whose state_dict mirrors model's.
     step(lr=(lr0, lr1, lr2), momentum, ema_decay) applies torch.optim.SGD(nesterov=True) arithmetic and the EMA rule."""
 
-    def __init__(self, model, groups, grads, ema_model=None, weight_decay: float = 0.0):
+    def __init__(self, model, groups, grads, ema_model=None, weight_decay: float = 0.0, momentum_buffers=None):
         self.device = next(model.parameters()).device
         ema_sd = dict(ema_model.state_dict()) if ema_model is not None else {}
         name_of = {id(p): n for n, p in model.named_parameters()}
@@ -128,7 +129,7 @@ class FusedSGDEMA:
             for p in plist:
                 g = grads[p]
                 assert p.dtype == torch.float32 and g.dtype == torch.float32 and p.is_contiguous() and g.is_contiguous()
-                m = torch.zeros_like(p)
+                m = momentum_buffers[p] if momentum_buffers is not None else torch.zeros_like(p)
                 self.mom[p] = m
                 e = ema_sd.get(name_of[id(p)])
                 ent.append(SgdEntry(p.data_ptr(), g.data_ptr(), m.data_ptr(), e.data_ptr() if e is not None else None, p.numel(),
@@ -148,7 +149,7 @@ class FusedSGDEMA:
         with torch.cuda.device(self.device):
             rc = _lib.lib().y5obb_sgd_ema_plan_create(arr, len(ent), ctypes.byref(self._h))
         _lib.check(rc, "y5obb_sgd_ema_plan_create")
-        self.steps = 0
+        self.steps = 0 if momentum_buffers is None else 1  # adopted buffers already hold a first step
 
     def step(self, lr, momentum: float, ema_decay: float = 0.0, stream=None):
         lr3 = (ctypes.c_float * 3)(*[float(v) for v in lr])

@@ -107,6 +107,13 @@ class TrainStep:
         self.ni = 0
         self._last_opt = -1
         self.optimizer.zero_grad(set_to_none=True)
+        # optimizer.step() + ema.update() as ONE kernel (csrc/sgd_ema.cu) whenever every batch ends with an
+        # optimizer step (accumulate == 1: the gradient of the step is exactly the backward plan's flat buffer).  With gradient
+        # accumulation torch.optim.SGD + the foreach EMA below stay in charge.  Y5OBB_FUSED_SGD=0 forces the torch path.
+        import os
+        self._fused = None
+        self._use_fused = (self.accumulate == 1 and os.environ.get("Y5OBB_FUSED_SGD", "1") != "0"
+                           and next(model.parameters()).is_cuda and hasattr(model, "_bump_generation"))
 
     def step(self, imgs: torch.Tensor, targets: torch.Tensor):
         """imgs: uint8 or float [B,3,H,W] on the device; targets [nt, 187] (image index, class, cx, cy, l, s, theta, CSL row)."""
@@ -115,15 +122,47 @@ class TrainStep:
         loss, items = self.compute_loss(pred, targets)
         loss.backward()                                     # (x WORLD_SIZE of train.py:328 is folded into the SUM below)
         if self.ni - self._last_opt >= self.accumulate:
-            if self.world > 1:
-                self._allreduce_grads()
-            self.optimizer.step()
-            self.optimizer.zero_grad(set_to_none=True)
-            if self.ema is not None:
-                self.ema.update(model)
+            if self._use_fused:
+                self._fused_step()
+            else:
+                if self.world > 1:
+                    self._allreduce_grads()
+                self.optimizer.step()
+                self.optimizer.zero_grad(set_to_none=True)
+                if self.ema is not None:
+                    self.ema.update(model)
             self._last_opt = self.ni
         self.ni += 1
         return loss.detach(), items
+
+    def _fused_step(self):
+        """train.py:336-342 (optimizer.step, zero_grad, ema.update) as one launch over a device-resident tensor table.
+        Gradients are read in place from the backward plan's flat fp32 buffer (all-reduced in place first when N > 1);
+        learning rates / momentum are taken from optimizer.param_groups every step, so warm-up schedules that edit them
+        (train.py:305-316) keep working; the momentum buffers are registered in optimizer.state for checkpoints."""
+        from .train_ops import FusedSGDEMA
+        model = self.model
+        plan = model._last_train_engine._bwd
+        if self.world > 1:
+            dist.all_reduce(plan.flat, op=dist.ReduceOp.SUM)
+        if self._fused is None or self._fused_plan is not plan:
+            groups = [g["params"] for g in self.optimizer.param_groups]
+            self._fused = FusedSGDEMA(model, groups, plan.pgrad, self.ema.ema if self.ema is not None else None,
+                                      weight_decay=self.hyp["weight_decay"], momentum_buffers=getattr(self, "_mom", None))
+            self._mom = self._fused.mom
+            self._fused_plan = plan
+            for p, m in self._fused.mom.items():
+                self.optimizer.state[p]["momentum_buffer"] = m
+        g = self.optimizer.param_groups
+        d = 0.0
+        if self.ema is not None:
+            self.ema.updates += 1
+            d = self.ema.decay(self.ema.updates)
+        self._fused.step((g[0]["lr"], g[1]["lr"], g[2]["lr"]), g[0]["momentum"], d)
+        self.optimizer.zero_grad(set_to_none=True)
+        model._bump_generation()   # parameters changed through raw pointers: inference plans must re-fold them
+        if self.ema is not None and hasattr(self.ema.ema, "_bump_generation"):
+            self.ema.ema._bump_generation()
 
     def _allreduce_grads(self):
         """DDP averages the gradients of a loss that train.py:328 multiplied by WORLD_SIZE: the net effect is the SUM
