@@ -126,6 +126,60 @@ def build_polyiou(force: bool = False) -> bool:
     return True
 
 
+POLYGPU_SHIM = r'''
+// extern "C" doors to the reference's C++ entry points (poly_nms.hpp:9-10, poly_overlaps.hpp:1): test infrastructure
+void %(decl)s;
+extern "C" void ref_%(name)s(%(params)s) { %(call)s; }
+'''
+
+
+def build_polygpu(force: bool = False) -> bool:
+    """oracle/_ref/libref_polygpu_{nms,overlaps}.so = the reference's DOTA_devkit/poly_nms_gpu/poly_nms_kernel.cu and
+    poly_overlaps_kernel.cu compiled unmodified, in place, for sm_100a (the reference's setup.py passes -arch=sm_35 and no
+    other code-generation flag).  Two libraries: both files define `_set_device`."""
+    outs = {"nms": OUT / "libref_polygpu_nms.so", "overlaps": OUT / "libref_polygpu_overlaps.so"}
+    if not REF.exists():
+        return all(o.exists() for o in outs.values())
+    if all(o.exists() for o in outs.values()) and not force:
+        return True
+    OUT.mkdir(exist_ok=True)
+    work = OUT / "_build"
+    work.mkdir(exist_ok=True)
+    src = REF / "DOTA_devkit" / "poly_nms_gpu"
+    spec = {
+        "nms": ("poly_nms_kernel.cu",
+                dict(decl="_poly_nms(int*, int*, const float*, int, int, float, int)", name="poly_nms",
+                     params="int* keep, int* num, const float* polys, int n, int dim, float thr, int dev",
+                     call="_poly_nms(keep, num, polys, n, dim, thr, dev)")),
+        "overlaps": ("poly_overlaps_kernel.cu",
+                     dict(decl="_overlaps(float*, const float*, const float*, int, int, int)", name="overlaps",
+                          params="float* ov, const float* b, const float* q, int n, int k, int dev",
+                          call="_overlaps(ov, b, q, n, k, dev)")),
+    }
+    for key, (cu, d) in spec.items():
+        shim = work / f"ref_polygpu_{key}_shim.cpp"
+        shim.write_text(POLYGPU_SHIM % d)
+        subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-w",
+                               "-I", str(src), "-o", str(outs[key]), str(src / cu), str(shim)])
+    return True
+
+
+def load_polygpu():
+    import ctypes
+    libs = {}
+    for key in ("nms", "overlaps"):
+        so = OUT / f"libref_polygpu_{key}.so"
+        if not so.exists():
+            raise FileNotFoundError(f"{so} not built; run python oracle/build_ref.py")
+        libs[key] = ctypes.CDLL(str(so))
+    vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+    libs["nms"].ref_poly_nms.argtypes = [vp, vp, vp, ci, ci, cf, ci]
+    libs["nms"].ref_poly_nms.restype = None
+    libs["overlaps"].ref_overlaps.argtypes = [vp, vp, vp, ci, ci, ci]
+    libs["overlaps"].ref_overlaps.restype = None
+    return libs["nms"].ref_poly_nms, libs["overlaps"].ref_overlaps
+
+
 def load_polyiou():
     import ctypes
     so = OUT / "libref_polyiou.so"
@@ -153,4 +207,6 @@ def load_ref():
 if __name__ == "__main__":
     ok = build(force="--force" in sys.argv)
     ok2 = build_polyiou(force="--force" in sys.argv)
-    print("oracle/_ref:", "ok" if ok else "unavailable", "| polyiou:", "ok" if ok2 else "unavailable")
+    ok3 = build_polygpu(force="--force" in sys.argv)
+    print("oracle/_ref:", "ok" if ok else "unavailable", "| polyiou:", "ok" if ok2 else "unavailable",
+          "| devkit poly_nms_gpu:", "ok" if ok3 else "unavailable")

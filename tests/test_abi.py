@@ -40,3 +40,19 @@ def test_no_product_import_of_oracle():
     for p in (ROOT / "yolov5_obb_b200").rglob("*.py"):
         src = p.read_text()
         assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), p
+
+
+def test_devkit_cpp_symbols_exported():
+    """include/y5obb_devkit.hpp: the DOTA devkit's `_poly_nms` / `_overlaps` are exported under the reference's own C++ names
+    (the mangled names the reference's poly_nms_kernel.cu / poly_overlaps_kernel.cu objects define), so the devkit's .pyx
+    modules link against liby5obb.so unchanged."""
+    from yolov5_obb_b200.build import build_lib
+    so = build_lib()
+    out = subprocess.run(["nm", "-D", "--defined-only", "-C", str(so)], capture_output=True, text=True).stdout
+    assert "_poly_nms(int*, int*, float const*, int, int, float, int)" in out
+    assert "_overlaps(float*, float const*, float const*, int, int, int)" in out
+    ref = ROOT / "oracle" / "_ref" / "libref_polygpu_nms.so"
+    if ref.exists():  # same mangled symbol as the reference's own object file
+        mangled = lambda p: set(re.findall(r" T (_Z9_\w+)", subprocess.run(["nm", "-D", "--defined-only", str(p)],
+                                                                            capture_output=True, text=True).stdout))
+        assert mangled(ref) <= mangled(so)

@@ -13,7 +13,8 @@ from yolov5_obb_b200.engine import InferenceEngine
 size, B, S = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
 which = [int(a) for a in sys.argv[4:]] or None
 m = build_mirror(size, nc=15, seed=0).cuda()
-eng = InferenceEngine(m, B, S, S, torch.device("cuda:0"))
+import os
+eng = InferenceEngine(m, B, S, S, torch.device("cuda:0"), conv_flags=int(os.environ.get("Y5OBB_CONV_FLAGS", "0")))
 x = torch.rand(B, 3, S, S, device="cuda")
 for _ in range(2):
     eng.forward(x)

@@ -1,0 +1,90 @@
+// Micro-benchmark (dev tool): issue cost and completion time of tcgen05.mma (M=128, N, K=16, bf16, both operands in shared
+// memory, K-major, 128B swizzle) issued back to back by ONE elected thread, and by TWO warps at once (different accumulators).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o mma_rate tools/micro/mma_rate.cu && ./mma_rate
+#include <cstdio>
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include "../../yolov5_obb_b200/csrc/ptx.cuh"
+using namespace y5obb;
+
+__global__ void __launch_bounds__(128, 1) k(int N, int n_batches, int n_warps, int reps, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar[2];
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  for (int i = threadIdx.x; i < 96 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(&bar[0], 1);
+    ptx::mbar_init(&bar[1], 1);
+    ptx::fence_mbar_init();
+  }
+  if (threadIdx.x < 32) {
+    ptx::tmem_alloc(&tmem_base_s, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::fence_proxy_async();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const int warp = threadIdx.x >> 5;
+  if (warp < n_warps) {
+    if (ptx::elect_one()) {
+      const uint32_t idesc = ptx::make_idesc_bf16(128, N);
+      const uint32_t a_u32 = ptx::smem_u32(smem) + (uint32_t)warp * 32768u, b_u32 = ptx::smem_u32(smem + 64 * 1024);
+      const uint64_t hi = ptx::make_kmajor_desc(0u, 128u);
+      const uint64_t da0 = hi | (uint64_t)((a_u32 & 0x3FFFFu) >> 4);
+      const uint64_t db0 = hi | (uint64_t)((b_u32 & 0x3FFFFu) >> 4);
+      const uint32_t d = tmem + (uint32_t)warp * 256u;
+      uint32_t ph = 0;
+      long long t_issue = 0, t_done = 0;
+      for (int r = 0; r < reps; ++r) {
+        const long long t0 = clock64();
+        for (int bt = 0; bt < n_batches; ++bt) {  // 8 MMAs per batch, compile-time operand offsets, no index arithmetic
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            ptx::umma_bf16(d, da0 + (uint64_t)((j >> 2) * 1024 + (j & 3) * 2), db0 + (uint64_t)((j & 3) * 2), idesc, (bt | j) ? 1u : 0u);
+        }
+        const long long t1 = clock64();
+        ptx::umma_commit(&bar[warp]);
+        ptx::mbar_wait(&bar[warp], ph);
+        ph ^= 1u;
+        const long long t2 = clock64();
+        if (r > 0) {
+          t_issue += t1 - t0;
+          t_done += t2 - t0;
+        }
+      }
+      if (blockIdx.x == 0 && warp == 0) {
+        out[0] = t_issue / (reps - 1);
+        out[1] = t_done / (reps - 1);
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem, 512);
+  }
+}
+
+int main() {
+  long long* d;
+  cudaMalloc(&d, 16);
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  printf("  N  n_mma warps | issue cycles (per mma) | until complete (per mma)   [tensor floor per mma = N/2 cycles]\n");
+  for (int N : {16, 32, 64, 128, 256})
+    for (int nb : {1, 2, 8, 32})
+      for (int nw : {1, 2}) {
+        k<<<148, 128, 200 * 1024>>>(N, nb, nw, 6, d);
+        long long h[2];
+        cudaError_t e = cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) {
+          printf("error %s\n", cudaGetErrorString(e));
+          return 1;
+        }
+        printf("%4d %5d %4d | %7lld (%6.1f) | %7lld (%6.1f)\n", N, nb * 8, nw, h[0], (double)h[0] / (nb * 8), h[1], (double)h[1] / (nb * 8));
+      }
+  return 0;
+}

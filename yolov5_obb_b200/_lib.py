@@ -69,6 +69,12 @@ PROTOTYPES = {
     "y5obb_poly_nms_workspace_bytes": (c_size_t, [c_int64]),
     "y5obb_poly_nms_f64": (c_int, [c_void_p, c_int64, ctypes.c_double, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "y5obb_poly_iou_pairs_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "y5obb_poly_nms_f32_workspace_bytes": (c_size_t, [c_int64]),
+    "y5obb_poly_nms_f32": (c_int, [c_void_p, c_int64, c_float, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "y5obb_poly_overlaps_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    "y5obb_poly_iou_pairs_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "y5obb_devkit_poly_nms": (None, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_int]),
+    "y5obb_devkit_overlaps": (None, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int]),
     "y5obb_pack_plan_create": (c_int, [c_void_p, c_int, ctypes.POINTER(c_void_p)]),
     "y5obb_pack_plan_run": (c_int, [c_void_p, c_void_p]),
     "y5obb_pack_plan_destroy": (None, [c_void_p]),

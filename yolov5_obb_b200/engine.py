@@ -149,6 +149,7 @@ class InferenceEngine:
             else:
                 out[i] = Slice.full(new(hw[i][0], hw[i][1], ch[i]))
 
+        self.out_slices = out   # per top-level layer: where its output lives (tests read them for teacher-forced parity)
         import os
         dbg_no_res = os.environ.get("Y5OBB_DEBUG_NO_RES") == "1"  # timing experiments only (wrong results)
 

@@ -74,8 +74,44 @@ def nms_rotated_batched(dets: torch.Tensor, scores: torch.Tensor, group_ids: tor
 
 
 def nms_poly(dets: torch.Tensor, iou_threshold: float) -> torch.Tensor:
-    """nms_rotated_ext.nms_poly: polygon NMS (reference kernel K2 cannot build on torch >= 1.11)."""
-    raise RuntimeError("nms_poly: polygon-input NMS is not part of this round's hot path (SURVEY §8 A14)")
+    """nms_rotated_ext.nms_poly(dets[N,9], thr) -> LongTensor[K] on dets' device (src/nms_rotated_ext.cpp:42-55 ->
+    src/poly_nms_cuda.cu:144-261): polygons (x1 y1 .. x4 y4 score) processed by descending score (ties: lower index first;
+    the reference's torch sort leaves them unordered), a polygon dropped when its IoU with an earlier kept one is > thr.
+    The reference's own kernel K2 cannot be built on torch >= 1.11 (THC); this one restates its float polygon IoU."""
+    _lib.require_cuda(dets, "dets")
+    if dets.dim() != 2 or dets.size(1) != 9:
+        raise RuntimeError(f"dets must be [N,9], got {tuple(dets.shape)}")
+    n = dets.size(0)
+    d = dets.detach().contiguous().float()
+    keep = torch.empty(max(n, 1), dtype=torch.int64, device=dets.device)
+    nkeep = torch.empty(1, dtype=torch.int64, device=dets.device)
+    L = _lib.lib()
+    with torch.cuda.device(dets.device):
+        ws = _lib.workspace(L.y5obb_poly_nms_f32_workspace_bytes(n), dets.device, "poly_nms_f32")
+        rc = L.y5obb_poly_nms_f32(_lib.ptr(d), n, float(iou_threshold), 0, _lib.ptr(keep), _lib.ptr(nkeep), _lib.ptr(ws),
+                                  ws.numel(), _lib.stream_ptr(dets.device))
+    _lib.check(rc, "y5obb_poly_nms_f32")
+    return keep[:int(nkeep.item())]
+
+
+def poly_nms(dets, iou_thr, device_id=None):
+    """nms_rotated_wrapper.py:49-67: (dets[inds], inds); CPU input raises NotImplementedError as the reference does."""
+    if isinstance(dets, torch.Tensor):
+        is_numpy = False
+        dets_th = dets
+    elif isinstance(dets, np.ndarray):
+        is_numpy = True
+        device = 'cpu' if device_id is None else f'cuda:{device_id}'
+        dets_th = torch.from_numpy(dets).to(device)
+    else:
+        raise TypeError('dets must be eithr a Tensor or numpy array, '
+                        f'but got {type(dets)}')
+    if dets_th.device == torch.device('cpu'):
+        raise NotImplementedError
+    inds = nms_poly(dets_th.float(), iou_thr)
+    if is_numpy:
+        inds = inds.cpu().numpy()
+    return dets[inds, :], inds
 
 
 class _Ext:
