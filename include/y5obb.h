@@ -114,6 +114,7 @@ typedef struct y5obb_conv y5obb_conv_t;
 #define Y5OBB_CONV_NO_PDL 32       /* flags: plain stream-ordered launch (default: programmatic dependent launch - the kernel's
                                       prologue overlaps the previous kernel's tail and it waits, griddepcontrol.wait, before its
                                       first global-memory access; also switched off by the environment variable Y5OBB_NO_PDL=1) */
+#define Y5OBB_CONV_MSUB1 128       /* flags: 128-pixel tiles only (default: up to four 128-pixel sub-tiles per tile) */
 #define Y5OBB_CONV_ACC2 64         /* flags: two TMEM accumulator stages only (A-B comparison; default: as many as 512 columns hold) */
 
 typedef struct {
@@ -175,6 +176,11 @@ int y5obb_sppf_pool(void* buf, int64_t pix_stride, int B, int H, int W, int C, v
  * Replaces utils/loss.py:122-192 (ComputeLoss.__call__), :194-275 (build_targets) and utils/metrics.py:201-236
  * (bbox_iou, CIoU).  p[i]: Detect training outputs [B, na, H_i, W_i, no] fp32 (models/yolo.py:65);
  * targets [nt, tcols] fp32 rows (img, cls, cx, cy, l, s, theta, csl[180]) in pixels (utils/datasets.py:643-659).
+ * Compact targets (ship 7-8 floats per box over PCIe instead of 187): tcols == 8 -> column 7 is the row's
+ * rotation index int(90 - angle) of utils/rboxs_utils.py:21, evaluated by the caller in fp64 like the reference, and the kernel
+ * rebuilds the Circular-Smooth-Label row from it (identical loss, the truncation being the only ill-conditioned step);
+ * tcols == 7 -> the index is derived in the kernel from theta (column 6): equal to the reference unless fp32 rounding of
+ * theta moves angle across an integer (exact multiples of 1 degree can land on either side).
  * loss1[0] = (lbox + lobj + lcls + ltheta) * B, items4 = (lbox, lobj, lcls, ltheta) after the hyp gains
  * (loss.py:185-192).  backward writes dLoss/dp[i] * grad_loss[0] into grad[i] (dense, same shape as p[i]); it
  * must be given the workspace its forward filled.  Duplicate (b,a,gj,gi) cells: the highest source row wins
@@ -192,6 +198,7 @@ typedef struct {
   float anchor_t, cp, cn;    /* hyp['anchor_t']; smooth_BCE targets (loss.py:107) */
   float hyp_box, hyp_obj, hyp_cls, hyp_theta;  /* already rescaled as train.py:249-252 does */
   float cls_pw, obj_pw, theta_pw;              /* BCEWithLogitsLoss pos_weight (loss.py:99-101) */
+  float csl_sigma;                             /* hyp['csl_radius'] for compact targets (tcols 7 / 8); 0 = 2.0 */
 } y5obb_loss_desc;
 
 size_t y5obb_loss_workspace_bytes(const y5obb_loss_desc* desc);
@@ -340,6 +347,17 @@ size_t y5obb_poly_nms_workspace_bytes(int64_t n);
 int y5obb_poly_nms_f64(const double* dets9, int64_t n, double thresh, int64_t* keep_out, int64_t* n_keep_out, void* workspace,
                        size_t workspace_bytes, void* stream);
 int y5obb_poly_iou_pairs_f64(const double* p8, const double* q8, double* iou_out, int64_t n, void* stream);
+
+/* ---- post-NMS geometry + validation matching ------------------------------------------------------
+ * One launch per batch for val.py:226-250 + process_batch (val.py:69-92): detections pred7 [batch, max_det, 7] (the packed
+ * output of y5obb_nms_obb_f32, counts[b] valid rows) -> native-space polygons polyn8 [batch, max_det, 8] (rbox2poly +
+ * scale_polys) and boxes hbbn4 [batch, max_det, 4] (poly2hbb + xywh2xyxy) (either may be NULL), and correct
+ * [batch, max_det, niou] (uint8) against labels7 [n_labels, 7] = (image, cls, cx, cy, l, s, theta) in network-input pixels.
+ * scale5 [batch, 5] = (gain, pad_x, pad_y, raw_h, raw_w) per image (shapes[si] of val.py:213).  *overflow_flag is set when an
+ * image carries more than 1536 labels (the surplus is ignored). */
+int y5obb_val_match_f32(const float* pred7, const int64_t* counts, int batch, int max_det, const float* labels7, int n_labels,
+                        const float* scale5, const float* iouv, int niou, uint8_t* correct, float* polyn8, float* hbbn4,
+                        int* overflow_flag, void* stream);
 
 /* ---- float polygon NMS / rotated-box overlaps (rows A14, B4) ---------------------------------------------------------
  * Device-pointer forms of  utils/nms_rotated/src/nms_rotated_ext.cpp:42-55 nms_poly -> src/poly_nms_cuda.cu:144-261 (K2),

@@ -74,3 +74,42 @@ def test_loss_amp_inputs_and_errors():
         cl([x.cpu() for x in p16], tg)
     with pytest.raises(RuntimeError):
         ComputeLoss(FakeModel(dict(hyp, fl_gamma=1.5)))
+
+
+def test_compact_targets_rebuild_the_csl_rows():
+    """ship [nt, 8] (.., theta, csl index) or [nt, 7] (.., theta) instead of the reference's [nt, 187]: the
+    kernel rebuilds the Circular-Smooth-Label rows.  8 columns (index = int(90 - angle) evaluated in fp64 by the caller, as
+    utils/rboxs_utils.py:21 does): loss, items and gradients equal the 187-column path on ON-GRID angles (the ill-conditioned
+    truncation case, SURVEY 8a' 6).  7 columns: equal when theta sits off the 1-degree grid."""
+    from yolov5_obb_b200.loss import ComputeLoss, compact_csl_index
+    from tests.lossgen import gaussian_label, PI
+    B, imgsz, nt = 4, 256, 60
+    hyp = loss_ref.scaled_hyp(loss_ref.DEFAULT_HYP, 3, 15, imgsz)
+    cl = ComputeLoss(FakeModel(hyp))
+    full = synth_targets(B, nt, imgsz, seed=4)                       # on-grid thetas, fp64-evaluated rows
+    rng = np.random.default_rng(4)
+    theta64 = (rng.integers(0, 180, nt) - 90) / 180 * PI
+    off = theta64 + rng.uniform(0.2, 0.8, nt) / 180 * PI              # off-grid variant for the 7-column form
+    results = {}
+    for name, th in (("grid", theta64), ("off", off)):
+        t187 = full.copy()
+        t187[:, 6] = th
+        for i in range(nt):
+            t187[i, 7:] = gaussian_label(th[i] * 180 / PI + 90)
+        t8 = np.concatenate([t187[:, :7], compact_csl_index(th)[:, None]], 1).astype(np.float32)
+        t7 = np.ascontiguousarray(t187[:, :7])
+        for form, tg in (("187", t187), ("8", t8), ("7", t7)):
+            p = [x.to(DEV).requires_grad_(True) for x in synth_preds(B, imgsz, seed=11)]
+            loss, items = cl(p, torch.from_numpy(tg).to(DEV))
+            loss.backward()
+            results[(name, form)] = (loss.item(), items.cpu().numpy(), [x.grad.cpu() for x in p])
+    for name, forms in (("grid", ("8",)), ("off", ("8", "7"))):
+        l0, i0, g0 = results[(name, "187")]
+        for form in forms:
+            l1, i1, g1 = results[(name, form)]
+            assert abs(l1 - l0) <= 1e-6 * max(1.0, abs(l0)), (name, form, l1, l0)
+            np.testing.assert_allclose(i1, i0, rtol=1e-6, atol=1e-7)
+            for a, b in zip(g1, g0):
+                assert (a - b).abs().max().item() <= 1e-6 * b.abs().max().item() + 1e-10, (name, form)
+    with pytest.raises(RuntimeError):
+        cl([x.to(DEV) for x in synth_preds(B, imgsz, seed=11)], torch.zeros((3, 20), device=DEV))

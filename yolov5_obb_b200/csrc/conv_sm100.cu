@@ -73,6 +73,11 @@ struct ConvK {
   int Cin, kchunks, KH, KW, stride, pad_h, pad_w;
   int stages;
   int n_acc, acc_shift, acc_stride;  // TMEM accumulator stages (power of two), log2, columns between them
+  int m_sub;           // 128-pixel sub-tiles per tile (1, 2 or 4), stacked along H: one barrier round trip, one weight
+                       // load and one epilogue hand-over serve m_sub * 128 pixels (sub-tile m: accumulator columns
+                       // [m * sub_cols, ...), A rows [m * 128, (m + 1) * 128) of the stage)
+  int sub_cols;        // TMEM columns per sub-tile accumulator (acc_stride = m_sub * sub_cols)
+  uint32_t a_sub16;    // (128 rows * row bytes) >> 4: descriptor distance between the sub-tiles' A rows
   int pdl;             // launched with programmatic stream serialisation: griddepcontrol.wait before the first global access
   int dbg;             // timing experiments only (results are garbage): 1 = no TMA loads, 2 = no MMAs, 4 = no epilogue work
   int pairw;           // 1: stride-2 conv whose input is viewed as horizontal pixel PAIRS (2*pix_stride channels per
@@ -122,7 +127,7 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvK& p, int t) {
   c.b = (int)fdiv((uint32_t)mt, p.fd_per_img);
   const int r = mt - c.b * per_img;
   const int th = (int)fdiv((uint32_t)r, p.fd_tiles_w);
-  c.h0 = th * p.Ht;
+  c.h0 = th * p.Ht * p.m_sub;
   c.w0 = (r - th * p.tiles_w) * p.Wt;
   c.n0 = c.nt * p.BN;
   return c;
@@ -146,7 +151,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 // One (tap, K-chunk) unit: KSUB vertical taps x NK sub-blocks of 16 channels, fully unrolled
 template <int KSUB, int NK>
 __device__ __forceinline__ void issue_unit(uint32_t d_tmem, uint64_t da0, uint64_t db0, uint32_t a_step, uint32_t b_step,
-                                           uint32_t idesc, uint32_t& accumulate) {
+                                           uint32_t idesc, uint32_t accumulate) {
 #pragma unroll
   for (int u = 0; u < KSUB; ++u) {
 #pragma unroll
@@ -155,7 +160,6 @@ __device__ __forceinline__ void issue_unit(uint32_t d_tmem, uint64_t da0, uint64
                      (u | j) ? 1u : accumulate);
     }
   }
-  accumulate = 1u;
 }
 
 // ---- epilogue of one MODE_CONV tile for one warp -----------------------------------------------------
@@ -410,29 +414,34 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                                              : sa + p.a_bytes;
             const uint64_t db0 = desc_hi | (uint64_t)((b0 & 0x3FFFFu) >> 4);
             if (!(p.dbg & 2)) {
-              // fully unrolled issue sequences: the single issuing thread does ~4 scalar instructions per MMA
-              if (ksub == 3) {
-                switch (nk) {
-                  case 1: issue_unit<3, 1>(d_tmem, da0, db0, a_step, b_step, p.idesc, accumulate); break;
-                  case 2: issue_unit<3, 2>(d_tmem, da0, db0, a_step, b_step, p.idesc, accumulate); break;
-                  case 3: issue_unit<3, 3>(d_tmem, da0, db0, a_step, b_step, p.idesc, accumulate); break;
-                  default: issue_unit<3, 4>(d_tmem, da0, db0, a_step, b_step, p.idesc, accumulate); break;
-                }
-              } else if (ksub == 1) {
-                switch (nk) {
-                  case 1: issue_unit<1, 1>(d_tmem, da0, db0, a_step, b_step, p.idesc, accumulate); break;
-                  case 2: issue_unit<1, 2>(d_tmem, da0, db0, a_step, b_step, p.idesc, accumulate); break;
-                  case 3: issue_unit<1, 3>(d_tmem, da0, db0, a_step, b_step, p.idesc, accumulate); break;
-                  default: issue_unit<1, 4>(d_tmem, da0, db0, a_step, b_step, p.idesc, accumulate); break;
-                }
-              } else {
-                for (int u = 0; u < ksub; ++u)
-                  for (int j = 0; j < nk; ++j) {
-                    ptx::umma_bf16(d_tmem, da0 + (uint64_t)(u * a_step + 2 * j), db0 + (uint64_t)(u * b_step + 2 * j),
-                                   p.idesc, accumulate);
-                    accumulate = 1u;
+              // fully unrolled issue sequences; the m_sub sub-tiles of the tile share this unit's weights
+              for (int m = 0; m < p.m_sub; ++m) {
+                const uint32_t dm = d_tmem + (uint32_t)(m * p.sub_cols);
+                const uint64_t dam = da0 + (uint64_t)((uint32_t)m * p.a_sub16);
+                if (ksub == 3) {
+                  switch (nk) {
+                    case 1: issue_unit<3, 1>(dm, dam, db0, a_step, b_step, p.idesc, accumulate); break;
+                    case 2: issue_unit<3, 2>(dm, dam, db0, a_step, b_step, p.idesc, accumulate); break;
+                    case 3: issue_unit<3, 3>(dm, dam, db0, a_step, b_step, p.idesc, accumulate); break;
+                    default: issue_unit<3, 4>(dm, dam, db0, a_step, b_step, p.idesc, accumulate); break;
                   }
+                } else if (ksub == 1) {
+                  switch (nk) {
+                    case 1: issue_unit<1, 1>(dm, dam, db0, a_step, b_step, p.idesc, accumulate); break;
+                    case 2: issue_unit<1, 2>(dm, dam, db0, a_step, b_step, p.idesc, accumulate); break;
+                    case 3: issue_unit<1, 3>(dm, dam, db0, a_step, b_step, p.idesc, accumulate); break;
+                    default: issue_unit<1, 4>(dm, dam, db0, a_step, b_step, p.idesc, accumulate); break;
+                  }
+                } else {
+                  uint32_t acc_m = accumulate;
+                  for (int u = 0; u < ksub; ++u)
+                    for (int j = 0; j < nk; ++j) {
+                      ptx::umma_bf16(dm, dam + (uint64_t)(u * a_step + 2 * j), db0 + (uint64_t)(u * b_step + 2 * j), p.idesc, acc_m);
+                      acc_m = 1u;
+                    }
+                }
               }
+              accumulate = 1u;
             }
             if (++kc == p.kchunks) {
               kc = 0;
@@ -474,9 +483,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       if (p.epi_tile_split && (it & 1) != half) continue;  // the other warp group owns this tile
       const TileCoord c = decode_tile(p, t);
       const uint32_t acc_ph = (uint32_t)(it >> p.acc_shift) & 1u;
-      const int h = c.h0 + hl, w = c.w0 + wl;
-      const bool valid = (h < p.Hout) && (w < p.Wout);
-      const long long pix = ((long long)c.b * p.Hout + h) * p.Wout + w;
 
       const bool ts_on = leader && (e & 3) == 0 && (p.epi_tile_split || e == 0);
       if (ts_on) Y5_TS(2, it, 0);
@@ -488,7 +494,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         ptx::mbar_arrive(&tmem_empty[acc]);
         continue;
       }
-      const uint32_t taddr = tmem_base + (uint32_t)(acc * p.acc_stride) + ((uint32_t)(q * 32) << 16);
+      for (int m = 0; m < p.m_sub; ++m) {  // the tile's 128-pixel sub-tiles, stacked along H
+      const int hsub = c.h0 + m * p.Ht;
+      const int h = hsub + hl, w = c.w0 + wl;
+      const bool valid = (h < p.Hout) && (w < p.Wout);
+      const uint32_t taddr = tmem_base + (uint32_t)(acc * p.acc_stride + m * p.sub_cols) + ((uint32_t)(q * 32) << 16);
 
       if (p.mode == MODE_CONV) {
         const __nv_bfloat16* rrow =
@@ -515,7 +525,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         et.tm = &p.tmO;
         et.cn0 = c.n0;
         et.cw = c.w0 + box_w0;
-        et.chh = c.h0 + box_h0;
+        et.chh = hsub + box_h0;
         et.cb = c.b;
         // one specialised instantiation per layer flavour: nothing of the unused paths is issued
         const int flavour = (p.act ? 1 : 0) | (p.res ? 2 : 0) | (p.out2x ? 4 : 0);
@@ -567,12 +577,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
           ptx::fence_proxy_async();
           __syncwarp();
           if (leader) {
-            ptx::tma_store_5d(&p.tmO, sb, c0, c.w0 + box_w0, c.h0 + box_h0, a, c.b);
+            ptx::tma_store_5d(&p.tmO, sb, c0, c.w0 + box_w0, hsub + box_h0, a, c.b);
             ptx::tma_store_commit();
           }
           sbuf ^= 1;
         }
       }
+      }  // sub-tiles
       if (ts_on) Y5_TS(2, it, 2);
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tmem_empty[acc]);
@@ -716,14 +727,17 @@ int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
   // rows; the KH vertical taps read the same stage at row offsets that are whole 8-row swizzle groups, so each
   // input row crosses L2 -> shared memory (Ht + KH - 1) / Ht times per kw instead of KH times.  Taken when the
   // weights are resident or at least 3 pipeline stages still fit; otherwise one load per tap (classic).
-  auto plan = [&](bool rowshift) -> bool {
+  // A tile is m_sub 128-pixel sub-tiles stacked along H (Wt x Ht*m_sub pixels): they share the weight tiles of every unit and
+  // one trip through the producer -> MMA -> epilogue hand-shakes (about 1000 cycles of single-thread latencies per tile,
+  // profiles/r2_conv_timeline*.txt), so narrow layers (few MMAs per 128 pixels) and weight-streaming layers both gain.
+  auto plan = [&](bool rowshift, int m_sub) -> bool {
     int best_wt = 128;
     if (rowshift) {
       best_wt = 8;
     } else {  // Wt x Ht = 128 pixels, Wt the power of two (<=128) that wastes the fewest edge pixels
       double best_eff = -1;
       for (int wt = 128; wt >= 8; wt >>= 1) {
-        int ht = BM / wt;
+        int ht = BM / wt * m_sub;
         if (wt * d->stride > 256 || ht * d->stride > 256) continue;
         double eff = (double)Wout * Hout / ((double)((Wout + wt - 1) / wt * wt) * ((Hout + ht - 1) / ht * ht));
         if (eff > best_eff + 1e-9) {
@@ -734,11 +748,14 @@ int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
     }
     k.Wt = best_wt;
     k.Ht = BM / best_wt;
+    k.m_sub = m_sub;
+    const int tile_h = k.Ht * m_sub;
     k.tiles_w = (Wout + k.Wt - 1) / k.Wt;
-    k.tiles_h = (Hout + k.Ht - 1) / k.Ht;
+    k.tiles_h = (Hout + tile_h - 1) / tile_h;
     k.n_tiles_m = d->B * k.tiles_w * k.tiles_h;
     k.rowshift = rowshift ? 1 : 0;
-    a_rows = rowshift ? k.Ht + d->KH - 1 : k.Ht;  // image rows per A stage
+    a_rows = rowshift ? tile_h + d->KH - 1 : tile_h;  // image rows per A stage
+    if (a_rows * d->stride > 256) return false;          // TMA box dimension limit
     k.a_tx_bytes = (uint32_t)a_rows * k.Wt * bk * 2;
     k.row_shift_bytes = (uint32_t)k.Wt * bk * 2;
     const size_t a_stage = align_up(k.a_tx_bytes, 1024);
@@ -764,12 +781,31 @@ int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
     return k.stages >= (rowshift ? 3 : 2);
   };
   const bool want_rowshift = d->stride == 1 && d->KH > 1 && Wout >= 8 && !(d->flags & Y5OBB_CONV_NO_ROWSHIFT);
-  if (!(want_rowshift && plan(true)) && !plan(false)) {
-    delete o;
-    return Y5OBB_EINVAL;
+  const int sub_cols = bn <= 32 ? 32 : (bn <= 64 ? 64 : (bn <= 128 ? 128 : 256));
+  {
+    // largest m_sub whose two accumulator stages fit the 512 TMEM columns, that keeps every SM busy, adds no edge waste along
+    // H and still leaves a 3-deep operand ring; Y5OBB_CONV_MSUB1 / the environment variable Y5OBB_MSUB_MAX cap it (A-B runs)
+    int m_max = 4;
+    if (d->flags & Y5OBB_CONV_MSUB1) m_max = 1;
+    if (const char* e = getenv("Y5OBB_MSUB_MAX")) m_max = std::max(1, std::min(4, atoi(e)));
+    bool ok = false;
+    for (int m = 4; m >= 1 && !ok; m >>= 1) {
+      if (m > m_max || m * sub_cols * 2 > 512) continue;
+      for (int rs = want_rowshift ? 1 : 0; rs >= 0 && !ok; --rs) {
+        if (!plan(rs == 1, m)) continue;
+        const bool enough = m == 1 || ((long long)k.n_tiles_m * nt >= sm_count() && Hout % (k.Ht * m) == 0 && k.stages >= 3);
+        ok = enough;
+      }
+    }
+    if (!ok) {
+      delete o;
+      return Y5OBB_EINVAL;
+    }
   }
   // TMEM accumulator stages: the MMA issuer may run that many tiles ahead of the epilogue warps
-  k.acc_stride = bn <= 32 ? 32 : (bn <= 64 ? 64 : (bn <= 128 ? 128 : 256));
+  k.sub_cols = sub_cols;
+  k.acc_stride = sub_cols * k.m_sub;
+  k.a_sub16 = (uint32_t)(BM * bk * 2) >> 4;
   k.n_acc = std::min(MAX_ACC, 512 / k.acc_stride);
   if (d->flags & Y5OBB_CONV_ACC2) k.n_acc = 2;
   k.acc_shift = 0;

@@ -22,6 +22,8 @@
 #include <algorithm>
 #include <cstring>
 
+#include <cmath>
+
 #include "common.cuh"
 
 namespace y5obb {
@@ -56,7 +58,26 @@ struct LossK {
   int obj_blocks[3];
   long long obj_block_off[4];
   int ncand;          // nl * 5 * na * nt
+  // Circular-Smooth-Label rows (utils/rboxs_utils.py:9-26): csl_mode 0 = 180 floats per target at column 7 (the reference's
+  // [nt,187] layout), 1 = column 7 holds the row's rotation index int(90 - angle) (the caller evaluated the truncation in
+  // fp64 like the reference), 2 = the index is derived here from theta (column 6, fp32).  Modes 1/2 read gauss[].
+  int csl_mode;
+  float gauss[180];   // (float)exp(-(j - 90)^2 / (2 sigma^2)), j = 0..179: the un-rotated row of gaussian_label_cpu
 };
+
+// element c of target t's CSL row: gaussian_label_cpu's np.concatenate([y_sig[index:], y_sig[:index]]) = y_sig[(c + index) mod 180]
+__device__ __forceinline__ int csl_index(const LossK& L, int t) {
+  if (L.csl_mode == 1) return (int)L.targets[(long long)t * L.tcols + 7];
+  // rboxs_utils.py:70 angle = theta * 180 / pi + 90 with pi = 3.141592 (fp64), :21 index = int(num_class / 2 - angle)
+  const double angle = (double)L.targets[(long long)t * L.tcols + 6] * 180.0 / 3.141592 + 90.0;
+  return (int)(90.0 - angle);
+}
+__device__ __forceinline__ float csl_value(const LossK& L, const float* row, int index, int c) {
+  if (L.csl_mode == 0) return row[c];
+  int j = (c + index) % 180;
+  if (j < 0) j += 180;
+  return L.gauss[j];
+}
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
@@ -240,11 +261,12 @@ __global__ void k_rows(LossK L) {
   if (r.b < 0 || r.b >= L.B) return;  // malformed target row
   const float* ps = L.p[r.lvl] + (long long)r.cell_local * L.no;
   const float* csl = L.targets + (long long)r.t * L.tcols + 7;
+  const int csl_i = L.csl_mode ? csl_index(L, r.t) : 0;
   float s_cls = 0.f, s_th = 0.f;
   const int ci = 5 + L.nc;
   if (L.nc > 1)
     for (int c = lane; c < L.nc; c += 32) s_cls += bce_logits(ps[5 + c], c == r.cls ? L.cp : L.cn, L.cls_pw);
-  for (int c = lane; c < 180; c += 32) s_th += bce_logits(ps[ci + c], csl[c], L.theta_pw);
+  for (int c = lane; c < 180; c += 32) s_th += bce_logits(ps[ci + c], csl_value(L, csl, csl_i, c), L.theta_pw);
 #pragma unroll
   for (int o = 16; o; o >>= 1) {
     s_cls += __shfl_xor_sync(0xffffffffu, s_cls, o);
@@ -353,6 +375,7 @@ __global__ void k_bwd_rows(LossK L, const float* __restrict__ gloss) {
   const float* ps = L.p[r.lvl] + (long long)r.cell_local * L.no;
   float* gp = L.grad[r.lvl] + (long long)r.cell_local * L.no;
   const float* csl = L.targets + (long long)r.t * L.tcols + 7;
+  const int csl_i = L.csl_mode ? csl_index(L, r.t) : 0;
   const int ci = 5 + L.nc;
   if (L.nc > 1) {
     const float gc = up * L.hyp_cls / ((float)n * (float)L.nc);
@@ -360,7 +383,8 @@ __global__ void k_bwd_rows(LossK L, const float* __restrict__ gloss) {
       atomicAdd(gp + 5 + c, gc * bce_logits_grad(ps[5 + c], c == r.cls ? L.cp : L.cn, L.cls_pw));
   }
   const float gt = up * L.hyp_theta / ((float)n * 180.0f);
-  for (int c = lane; c < 180; c += 32) atomicAdd(gp + ci + c, gt * bce_logits_grad(ps[ci + c], csl[c], L.theta_pw));
+  for (int c = lane; c < 180; c += 32)
+    atomicAdd(gp + ci + c, gt * bce_logits_grad(ps[ci + c], csl_value(L, csl, csl_i, c), L.theta_pw));
   if (lane == 0) {
     const float s[4] = {ps[0], ps[1], ps[2], ps[3]};
     const D4 ciou = ciou_dual(s, r.aw, r.ah, r.tx, r.ty, r.tw, r.th);
@@ -372,8 +396,17 @@ __global__ void k_bwd_rows(LossK L, const float* __restrict__ gloss) {
 
 int fill(LossK& L, const y5obb_loss_desc* d, void* ws, size_t ws_bytes, size_t* need) {
   if (!d || d->nl < 1 || d->nl > 3 || d->B < 1 || d->na < 1 || d->na > 3 || d->nt < 0) return Y5OBB_EINVAL;
-  if (d->no != d->nc + 5 + 180 || d->no % 4 || d->tcols < 7 + 180) return Y5OBB_EINVAL;
+  if (d->no != d->nc + 5 + 180 || d->no % 4) return Y5OBB_EINVAL;
+  if (d->tcols != 7 && d->tcols != 8 && d->tcols < 7 + 180) return Y5OBB_EINVAL;
   memset(&L, 0, sizeof(L));
+  L.csl_mode = d->tcols == 7 ? 2 : (d->tcols == 8 ? 1 : 0);
+  {
+    const double sig = d->csl_sigma > 0 ? (double)d->csl_sigma : 2.0;  // hyp['csl_radius'] (hyp.finetune_dota.yaml:34)
+    for (int j = 0; j < 180; ++j) {
+      const double x = (double)j - 90.0;
+      L.gauss[j] = (float)std::exp(-(x * x) / (2.0 * sig * sig));
+    }
+  }
   L.nl = d->nl;
   L.B = d->B;
   L.na = d->na;

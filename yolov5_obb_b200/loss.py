@@ -24,7 +24,7 @@ class LossDesc(ctypes.Structure):
         ("targets", c_void_p), ("nt", c_int), ("tcols", c_int),
         ("anchor_t", c_float), ("cp", c_float), ("cn", c_float),
         ("hyp_box", c_float), ("hyp_obj", c_float), ("hyp_cls", c_float), ("hyp_theta", c_float),
-        ("cls_pw", c_float), ("obj_pw", c_float), ("theta_pw", c_float),
+        ("cls_pw", c_float), ("obj_pw", c_float), ("theta_pw", c_float), ("csl_sigma", c_float),
     ]
 
 
@@ -112,6 +112,9 @@ class ComputeLoss:
         d.anchor_t, d.cp, d.cn = h["anchor_t"], self.cp, self.cn
         d.hyp_box, d.hyp_obj, d.hyp_cls, d.hyp_theta = h["box"], h["obj"], h["cls"], h["theta"]
         d.cls_pw, d.obj_pw, d.theta_pw = h.get("cls_pw", 1.0), h.get("obj_pw", 1.0), h.get("theta_pw", 1.0)
+        d.csl_sigma = float(h.get("csl_radius", 2.0))
+        if d.tcols not in (7, 8) and d.tcols < 187:
+            raise RuntimeError("targets must have 187 columns (reference layout), or 8 (.., theta, csl index) or 7 (.., theta)")
         return d
 
     def __call__(self, p, targets):  # predictions, targets
@@ -119,6 +122,8 @@ class ComputeLoss:
         Args:
             p (list[P3_out,...]): torch.Size(b, self.na, h_i, w_i, self.no)
             targets (tensor): (n_gt_all_batch, [img_index clsid cx cy l s theta gaussian_θ_labels])
+                compact forms (8f rank 2): [nt, 8] = (..., theta, csl_index) with csl_index = compact_csl_index(theta) below, or
+                [nt, 7] = (..., theta): the Circular-Smooth-Label row is rebuilt inside the kernel
         Return:
             total_loss * bs (tensor): [1];  torch.cat((lbox, lobj, lcls, ltheta)).detach(): [4]
         """
@@ -127,3 +132,12 @@ class ComputeLoss:
         _lib.require_cuda(targets, "targets")
         ps = [x.float() for x in p]  # AMP half predictions are widened; autograd casts the gradient back
         return _LossFn.apply(self, targets, *ps)
+
+
+def compact_csl_index(theta_rad, num_class: int = 180):
+    """Column 7 of the 8-column compact target layout: the rotation index of utils/rboxs_utils.py:21,
+    `int(num_class / 2 - angle)` with `angle = theta * 180 / 3.141592 + 90` (:70, :5), evaluated in fp64 on the host exactly as
+    the reference's dataloader does.  theta_rad: float64 numpy array (the values poly2rbox returned)."""
+    import numpy as np
+    angle = np.asarray(theta_rad, dtype=np.float64) * 180 / 3.141592 + 90
+    return np.trunc(num_class / 2 - angle).astype(np.float32)
