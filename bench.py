@@ -7,7 +7,8 @@ tiles, the three stages the reference's `val.py --task speed` times (val.py:183-
 val.py:378-383).  Metric: images/s.
 
   value      whole-job images/s with the uint8 batch already resident in HBM (device timing, CUDA events,
-             max over ranks)
+             max over ranks); the step is Model.detect_records + non_max_suppression_obb: Model.forward with the Detect rows
+             written as the compact records the post-process reads (checked equal to Model.forward + NMS before timing)
   e2e        the same step through the public API from PINNED HOST memory: H2D of the uint8 batch and D2H
              of the detections inside the timed region
   roofline   conv_tc_kernel (tcgen05 implicit GEMM), the dominant kernel: algorithmic conv FLOPs per launch
@@ -578,12 +579,20 @@ def run_ours(args):
     # distinct tiles per batch a per-rank seed made rank 1's step 12 % longer than rank 0's - sample noise, not scaling
     x_host = synth_batch(B, seed=0).pin_memory()
     x_dev = x_host.to(dev)
-    pred0, _ = model(x_dev)  # builds the plan
-    eng = model._engines[(tuple(x_dev.shape), dev.index)]
+    pred0, _ = model(x_dev)                 # Model.forward: the [B, A, no] tensor of the reference API
+    pred0 = pred0.clone()
+    rec0 = model.detect_records(x_dev)      # the timed plan: same network, Detect rows as compact records
+    eng = model._engines[("records", tuple(x_dev.shape), dev.index)]
     # the number below is only worth reporting if THIS plan computes the right thing: compare it with the oracle first
     parity = None
     if not args.no_parity_gate and rank == 0:
         parity = parity_gate(model_cpu, x_dev, pred0)
+        # ... and the fused plan (records) must give exactly the detections of Model.forward + non_max_suppression_obb
+        d_full = non_max_suppression_obb(pred0, CONF, IOU, multi_label=True, max_det=MAX_DET)
+        d_rec = non_max_suppression_obb(rec0, CONF, IOU, multi_label=True, max_det=MAX_DET)
+        parity["fused_records_equal_model_forward_plus_nms"] = all(torch.equal(a, b) for a, b in zip(d_full, d_rec))
+        if not parity["fused_records_equal_model_forward_plus_nms"]:
+            raise RuntimeError("the fused Detect-records plan and Model.forward + non_max_suppression_obb disagree")
     conv_flops = [c.info()["flops"] for c in eng.convs]
     n_conv = len(eng.convs)
     st = _lib.stream_ptr(dev)
@@ -593,8 +602,8 @@ def run_ours(args):
     def step_device():
         """pre-process + forward + NMS of one resident batch; the result stays on the device as the packed
         ([B, max_det, 7], rows per image) pair, so consecutive steps queue back to back (no host read per step)."""
-        pred, _ = model(x_dev)
-        return non_max_suppression_obb(pred, CONF, IOU, multi_label=True, max_det=MAX_DET, return_packed="async")
+        rec = model.detect_records(x_dev)   # Model.forward with the Detect rows written as compact records (fused post-process)
+        return non_max_suppression_obb(rec, CONF, IOU, multi_label=True, max_det=MAX_DET, return_packed="async")
 
     from yolov5_obb_b200.pipeline import DetectPipeline
     pipe = DetectPipeline(model, CONF, IOU, MAX_DET, multi_label=True, device=dev)
@@ -632,7 +641,7 @@ def run_ours(args):
     # the timed region runs; warm-up and timed steps are the same load
     sampler = ClockSampler(local) if rank == 0 else None
     # one blocking call first: it sizes the candidate capacity for this workload (sticky hint, general._CAP_HINT)
-    non_max_suppression_obb(model(x_dev)[0], CONF, IOU, multi_label=True, max_det=MAX_DET)
+    non_max_suppression_obb(model.detect_records(x_dev), CONF, IOU, multi_label=True, max_det=MAX_DET)
     for _ in range(max(args.warmup, 3)):
         dets = step_device()
     ms_total, dets = timed(step_device, args.steps)

@@ -46,6 +46,10 @@ const char* y5obb_build_info(void);     /* "sm_100a nvcc <ver> <date>" */
                                        the kernel verifies per box (r + max(|cx|,|cy|) < max_wh/2 - 8); if the test
                                        fails counts[batch] comes back as -2 and the caller re-runs with this flag */
 
+#define Y5OBB_NMS_COMPACT_PRED 8     /* y5obb_nms_obb_f32 only: `pred` holds the Detect epilogue's compact records
+                                       [batch, anchors, ((nc + 6) + 3) / 4 * 4] = (cx, cy, w, h, obj, cls[nc], theta index, pad)
+                                       instead of the [batch, anchors, no] tensor (y5obb_conv_desc.det_decode = 2) */
+
 /* Workspace needed for n_total boxes over n_images images with at most max_per_image boxes in any one
  * image (pass n_total if unknown). */
 size_t y5obb_nms_workspace_bytes(int64_t n_total, int64_t n_images, int64_t max_per_image);
@@ -115,6 +119,7 @@ typedef struct y5obb_conv y5obb_conv_t;
                                       prologue overlaps the previous kernel's tail and it waits, griddepcontrol.wait, before its
                                       first global-memory access; also switched off by the environment variable Y5OBB_NO_PDL=1) */
 #define Y5OBB_CONV_MSUB1 128       /* flags: 128-pixel tiles only (default: up to four 128-pixel sub-tiles per tile) */
+#define Y5OBB_CONV_NO_UP_TMA 2048  /* flags: the 2x up-sampled copy through per-thread stores (default: four TMA stores of the staged tile) */
 #define Y5OBB_CONV_ACC2 64         /* flags: two TMEM accumulator stages only (A-B comparison; default: as many as 512 columns hold) */
 
 typedef struct {

@@ -39,3 +39,27 @@ def test_pipeline_equals_blocking_calls():
         for a, b in zip(g, w):
             assert not a.is_cuda and torch.equal(a, b)
     assert pipe.h2d_bytes == sum(x.numel() for x in batches)
+
+
+@pytest.mark.parametrize("size,B,S", [("n", 3, 160), ("s", 2, 256)])
+def test_fused_detect_records_equal_forward_plus_nms(size, B, S):
+    """Model.detect_records (Detect epilogue writes compact (box, obj, cls, theta index) records) + the post-process gives
+    bit-identical detections to Model.forward + non_max_suppression_obb on the [B, A, no] tensor, and the records hold
+    exactly the tensor's values (same sigmoid / decode arithmetic; theta index = first maximum of the 180 bins)."""
+    import torch
+    from tests.modelgen import build_mirror
+    from yolov5_obb_b200.general import non_max_suppression_obb
+    m = build_mirror(size, nc=15, seed=3, obj_bias=1.0, cls_bias=-1.0, det_gain=6.0).to("cuda:0")
+    x = torch.rand(B, 3, S, S + 32, generator=torch.Generator().manual_seed(2)).to("cuda:0")
+    pred, _ = m(x)
+    pred = pred.clone()
+    rec = m.detect_records(x)
+    assert rec.data.shape == (B, pred.shape[1], 24) and rec.nc == 15
+    assert torch.equal(rec.data[..., :20], pred[..., :20])
+    assert torch.equal(rec.data[..., 20].long(), pred[..., 20:].argmax(-1))
+    for kw in (dict(multi_label=True, max_det=300), dict(multi_label=False, max_det=100), dict(multi_label=True, classes=[1, 5])):
+        a = non_max_suppression_obb(pred, 0.25, 0.45, **kw)
+        b = non_max_suppression_obb(rec, 0.25, 0.45, **kw)
+        assert sum(t.shape[0] for t in a) > 0
+        for u, v in zip(a, b):
+            assert torch.equal(u, v)

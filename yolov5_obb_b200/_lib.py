@@ -94,6 +94,7 @@ PROTOTYPES = {
 NMS_STRICT_GT = 1
 NMS_DROP_SMALL = 2
 NMS_NO_CLASS_SPLIT = 4
+NMS_COMPACT_PRED = 8
 
 
 def lib() -> ctypes.CDLL:

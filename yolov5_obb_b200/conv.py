@@ -164,7 +164,7 @@ class Conv:
         if det:
             d.det_out = det["out"].data_ptr()
             d.det_rows_per_image, d.det_row_off = det["rows_per_image"], det["row_off"]
-            d.det_no, d.det_decode, d.det_stride = det["no"], int(det["decode"]), float(det["stride"])
+            d.det_no, d.det_decode, d.det_stride = det["no"], int(det["decode"]), float(det["stride"])  # decode 2 = compact records
             d.det_anchor = (c_float * 6)(*[float(v) for v in det["anchors_px"]])
         self._keep = (x, w_packed, bias_pad, out, res, out2x, det)  # buffers must outlive the descriptors
         self._h = c_void_p()

@@ -63,6 +63,8 @@ struct ConvK {
   CUtensorMap tmA;
   CUtensorMap tmB;
   CUtensorMap tmO;  // output slice, box {32 ch, min(Wt,32), 32/min(Wt,32), 1}, 64-byte swizzle (MODE_CONV)
+  CUtensorMap tmU;  // the 2x nearest up-sampled copy viewed as (C, dx, W, dy, B*H): the staged tile is stored four times
+  int up_tma;       // 1: up-sampled copy through tmU (needs Hout % tile height == 0: B and H share a dimension); 0: per-thread stores
   // geometry
   int B, Hout, Wout;
   int Wt, Ht, tiles_w, tiles_h;
@@ -104,7 +106,8 @@ struct ConvK {
   // detect
   float* det_out;
   long long det_rows_per_image, det_row_off;
-  int det_no, det_decode;
+  int det_no, det_decode;  // det_decode: 0 raw logits, 1 sigmoid + grid/anchor decode, 2 = 1 as compact records (see the epilogue)
+  int det_rec_w;           // floats per compact record: (5 + nc + 1) rounded up to 4
   float det_stride;
   float det_anchor[6];
   unsigned long long* ts;  // debug: clock64 stamps of CTA 0, [role 3][tile 32][slot 8] (y5obb_conv_debug_timestamps)
@@ -177,6 +180,8 @@ struct EpiTile {
   int nvalid, col_first, col_step;
   const CUtensorMap* tm;
   int cn0, cw, chh, cb;
+  const CUtensorMap* tmu;  // up-sampled copy by TMA (null: per-thread stores through urow)
+  int ubh;                 // cb * Hout + chh
 };
 
 template <bool ACT, bool RES, bool UP>
@@ -231,7 +236,7 @@ __device__ __forceinline__ void conv_epi_tile(const EpiTile& e, int& sbuf) {
       o.w = pack_bf16(v[6], v[7]);
       // 64-byte swizzle (Swizzle<2,4,3>): 16-byte chunk index ^= (row >> 1) & 3
       *reinterpret_cast<uint4*>(sb + (((uint32_t)g ^ e.swz) << 4)) = o;
-      if (UP) {
+      if (UP && !e.tmu) {
         const int cg = c0 + g * 8;
         if (e.urow && cg < e.nvalid) {
           *reinterpret_cast<uint4*>(e.urow + cg) = o;
@@ -246,6 +251,11 @@ __device__ __forceinline__ void conv_epi_tile(const EpiTile& e, int& sbuf) {
     if (e.leader) {
       // rows beyond the image and channels beyond Cout are clipped by the tensor map
       ptx::tma_store_4d(e.tm, e.stage + sbuf * e.stage_bytes, e.cn0 + c0, e.cw, e.chh, e.cb);
+      if (UP && e.tmu) {  // nn.Upsample(2x nearest): the same staged tile lands on the four (dy, dx) phases
+#pragma unroll
+        for (int ph = 0; ph < 4; ++ph)
+          ptx::tma_store_5d(e.tmu, e.stage + sbuf * e.stage_bytes, e.cn0 + c0, ph & 1, e.cw, ph >> 1, e.ubh);
+      }
       ptx::tma_store_commit();
     }
     sbuf ^= 1;
@@ -275,7 +285,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&p.tmA);
     ptx::prefetch_tmap(&p.tmB);
-    ptx::prefetch_tmap(&p.tmO);
+    if (!(p.mode == MODE_DETECT && p.det_decode == 2)) ptx::prefetch_tmap(&p.tmO);
+    if (p.out2x && p.up_tma) ptx::prefetch_tmap(&p.tmU);
     for (int s = 0; s < p.stages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
@@ -527,6 +538,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         et.cw = c.w0 + box_w0;
         et.chh = hsub + box_h0;
         et.cb = c.b;
+        et.tmu = (p.out2x && p.up_tma) ? &p.tmU : nullptr;
+        et.ubh = c.b * p.Hout + hsub + box_h0;
         // one specialised instantiation per layer flavour: nothing of the unused paths is issued
         const int flavour = (p.act ? 1 : 0) | (p.res ? 2 : 0) | (p.out2x ? 4 : 0);
         switch (flavour) {
@@ -539,6 +552,54 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
           case 6: conv_epi_tile<false, true, true>(et, sbuf); break;  // generic paths tolerate null rrow / urow
           default: conv_epi_tile<true, true, true>(et, sbuf); break;
         }
+      } else if (p.det_decode == 2) {
+        // Detect, compact records for the fused post-process (the [B, A, no] tensor is never written): per anchor row
+        // rec_w floats = (cx, cy, w, h, obj, cls[nc], theta index) - everything non_max_suppression_obb reads of a row
+        // (utils/general.py:781-832).  Same sigmoid and decode arithmetic as the full-tensor mode below; the theta index is
+        // the first maximum over the 180 sigmoid values, as torch.max returns it (:822).  Every warp owns whole tiles here.
+        const int a = c.nt;
+        const int nfix = p.det_no - 180;                    // 5 + nc leading columns
+        float* rec = p.det_out + ((long long)c.b * p.det_rows_per_image + p.det_row_off + ((long long)a * p.Hout + h) * p.Wout + w) * p.det_rec_w;
+        float best = -INFINITY;
+        int bk = 0;
+        for (int c0 = 0; c0 < p.det_no; c0 += 32) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)c0, r);
+          ptx::tmem_ld_wait();
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + c.n0 + c0);
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const int col = c0 + 4 * g;
+            if (col >= p.det_no) break;
+            const float4 bv = __ldg(b4 + g);
+            float v[4];
+            v[0] = sigmoid_fast(__uint_as_float(r[g * 4 + 0]) + bv.x);
+            v[1] = sigmoid_fast(__uint_as_float(r[g * 4 + 1]) + bv.y);
+            v[2] = sigmoid_fast(__uint_as_float(r[g * 4 + 2]) + bv.z);
+            v[3] = sigmoid_fast(__uint_as_float(r[g * 4 + 3]) + bv.w);
+            if (col == 0) {  // xy, wh (models/yolo.py:73-74)
+              v[0] = (v[0] * 2.0f - 0.5f + (float)w) * p.det_stride;
+              v[1] = (v[1] * 2.0f - 0.5f + (float)h) * p.det_stride;
+              v[2] = (v[2] * 2.0f) * (v[2] * 2.0f) * p.det_anchor[2 * a];
+              v[3] = (v[3] * 2.0f) * (v[3] * 2.0f) * p.det_anchor[2 * a + 1];
+            }
+            if (col + 3 < nfix) {
+              if (valid) *reinterpret_cast<float4*>(rec + col) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int cc = col + k;
+                if (cc < nfix) {
+                  if (valid) rec[cc] = v[k];
+                } else if (cc < p.det_no && v[k] > best) {
+                  best = v[k];
+                  bk = cc - nfix;
+                }
+              }
+            }
+          }
+        }
+        if (valid) rec[nfix] = (float)bk;
       } else {
         // Detect: N tile nt == anchor nt; columns [0, det_no) are that anchor's outputs.
         // out row = b * rows_per_image + row_off + (a * H + h) * W + w   (models/yolo.py:65,81): the tensor map
@@ -835,6 +896,7 @@ int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
   k.det_row_off = d->det_row_off;
   k.det_no = d->det_no;
   k.det_decode = d->det_decode;
+  k.det_rec_w = ((d->det_no - 180 + 1) + 3) / 4 * 4;
   k.det_stride = d->det_stride;
   for (int i = 0; i < 6; ++i) k.det_anchor[i] = d->det_anchor[i];
   if (d->mode == MODE_CONV) {
@@ -909,7 +971,26 @@ int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
       return Y5OBB_ECUDA;
     }
   }
-  if (d->mode == MODE_DETECT) {  // output rows as (no, W, H, anchor, image) fp32; each warp stores 32 pixels x 32 floats
+  k.up_tma = 0;
+  if (d->mode == MODE_CONV && d->out2x && Hout % (k.Ht * k.m_sub) == 0 && !(d->out2x_pix_stride % 8) &&
+      !(reinterpret_cast<uintptr_t>(d->out2x) & 15)) {
+    // out2x[b, 2h + dy, 2w + dx, c] as a 5-D tensor (c, dx, w, dy, b * H + h): images are contiguous, so b and h share one
+    // dimension - which is why the tile rows must not run past the image (no per-image clipping along that dimension)
+    const int bw = std::min(k.Wt, 32);
+    const cuuint64_t pix = (cuuint64_t)d->out2x_pix_stride * 2, row = pix * 2 * Wout;
+    cuuint64_t dims[5] = {(cuuint64_t)d->Cout, 2, (cuuint64_t)Wout, 2, (cuuint64_t)d->B * Hout};
+    cuuint64_t strides[4] = {pix, 2 * pix, row, 2 * row};
+    cuuint32_t box[5] = {32, 1, (cuuint32_t)bw, 1, (cuuint32_t)(32 / bw)};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&k.tmU, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, d->out2x, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS && !(d->flags & Y5OBB_CONV_NO_UP_TMA)) k.up_tma = 1;
+  }
+  if (d->mode == MODE_DETECT && d->det_decode == 2 && (reinterpret_cast<uintptr_t>(d->det_out) & 15)) {
+    delete o;
+    return Y5OBB_EINVAL;
+  }
+  if (d->mode == MODE_DETECT && d->det_decode != 2) {  // output rows as (no, W, H, anchor, image) fp32; each warp stores 32 pixels x 32 floats
     const int bw = std::min(k.Wt, 32);
     cuuint64_t dims[5] = {(cuuint64_t)d->det_no, (cuuint64_t)Wout, (cuuint64_t)Hout, (cuuint64_t)nt, (cuuint64_t)d->B};
     const cuuint64_t rowb = (cuuint64_t)d->det_no * 4;
@@ -935,6 +1016,7 @@ int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
   // many tiles per CTA: the two epilogue groups alternate tiles (two epilogues in flight, any BN);
   // few tiles per CTA: they split the columns of each tile (shortest single-tile latency)
   k.epi_tile_split = (total >= 4 * o->grid) ? 1 : 0;
+  if (d->mode == MODE_DETECT && d->det_decode == 2) k.epi_tile_split = 1;  // a record is assembled by one thread over all columns
   // >= 116 KB so that two CTAs (each owning all 512 TMEM columns) can never share an SM
   o->smem = std::max<size_t>(k.b_res_bytes + (size_t)k.stages * stage_bytes + EPI_WARPS * 2 * k.epi_stage_bytes + 1024,
                              116 * 1024);

@@ -530,13 +530,15 @@ struct PPArgs {
   unsigned long long class_mask;  // bit j set = class j allowed
   float max_wh;
   int* far_flag;  // set when a box is so large / far out that boxes of different classes could touch despite the offset
+  int row_w;      // floats per row of `pred`: no (the Detect tensor) or the compact record width (Y5OBB_NMS_COMPACT_PRED)
+  int compact;    // 1: rows are (cx, cy, w, h, obj, cls[nc], theta index) records written by the Detect epilogue
 };
 
 __global__ void k_pp_count(PPArgs a, int* __restrict__ cnt) {
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= a.rows) return;
-  const float* p = a.pred + row * a.no;
+  const float* p = a.pred + row * a.row_w;
   const float obj = p[4];
   int n = 0;
   if (obj > a.conf) {
@@ -584,13 +586,13 @@ __global__ void k_pp_emit(PPArgs a, const int* __restrict__ cnt, const int* __re
     n_valid[1] = total;                                // what the host checks against capacity
   }
   if (cnt[row] == 0) return;
-  const float* p = a.pred + row * a.no;
+  const float* p = a.pred + row * a.row_w;
   const float obj = p[4];
-  // theta = first argmax over the 180 angle bins
+  // theta = first argmax over the 180 angle bins (compact records carry it already)
   float bv = -INFINITY;
   int bk = 0x7fffffff;
   const int cidx = 5 + a.nc;
-  for (int k = lane; k < 180; k += 32) {
+  for (int k = lane; k < (a.compact ? 0 : 180); k += 32) {
     const float v = p[cidx + k];
     if (v > bv) {
       bv = v;
@@ -606,7 +608,8 @@ __global__ void k_pp_emit(PPArgs a, const int* __restrict__ cnt, const int* __re
       bk = ok;
     }
   }
-  if (bk > 179) bk = 0;  // all-NaN row: torch.max returns index 0
+  if (a.compact) bk = (int)p[cidx];
+  if (bk > 179 || bk < 0) bk = 0;  // all-NaN row: torch.max returns index 0
   const float theta = __fmul_rn(__fdiv_rn((float)(bk - 90), 180.0f), 3.141592f);
   const float cx = p[0], cy = p[1], w = p[2], h = p[3];
   const int img = (int)(row / a.A);
@@ -965,6 +968,8 @@ int y5obb_nms_obb_f32(const float* pred, int64_t batch, int64_t anchors, int no,
   PPWs w = carve_pp(workspace, rows, (int)batch, max_candidates, max_nms, nc);
   if (w.total > workspace_bytes) return Y5OBB_EWORKSPACE;
   PPArgs a;
+  a.compact = (flags & Y5OBB_NMS_COMPACT_PRED) ? 1 : 0;
+  a.row_w = a.compact ? ((nc + 6) + 3) / 4 * 4 : no;
   a.pred = pred;
   a.rows = rows;
   a.A = (int)anchors;

@@ -51,7 +51,7 @@ def _is(m, name: str) -> bool:
 
 
 class InferenceEngine:
-    def __init__(self, model: "Y.Model", B: int, H: int, W: int, device, conv_flags: int = 0):
+    def __init__(self, model: "Y.Model", B: int, H: int, W: int, device, conv_flags: int = 0, compact_detect: bool = False):
         device = torch.device(device)
         if device.type != "cuda":
             raise RuntimeError("InferenceEngine needs a CUDA device (sm_100a); there is no CPU path")
@@ -232,17 +232,23 @@ class InferenceEngine:
         self.no, self.na = det.no, det.na
         rows = [det.na * hw[f][0] * hw[f][1] for f in det.f]
         self.rows_total = sum(rows)
-        self.pred = torch.empty((B, self.rows_total, det.no), dtype=torch.float32, device=device)
+        # compact_detect: the Detect epilogue writes (cx, cy, w, h, obj, cls[nc], theta index) records - all that
+        # non_max_suppression_obb reads of a row - instead of the [B, A, no] tensor (96 B instead of 800 B per anchor row)
+        self.compact_detect = bool(compact_detect)
+        self.rec_w = ((det.nc + 6) + 3) // 4 * 4
+        self.nc = det.nc
+        self.pred = torch.empty((B, self.rows_total, self.rec_w if compact_detect else det.no), dtype=torch.float32, device=device)
         row_off = 0
         for l, f in enumerate(det.f):
             mi = det.m[l]
             stride = float(det.stride[l])
             anchors_px = (det.anchors[l].detach().float().cpu() * stride).flatten().tolist()
             add_conv(out[f], mi.weight.detach().float().cpu(), mi.bias.detach().float().cpu(), 1, 1, 0, False,
-                     detd=dict(out=self.pred, rows_per_image=self.rows_total, row_off=row_off, no=det.no, decode=True,
+                     detd=dict(out=self.pred, rows_per_image=self.rows_total, row_off=row_off, no=det.no,
+                               decode=2 if compact_detect else True,
                                stride=stride, anchors_px=anchors_px))
             row_off += rows[l]
-        self.hbm_bytes += 4.0 * self.pred.numel() + 4.0 * B * 3 * H * W + 2.0 * self.x_s2d.numel()
+        self.hbm_bytes += 4.0 * B * self.rows_total * det.no + 4.0 * B * 3 * H * W + 2.0 * self.x_s2d.numel()
         self.n_launches = len(self.ops) + 1
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:

@@ -12,6 +12,14 @@ MAX_WH = 4096     # general.py:793
 MAX_NMS = 30000   # general.py:794
 
 
+class DetectRecords:
+    """What yolo.Model.detect_records returns: `data` [B, A, rec_w] fp32 rows (cx, cy, w, h, obj, cls[nc], theta index, pad)
+    written by the Detect epilogue (engine-owned buffer, overwritten by the next forward), and the class count."""
+
+    def __init__(self, data: torch.Tensor, nc: int):
+        self.data, self.nc = data, int(nc)
+
+
 def non_max_suppression_obb(prediction: torch.Tensor, conf_thres: float = 0.25, iou_thres: float = 0.45,
                             classes: Optional[Sequence[int]] = None, agnostic: bool = False, multi_label: bool = False,
                             labels=(), max_det: int = 1500, return_packed: bool = False):
@@ -22,10 +30,14 @@ def non_max_suppression_obb(prediction: torch.Tensor, conf_thres: float = 0.25, 
     Returns:
         list of detections, len=batch_size, on (n,7) tensor per image [xylsθ, conf, cls] θ ∈ [-pi/2, pi/2)
     """
+    compact = isinstance(prediction, DetectRecords)
+    if compact:
+        nc_rec = prediction.nc
+        prediction = prediction.data
     _lib.require_cuda(prediction, "prediction")
     if prediction.dim() != 3:
         raise RuntimeError("prediction must be [batch, anchors, nc+185]")
-    nc = prediction.shape[2] - 5 - 180
+    nc = nc_rec if compact else prediction.shape[2] - 5 - 180
     assert 0 <= conf_thres <= 1, f'Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0'
     assert 0 <= iou_thres <= 1, f'Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0'
     if labels:
@@ -33,6 +45,8 @@ def non_max_suppression_obb(prediction: torch.Tensor, conf_thres: float = 0.25, 
     if nc < 1 or nc > 64:
         raise RuntimeError(f"nc={nc} unsupported (1..64)")
     B, A, no = prediction.shape
+    if compact:
+        no = nc + 185
     dev = prediction.device
     if B == 0 or A == 0:
         return [torch.zeros((0, 7), device=dev) for _ in range(B)]
@@ -46,7 +60,7 @@ def non_max_suppression_obb(prediction: torch.Tensor, conf_thres: float = 0.25, 
     # optimistic capacity (every kernel of the pipeline runs over `cap` slots); grown on overflow below
     cap = min(worst, max(B * 8192, 1 << 16, int(_CAP_HINT.get((B, A, nc), 0))))
     nosplit = _NO_SPLIT.get((B, A, nc), False)
-    args = (pred, B, A, no, nc, conf_thres, iou_thres, mask, agnostic, multi_label, max_det, nosplit)
+    args = (pred, B, A, no, nc, conf_thres, iou_thres, mask, agnostic, multi_label, max_det, nosplit, compact)
     if return_packed == "async":
         # no host read at all: (device [B, max_det, 7], device int64 [B + 1] = rows per image + total candidates, cap).
         # The caller checks counts[B] <= cap when it reads the counts (pipeline.DetectPipeline does, and re-runs).
@@ -60,7 +74,7 @@ def non_max_suppression_obb(prediction: torch.Tensor, conf_thres: float = 0.25, 
         c = counts.tolist()  # the one host read: rows per image (+ total candidates)
         if c[B] == -2:  # a box reaches another class's offset copy: the class-split shortcut is not exact here
             _NO_SPLIT[(B, A, nc)] = True
-            args = args[:-1] + (True,)
+            args = args[:-2] + (True, args[-1])
             continue
         if c[B] <= cap:
             break
@@ -85,7 +99,7 @@ def _launch_graphed(args, cap):
     pred = args[0]
     if os.environ.get("Y5OBB_NO_GRAPH", "0") == "1":
         return _launch(args, cap)
-    key = (pred.data_ptr(), pred.device.index, cap) + tuple(args[1:])
+    key = (pred.data_ptr(), pred.device.index, cap) + tuple(args[1:])  # (includes the compact-record flag)
     slot = _GRAPHS.get(key)
     if slot is None:
         if len(_GRAPHS) > 16:
@@ -105,7 +119,7 @@ def _launch_graphed(args, cap):
 
 
 def _launch(args, cap, keep_ws=False):
-    pred, B, A, no, nc, conf_thres, iou_thres, mask, agnostic, multi_label, max_det, nosplit = args
+    pred, B, A, no, nc, conf_thres, iou_thres, mask, agnostic, multi_label, max_det, nosplit, compact = args
     L = _lib.lib()
     dev = pred.device
     out = torch.empty((B, max_det, 7), dtype=torch.float32, device=dev)
@@ -116,7 +130,8 @@ def _launch(args, cap, keep_ws=False):
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev) if keep_ws else _lib.workspace(nbytes, dev, "nms_obb")
         rc = L.y5obb_nms_obb_f32(pred.data_ptr(), B, A, no, nc, float(conf_thres), float(iou_thres), mask,
                                  int(bool(agnostic)), int(bool(multi_label)), int(max_det), MAX_NMS, float(MAX_WH),
-                                 _lib.NMS_STRICT_GT | (_lib.NMS_NO_CLASS_SPLIT if nosplit else 0), cap, out.data_ptr(),
+                                 _lib.NMS_STRICT_GT | (_lib.NMS_NO_CLASS_SPLIT if nosplit else 0) | (_lib.NMS_COMPACT_PRED if compact else 0),
+                                 cap, out.data_ptr(),
                                  counts.data_ptr(), ws.data_ptr(),
                                  ws.numel(), _lib.stream_ptr(dev))
     _lib.check(rc, "y5obb_nms_obb_f32")

@@ -12,8 +12,11 @@ from .general import non_max_suppression_obb
 
 class DetectPipeline:
     def __init__(self, model, conf_thres: float = 0.25, iou_thres: float = 0.45, max_det: int = 1500,
-                 multi_label: bool = True, classes=None, agnostic: bool = False, device=None):
+                 multi_label: bool = True, classes=None, agnostic: bool = False, device=None, fused_detect: bool = True):
         self.model = model
+        # fused_detect: Model.detect_records + the post-process on the compact records (the [B, A, no] prediction tensor never
+        # crosses HBM); False: Model.forward + non_max_suppression_obb on the tensor, as the two separate reference calls
+        self.fused = bool(fused_detect) and hasattr(model, "detect_records")
         self.kw = dict(conf_thres=conf_thres, iou_thres=iou_thres, classes=classes, agnostic=agnostic,
                        multi_label=multi_label, max_det=max_det)
         self.device = torch.device(device) if device is not None else next(model.parameters()).device
@@ -64,7 +67,7 @@ class DetectPipeline:
                 self._upload(slot ^ 1, nxt, not used[slot ^ 1])
                 used[slot ^ 1] = True
             compute.wait_event(self._copied[slot])
-            pred, _ = self.model(self._bufs[slot])
+            pred = self.model.detect_records(self._bufs[slot]) if self.fused else self.model(self._bufs[slot])[0]
             self._consumed[slot].record(compute)  # the first kernel has consumed the input by now (stream order)
             packed, counts, cap = non_max_suppression_obb(pred, return_packed="async", **self.kw)
             hout, hcnt, ev = self._host_slot(slot, packed.shape[0], packed.shape[1])
@@ -86,7 +89,8 @@ class DetectPipeline:
         c = hcnt.tolist()
         B = len(c) - 1
         if c[B] > cap or c[B] < 0 or any(k < 0 for k in c[:B]):  # rare: more candidates than the optimistic capacity -> re-run, blocking
-            pred, _ = self.model(x_host.to(self.device))
+            xd = x_host.to(self.device)
+            pred = self.model.detect_records(xd) if self.fused else self.model(xd)[0]
             packed, counts = non_max_suppression_obb(pred, return_packed=True, **self.kw)
             host = packed.cpu()
             return [host[b, :k].clone() for b, k in enumerate(counts)]
