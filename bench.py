@@ -651,6 +651,23 @@ def run_ours(args):
         raise RuntimeError("NMS candidate capacity exceeded in the timed steps: the measurement would be invalid")
     det_per_img = float(sum(rows[:B])) / B
     ms_step = ms_total / args.steps
+    # where the step goes (a few extra steps with events between the two public calls; not part of the timed region)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    bd = [0.0, 0.0]
+    host_s = 0.0
+    torch.cuda.synchronize()
+    for _ in range(5):
+        t0 = time.perf_counter()
+        ev[0].record()
+        rec = model.detect_records(x_dev)
+        ev[1].record()
+        non_max_suppression_obb(rec, CONF, IOU, multi_label=True, max_det=MAX_DET, return_packed="async")
+        ev[2].record()
+        host_s += time.perf_counter() - t0
+        torch.cuda.synchronize()
+        bd[0] += ev[0].elapsed_time(ev[1])
+        bd[1] += ev[1].elapsed_time(ev[2])
+    breakdown = {"forward_ms": bd[0] / 5, "post_process_ms": bd[1] / 5, "host_enqueue_ms": host_s / 5 * 1e3}
     value = world * B / (ms_step / 1e3)
 
     run_e2e(3)
@@ -737,7 +754,7 @@ def run_ours(args):
                 "api": "yolov5_obb_b200.pipeline.DetectPipeline (pinned host uint8 in, per-image host detections out; "
                        "two-deep software pipeline: H2D of batch i+1 and host read-out of batch i-1 overlap batch i)"},
         "gpu_launches": (1 + len(eng.ops) + 10) * args.steps,
-        "detections_per_image": det_per_img,
+        "detections_per_image": det_per_img, "step_breakdown": breakdown,
         "clocks": clocks, "roofline": roof,
     }
     if parity is not None:

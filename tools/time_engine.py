@@ -10,10 +10,17 @@ from yolov5_obb_b200 import _lib
 from yolov5_obb_b200.engine import InferenceEngine
 
 size, B, S = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
-m = build_mirror(size, nc=15, seed=0).cuda()
 import os
+if os.environ.get("Y5OBB_TE_CALIBRATED") == "1":   # the benchmark's 'alive' model (tests/modelgen.calibrated_bench_model)
+    import bench
+    m = bench.build_model(size).cuda()
+    x = bench.synth_batch(B, 0).cuda()
+else:
+    m = build_mirror(size, nc=15, seed=0).cuda()
+    x = None
 eng = InferenceEngine(m, B, S, S, torch.device("cuda:0"), conv_flags=int(os.environ.get("Y5OBB_CONV_FLAGS", "0")))
-x = torch.rand(B, 3, S, S, device="cuda")
+if x is None:
+    x = torch.rand(B, 3, S, S, device="cuda")
 for _ in range(3):
     eng.forward(x)
 torch.cuda.synchronize()

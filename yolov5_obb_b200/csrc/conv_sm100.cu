@@ -36,10 +36,11 @@ namespace {
 constexpr int BM = 128;  // output pixels per tile == TMEM lanes
 constexpr int MAX_STAGES = 16;
 constexpr int MAX_ACC = 8;                // TMEM accumulator stages: 512 columns / accumulator stride
-constexpr int NUM_THREADS = 320;          // TMA producer, MMA issuer, 8 epilogue warps
-constexpr int EPI_WARPS = 8;
+constexpr int NUM_THREADS = 320;          // TMA producer, MMA issuer, 8 epilogue warps (the one-CTA-per-SM configuration)
+constexpr int EPI_WARPS = 8;              // ... or 4 epilogue warps (192 threads) when two CTAs share an SM, see ConvK::epi_warps
 constexpr int EPI_STAGE_CONV = 32 * 64;    // 32 pixels x 32 bf16 channels, 64-byte swizzled
 constexpr int EPI_STAGE_DET = 32 * 128;    // 32 pixels x 32 fp32 outputs, 128-byte swizzled
+constexpr int DUAL_SMEM = 112 * 1024;     // per CTA when two share an SM (228 KB per SM, 1 KB reserved per CTA)
 constexpr int SMEM_TOTAL = 224 * 1024;    // dynamic shared memory we ask for at most (227 KB is the hardware cap)
 
 enum Mode : int { MODE_CONV = 0, MODE_DETECT = 1 };
@@ -85,6 +86,10 @@ struct ConvK {
   int pairw;           // 1: stride-2 conv whose input is viewed as horizontal pixel PAIRS (2*pix_stride channels per
                        // position): the column phase of a tap is a channel offset, so TMA reads contiguous rows
   int in_pix_stride;
+  int epi_warps;       // 8: one CTA per SM (all 512 TMEM columns, two epilogue groups); 4: TWO CTAs per SM, each with 256 TMEM
+                       // columns, half the shared memory and one epilogue group - two independent producer / MMA / epilogue
+                       // pipelines whose hand-shake bubbles overlap (ncu: no unit of the single pipeline is above 45 % busy)
+  int tmem_cols;       // 512 or 256
   int epi_tile_split;  // 1: epilogue warp group g handles the tiles whose accumulator is g (all columns); 0: both
                        // groups work on every tile and split its columns (few tiles per CTA)
   int rowshift;    // 1: one A stage holds Ht + KH - 1 image rows; the KH taps of a column read it at row offsets
@@ -285,7 +290,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&p.tmA);
     ptx::prefetch_tmap(&p.tmB);
-    if (!(p.mode == MODE_DETECT && p.det_decode == 2)) ptx::prefetch_tmap(&p.tmO);
+    ptx::prefetch_tmap(&p.tmO);
     if (p.out2x && p.up_tma) ptx::prefetch_tmap(&p.tmU);
     for (int s = 0; s < p.stages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
@@ -293,13 +298,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     }
     for (int a = 0; a < p.n_acc; ++a) {
       ptx::mbar_init(&tmem_full[a], 1);
-      ptx::mbar_init(&tmem_empty[a], p.epi_tile_split ? 128 : EPI_WARPS * 32);
+      ptx::mbar_init(&tmem_empty[a], (p.epi_tile_split || p.epi_warps == 4) ? 128 : EPI_WARPS * 32);
     }
     ptx::mbar_init(&wres_bar, 1);
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(&tmem_base_smem, 512);
+    ptx::tmem_alloc(&tmem_base_smem, (uint32_t)p.tmem_cols);
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
@@ -487,15 +492,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     uint8_t* stage = smem + (size_t)p.stages * stage_bytes + (size_t)e * (2 * p.epi_stage_bytes);
     int sbuf = 0;
     int it = 0;
-    const int col_first = p.epi_tile_split ? 0 : half * 32;  // first 32-column chunk of this warp
-    const int col_step = p.epi_tile_split ? 32 : 64;
+    const bool one_group = p.epi_warps == 4;                              // a single epilogue group takes every tile, every column
+    const int col_first = (p.epi_tile_split || one_group) ? 0 : half * 32;  // first 32-column chunk of this warp
+    const int col_step = (p.epi_tile_split || one_group) ? 32 : 64;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int acc = it & (p.n_acc - 1);
-      if (p.epi_tile_split && (it & 1) != half) continue;  // the other warp group owns this tile
+      if (p.epi_tile_split && !one_group && (it & 1) != half) continue;  // the other warp group owns this tile
       const TileCoord c = decode_tile(p, t);
       const uint32_t acc_ph = (uint32_t)(it >> p.acc_shift) & 1u;
 
-      const bool ts_on = leader && (e & 3) == 0 && (p.epi_tile_split || e == 0);
+      const bool ts_on = leader && (e & 3) == 0 && (p.epi_tile_split || one_group || e == 0);
       if (ts_on) Y5_TS(2, it, 0);
       ptx::mbar_wait(&tmem_full[acc], acc_ph);
       ptx::tc_fence_after();
@@ -557,9 +563,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         // rec_w floats = (cx, cy, w, h, obj, cls[nc], theta index) - everything non_max_suppression_obb reads of a row
         // (utils/general.py:781-832).  Same sigmoid and decode arithmetic as the full-tensor mode below; the theta index is
         // the first maximum over the 180 sigmoid values, as torch.max returns it (:822).  Every warp owns whole tiles here.
+        // The warp's 32 records are staged densely ([32][rec_w] fp32) and leave through ONE TMA store whose tensor map views
+        // the record buffer as (rec_w, W, H, anchor, image).
         const int a = c.nt;
         const int nfix = p.det_no - 180;                    // 5 + nc leading columns
-        float* rec = p.det_out + ((long long)c.b * p.det_rows_per_image + p.det_row_off + ((long long)a * p.Hout + h) * p.Wout + w) * p.det_rec_w;
+        if (leader) ptx::tma_store_wait_read<1>();
+        __syncwarp();
+        float* rec = reinterpret_cast<float*>(stage + sbuf * p.epi_stage_bytes) + lane * p.det_rec_w;
         float best = -INFINITY;
         int bk = 0;
         for (int c0 = 0; c0 < p.det_no; c0 += 32) {
@@ -584,13 +594,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
               v[3] = (v[3] * 2.0f) * (v[3] * 2.0f) * p.det_anchor[2 * a + 1];
             }
             if (col + 3 < nfix) {
-              if (valid) *reinterpret_cast<float4*>(rec + col) = make_float4(v[0], v[1], v[2], v[3]);
+              *reinterpret_cast<float4*>(rec + col) = make_float4(v[0], v[1], v[2], v[3]);
             } else {
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const int cc = col + k;
                 if (cc < nfix) {
-                  if (valid) rec[cc] = v[k];
+                  rec[cc] = v[k];
                 } else if (cc < p.det_no && v[k] > best) {
                   best = v[k];
                   bk = cc - nfix;
@@ -599,7 +609,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             }
           }
         }
-        if (valid) rec[nfix] = (float)bk;
+        rec[nfix] = (float)bk;
+        for (int cc = nfix + 1; cc < p.det_rec_w; ++cc) rec[cc] = 0.0f;  // padding columns
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (leader) {  // rows beyond the image are clipped by the tensor map
+          ptx::tma_store_5d(&p.tmO, stage + sbuf * p.epi_stage_bytes, 0, c.w0 + box_w0, hsub + box_h0, a, c.b);
+          ptx::tma_store_commit();
+        }
+        sbuf ^= 1;
       } else {
         // Detect: N tile nt == anchor nt; columns [0, det_no) are that anchor's outputs.
         // out row = b * rows_per_image + row_off + (a * H + h) * W + w   (models/yolo.py:65,81): the tensor map
@@ -657,7 +675,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
   __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, 512);
+    ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
 }
 
@@ -688,6 +706,7 @@ CUtensorMapSwizzle swizzle_for(int bk) {
 struct ConvObj {
   ConvK k;
   int grid;
+  int threads;
   size_t smem;
   double flops;      // algorithmic 2*MACs
   double hbm_bytes;  // algorithmic in + out (+ residual) bytes
@@ -783,7 +802,12 @@ int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
   int a_rows = 0;
   size_t stage_bytes = 0;
   k.epi_stage_bytes = d->mode == MODE_DETECT ? EPI_STAGE_DET : EPI_STAGE_CONV;
-  const size_t SMEM_BUDGET = (size_t)SMEM_TOTAL - 1024 - (size_t)EPI_WARPS * 2 * k.epi_stage_bytes;  // operand ring (+ resident weights)
+  const int det_rec_w = ((d->det_no - 180 + 1) + 3) / 4 * 4;  // compact record: (5 + nc + 1) floats rounded up to 4
+  if (d->mode == MODE_DETECT && d->det_decode == 2)
+    k.epi_stage_bytes = std::max<uint32_t>(EPI_STAGE_DET, (uint32_t)align_up((size_t)32 * det_rec_w * 4, 128));
+  // operand ring (+ resident weights): everything but the epilogue staging; `dual` = two CTAs per SM, each with half of it
+  size_t SMEM_BUDGET = (size_t)SMEM_TOTAL - 1024 - (size_t)EPI_WARPS * 2 * k.epi_stage_bytes;
+  const size_t BUDGET_ONE = SMEM_BUDGET, BUDGET_DUAL = (size_t)DUAL_SMEM - 1024 - (size_t)4 * 2 * k.epi_stage_bytes;
   // Row-shift mode (stride-1 convs with KH > 1): an 8 x 16 pixel tile whose A stage holds Ht + KH - 1 image
   // rows; the KH vertical taps read the same stage at row offsets that are whole 8-row swizzle groups, so each
   // input row crosses L2 -> shared memory (Ht + KH - 1) / Ht times per kw instead of KH times.  Taken when the
@@ -844,18 +868,47 @@ int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
   const bool want_rowshift = d->stride == 1 && d->KH > 1 && Wout >= 8 && !(d->flags & Y5OBB_CONV_NO_ROWSHIFT);
   const int sub_cols = bn <= 32 ? 32 : (bn <= 64 ? 64 : (bn <= 128 ? 128 : 256));
   {
-    // largest m_sub whose two accumulator stages fit the 512 TMEM columns, that keeps every SM busy, adds no edge waste along
-    // H and still leaves a 3-deep operand ring; Y5OBB_CONV_MSUB1 / the environment variable Y5OBB_MSUB_MAX cap it (A-B runs)
+    // Configuration search.  dual (two CTAs per SM: 256 TMEM columns and half the shared memory each, 4 epilogue warps) is
+    // preferred whenever a 3-deep ring fits: its two pipelines hide each other's hand-shake latencies.  Within a configuration
+    // the largest m_sub whose accumulator stages fit the TMEM columns (two stages; one is enough in dual mode, where the other
+    // CTA overlaps the epilogue), that keeps every SM busy and adds no edge waste along H.  Y5OBB_CONV_MSUB1 / Y5OBB_CONV_NO_DUAL
+    // and the environment variables Y5OBB_MSUB_MAX / Y5OBB_DUAL (0 / 1) pin the choice for A-B runs.
     int m_max = 4;
     if (d->flags & Y5OBB_CONV_MSUB1) m_max = 1;
     if (const char* e = getenv("Y5OBB_MSUB_MAX")) m_max = std::max(1, std::min(4, atoi(e)));
+    int dual_ok = (d->flags & Y5OBB_CONV_NO_DUAL) ? 0 : 1;
+    if (const char* e = getenv("Y5OBB_DUAL")) dual_ok = atoi(e) ? 1 : 0;
+    if (dual_ok) {  // the two CTAs must really fit together (registers: 192 threads x the kernel's count)
+      static int dual_fits = -1;
+      if (dual_fits < 0) {
+        int nb = 0;
+        cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+        cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, conv_tc_kernel, 64 + 4 * 32, DUAL_SMEM) != cudaSuccess) {
+          (void)cudaGetLastError();
+          nb = 0;
+        }
+        dual_fits = nb >= 2 ? 1 : 0;
+      }
+      dual_ok = dual_fits;
+    }
     bool ok = false;
-    for (int m = 4; m >= 1 && !ok; m >>= 1) {
-      if (m > m_max || m * sub_cols * 2 > 512) continue;
-      for (int rs = want_rowshift ? 1 : 0; rs >= 0 && !ok; --rs) {
-        if (!plan(rs == 1, m)) continue;
-        const bool enough = m == 1 || ((long long)k.n_tiles_m * nt >= sm_count() && Hout % (k.Ht * m) == 0 && k.stages >= 3);
-        ok = enough;
+    for (int dual = dual_ok; dual >= 0 && !ok; --dual) {
+      SMEM_BUDGET = dual ? BUDGET_DUAL : BUDGET_ONE;
+      const int cols = dual ? 256 : 512;
+      for (int m = 4; m >= 1 && !ok; m >>= 1) {
+        if (m > m_max || m * sub_cols * (dual ? 1 : 2) > cols) continue;
+        for (int rs = want_rowshift ? 1 : 0; rs >= 0 && !ok; --rs) {
+          if (!plan(rs == 1, m)) continue;
+          const long long tiles = (long long)k.n_tiles_m * nt;
+          const bool busy = tiles >= (long long)sm_count() * (dual ? 2 : 1);
+          const bool enough = (m == 1 && !dual) || (busy && Hout % (k.Ht * m) == 0 && k.stages >= 3);
+          ok = enough;
+          if (ok) {
+            k.epi_warps = dual ? 4 : 8;
+            k.tmem_cols = cols;
+          }
+        }
       }
     }
     if (!ok) {
@@ -867,7 +920,7 @@ int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
   k.sub_cols = sub_cols;
   k.acc_stride = sub_cols * k.m_sub;
   k.a_sub16 = (uint32_t)(BM * bk * 2) >> 4;
-  k.n_acc = std::min(MAX_ACC, 512 / k.acc_stride);
+  k.n_acc = std::min(MAX_ACC, k.tmem_cols / k.acc_stride);
   if (d->flags & Y5OBB_CONV_ACC2) k.n_acc = 2;
   k.acc_shift = 0;
   while ((1 << k.acc_shift) < k.n_acc) ++k.acc_shift;
@@ -986,9 +1039,23 @@ int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
                      CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r == CUDA_SUCCESS && !(d->flags & Y5OBB_CONV_NO_UP_TMA)) k.up_tma = 1;
   }
-  if (d->mode == MODE_DETECT && d->det_decode == 2 && (reinterpret_cast<uintptr_t>(d->det_out) & 15)) {
-    delete o;
-    return Y5OBB_EINVAL;
+  if (d->mode == MODE_DETECT && d->det_decode == 2) {  // records as (rec_w, W, H, anchor, image) fp32; a warp stores 32 records
+    const int bw = std::min(k.Wt, 32);
+    const cuuint64_t rowb = (cuuint64_t)det_rec_w * 4;
+    cuuint64_t dims[5] = {(cuuint64_t)det_rec_w, (cuuint64_t)Wout, (cuuint64_t)Hout, (cuuint64_t)nt, (cuuint64_t)d->B};
+    cuuint64_t strides[4] = {rowb, rowb * Wout, rowb * Wout * Hout, rowb * (cuuint64_t)d->det_rows_per_image};
+    cuuint32_t box[5] = {(cuuint32_t)det_rec_w, (cuuint32_t)bw, (cuuint32_t)(32 / bw), 1, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    float* base = d->det_out + (size_t)d->det_row_off * det_rec_w;
+    CUresult r = (reinterpret_cast<uintptr_t>(base) & 15)
+                     ? CUDA_ERROR_INVALID_VALUE
+                     : enc(&k.tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      g_last_cuda_error = (int)r;
+      delete o;
+      return Y5OBB_ECUDA;
+    }
   }
   if (d->mode == MODE_DETECT && d->det_decode != 2) {  // output rows as (no, W, H, anchor, image) fp32; each warp stores 32 pixels x 32 floats
     const int bw = std::min(k.Wt, 32);
@@ -1012,14 +1079,19 @@ int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
     }
   }
   const int total = k.n_tiles_m * k.n_tiles_n;
-  o->grid = std::min(total, sm_count());
+  o->grid = std::min(total, sm_count() * (k.epi_warps == 4 ? 2 : 1));
+  o->threads = 64 + 32 * k.epi_warps;
   // many tiles per CTA: the two epilogue groups alternate tiles (two epilogues in flight, any BN);
   // few tiles per CTA: they split the columns of each tile (shortest single-tile latency)
-  k.epi_tile_split = (total >= 4 * o->grid) ? 1 : 0;
-  if (d->mode == MODE_DETECT && d->det_decode == 2) k.epi_tile_split = 1;  // a record is assembled by one thread over all columns
+  k.epi_tile_split = (total >= 4 * o->grid && k.epi_warps == 8) ? 1 : 0;
+  if (d->mode == MODE_DETECT && d->det_decode == 2 && k.epi_warps == 8) k.epi_tile_split = 1;  // a record is assembled by one thread over all columns
   // >= 116 KB so that two CTAs (each owning all 512 TMEM columns) can never share an SM
-  o->smem = std::max<size_t>(k.b_res_bytes + (size_t)k.stages * stage_bytes + EPI_WARPS * 2 * k.epi_stage_bytes + 1024,
-                             116 * 1024);
+  o->smem = k.b_res_bytes + (size_t)k.stages * stage_bytes + (size_t)k.epi_warps * 2 * k.epi_stage_bytes + 1024;
+  if (k.epi_warps == 8) o->smem = std::max<size_t>(o->smem, 116 * 1024);
+  else if (o->smem > (size_t)DUAL_SMEM) {
+    delete o;
+    return Y5OBB_EINVAL;
+  }
   o->flops = 2.0 * d->B * Hout * Wout * (double)d->Cout * d->Cin * d->KH * d->KW;
   o->hbm_bytes = 2.0 * d->B * ((double)d->Hin * d->Win * (d->hbm_cin ? d->hbm_cin : d->Cin) + (double)Hout * Wout * d->Cout * (d->res ? 2 : 1));
   static bool attr_set = false;
@@ -1042,7 +1114,7 @@ int y5obb_conv_run(const y5obb_conv_t* conv, void* stream) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)o->grid);
-    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.blockDim = dim3((unsigned)o->threads);
     cfg.dynamicSmemBytes = o->smem;
     cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute at[1];
@@ -1054,7 +1126,7 @@ int y5obb_conv_run(const y5obb_conv_t* conv, void* stream) {
     if (e != cudaSuccess) return cuda_fail(e);
     return Y5OBB_OK;
   }
-  conv_tc_kernel<<<o->grid, NUM_THREADS, o->smem, (cudaStream_t)stream>>>(o->k);
+  conv_tc_kernel<<<o->grid, o->threads, o->smem, (cudaStream_t)stream>>>(o->k);
   Y5_LAUNCH_CHECK();
   return Y5OBB_OK;
 }

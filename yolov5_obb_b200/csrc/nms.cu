@@ -676,6 +676,96 @@ __global__ void k_pp_emit(PPArgs a, const int* __restrict__ cnt, const int* __re
   }
 }
 
+// ---- compact records (Y5OBB_NMS_COMPACT_PRED): one THREAD per anchor row.  A row is 96 B and almost every row fails the
+// objectness test on its first read, so a warp per row (the layout the 800-byte tensor rows want) would only schedule warps.
+// Same arithmetic, same candidate order (ascending class inside a row) as k_pp_count / k_pp_emit above.
+__global__ void k_pp_count_rec(PPArgs a, int* __restrict__ cnt) {
+  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= a.rows) return;
+  const float* p = a.pred + row * a.row_w;
+  const float obj = p[4];
+  int n = 0;
+  if (obj > a.conf) {
+    if (a.multi_label) {
+      for (int j = 0; j < a.nc; ++j)
+        n += ((__fmul_rn(p[5 + j], obj) > a.conf) && ((a.class_mask >> (j & 63)) & 1ull)) ? 1 : 0;
+    } else {
+      float bv = -INFINITY;
+      int bj = 0x7fffffff;
+      for (int j = 0; j < a.nc; ++j) {
+        const float v = __fmul_rn(p[5 + j], obj);
+        if (v > bv) {
+          bv = v;
+          bj = j;
+        }
+      }
+      n = (bv > a.conf && bj < a.nc && ((a.class_mask >> (bj & 63)) & 1ull)) ? 1 : 0;
+    }
+  }
+  cnt[row] = n;
+}
+
+__global__ void k_pp_emit_rec(PPArgs a, const int* __restrict__ cnt, const int* __restrict__ off, long long capacity,
+                              float* __restrict__ dets5, float* __restrict__ scores, int32_t* __restrict__ image_ids,
+                              float* __restrict__ out7, int64_t* __restrict__ n_valid) {
+  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= a.rows) return;
+  if (row == 0) {
+    const long long total = (long long)off[a.rows - 1] + cnt[a.rows - 1];
+    n_valid[0] = total < capacity ? total : capacity;
+    n_valid[1] = total;
+  }
+  if (cnt[row] == 0) return;
+  const float* p = a.pred + row * a.row_w;
+  const float obj = p[4];
+  int bk = (int)p[5 + a.nc];
+  if (bk > 179 || bk < 0) bk = 0;
+  const float theta = __fmul_rn(__fdiv_rn((float)(bk - 90), 180.0f), 3.141592f);
+  const float cx = p[0], cy = p[1], w = p[2], h = p[3];
+  const int img = (int)(row / a.A);
+  long long slot = off[row];
+  if (a.far_flag && !(0.5f * sqrtf(w * w + h * h) + fmaxf(fabsf(cx), fabsf(cy)) < 0.5f * a.max_wh - 8.0f)) atomicOr(a.far_flag, 1);
+  auto put = [&](int cls, float sc) {
+    if (slot < capacity) {
+      const float c = a.agnostic ? 0.0f : __fmul_rn((float)cls, a.max_wh);
+      float* d = dets5 + slot * 5;
+      d[0] = __fadd_rn(cx, c);
+      d[1] = __fadd_rn(cy, c);
+      d[2] = w;
+      d[3] = h;
+      d[4] = theta;
+      scores[slot] = sc;
+      image_ids[slot] = img;
+      float* o = out7 + slot * 7;
+      o[0] = cx;
+      o[1] = cy;
+      o[2] = w;
+      o[3] = h;
+      o[4] = theta;
+      o[5] = sc;
+      o[6] = (float)cls;
+    }
+    ++slot;
+  };
+  if (a.multi_label) {
+    for (int j = 0; j < a.nc; ++j) {
+      const float sc = __fmul_rn(p[5 + j], obj);
+      if ((sc > a.conf) && ((a.class_mask >> (j & 63)) & 1ull)) put(j, sc);
+    }
+  } else {
+    float cv = -INFINITY;
+    int cj = 0x7fffffff;
+    for (int j = 0; j < a.nc; ++j) {
+      const float v = __fmul_rn(p[5 + j], obj);
+      if (v > cv) {
+        cv = v;
+        cj = j;
+      }
+    }
+    put(cj, cv);
+  }
+}
+
 __global__ void k_pp_gather(const float* __restrict__ out7, const int64_t* __restrict__ keep,
                             const int64_t* __restrict__ n_keep, const int64_t* __restrict__ seg_off, int n_images,
                             int max_det, float* __restrict__ dst, int64_t* __restrict__ counts,
@@ -985,11 +1075,16 @@ int y5obb_nms_obb_f32(const float* pred, int64_t batch, int64_t anchors, int no,
   a.far_flag = split ? w.far_flag : nullptr;
   if (split) Y5_CUDA(cudaMemsetAsync(w.far_flag, 0, sizeof(int), st));
   const unsigned g = (unsigned)((rows * 32 + 255) / 256);
-  k_pp_count<<<g, 256, 0, st>>>(a, w.cnt);
+  const unsigned g1 = (unsigned)((rows + 255) / 256);
+  if (a.compact) k_pp_count_rec<<<g1, 256, 0, st>>>(a, w.cnt);
+  else k_pp_count<<<g, 256, 0, st>>>(a, w.cnt);
   Y5_LAUNCH_CHECK();
   size_t sb = w.scan_bytes;
   Y5_CUDA(cub::DeviceScan::ExclusiveSum(w.scan_tmp, sb, w.cnt, w.off, (int)rows, st));
-  k_pp_emit<<<g, 256, 0, st>>>(a, w.cnt, w.off, max_candidates, w.dets5, w.scores, w.image_ids, w.out7, w.n_valid);
+  if (a.compact)
+    k_pp_emit_rec<<<g1, 256, 0, st>>>(a, w.cnt, w.off, max_candidates, w.dets5, w.scores, w.image_ids, w.out7, w.n_valid);
+  else
+    k_pp_emit<<<g, 256, 0, st>>>(a, w.cnt, w.off, max_candidates, w.dets5, w.scores, w.image_ids, w.out7, w.n_valid);
   Y5_LAUNCH_CHECK();
   long long mpi = max_nms > 0 && max_nms < max_candidates ? max_nms : max_candidates;
   int rc;

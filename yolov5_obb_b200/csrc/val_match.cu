@@ -6,7 +6,9 @@
 //       correct[d, :] = iou >= iouv for the surviving pairs.
 // The reference runs ~40 small ATen kernels, two host round trips (numpy argsort / unique) and a Python loop per image.
 // Every arithmetic step below is a separately rounded fp32 op in the reference's order (no FMA contraction), so the boxes
-// are bit-identical to the ATen chain and the IoUs decide the same thresholds.  Ties (two labels with exactly the same IoU for
+// are bit-identical to the ATen chain ON A GPU (where val.py runs it) and the IoUs decide the same thresholds.  One ATen
+// detail matters for that: a CUDA tensor divided by a Python scalar is multiplied by the scalar's fp32 reciprocal
+// (BinaryDivTrueKernel.cu), so `/= gain` below is `* (1.0f / gain)`; divisions by 2 are exact either way.  Ties (two labels with exactly the same IoU for
 // one detection) go to the lower label index; the reference's numpy quicksort leaves them unspecified.
 // HBM-bound: 28 B read + (niou + 48) B written per detection; the label list of an image lives in shared memory.
 #include "common.cuh"
@@ -69,6 +71,7 @@ __global__ void __launch_bounds__(VM_THREADS) k_val_match(VmArgs a) {
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const float gain = a.scale[b * 5 + 0], pad_x = a.scale[b * 5 + 1], pad_y = a.scale[b * 5 + 2];
   const float raw_h = a.scale[b * 5 + 3], raw_w = a.scale[b * 5 + 4];
+  const float inv_gain = __fdiv_rn(1.0f, gain);
   if (tid == 0) s_n = 0;
   __syncthreads();
   // ---- labels of image b, in their order of appearance (val.py:214 `targets[targets[:, 0] == si, 1:7]`)
@@ -87,10 +90,10 @@ __global__ void __launch_bounds__(VM_THREADS) k_val_match(VmArgs a) {
       rbox_to_poly(L[2], L[3], L[4], L[5], L[6], poly);   // tpoly = rbox2poly(labels[:, 1:6])
       poly_to_xyxy(poly, box);                            // tbox = xywh2xyxy(poly2hbb(tpoly))
       // scale_coords (utils/general.py:621-634): subtract the padding, divide by the gain, clip to the raw image
-      box[0] = __fdiv_rn(__fsub_rn(box[0], pad_x), gain);
-      box[2] = __fdiv_rn(__fsub_rn(box[2], pad_x), gain);
-      box[1] = __fdiv_rn(__fsub_rn(box[1], pad_y), gain);
-      box[3] = __fdiv_rn(__fsub_rn(box[3], pad_y), gain);
+      box[0] = __fmul_rn(__fsub_rn(box[0], pad_x), inv_gain);
+      box[2] = __fmul_rn(__fsub_rn(box[2], pad_x), inv_gain);
+      box[1] = __fmul_rn(__fsub_rn(box[1], pad_y), inv_gain);
+      box[3] = __fmul_rn(__fsub_rn(box[3], pad_y), inv_gain);
       box[0] = fminf(fmaxf(box[0], 0.f), raw_w);
       box[2] = fminf(fmaxf(box[2], 0.f), raw_w);
       box[1] = fminf(fmaxf(box[1], 0.f), raw_h);
@@ -127,8 +130,8 @@ __global__ void __launch_bounds__(VM_THREADS) k_val_match(VmArgs a) {
       rbox_to_poly(P[0], P[1], P[2], P[3], P[4], poly);
 #pragma unroll
       for (int k = 0; k < 8; k += 2) {  // scale_polys (utils/general.py:636-650), no clipping
-        poly[k] = __fdiv_rn(__fsub_rn(poly[k], pad_x), gain);
-        poly[k + 1] = __fdiv_rn(__fsub_rn(poly[k + 1], pad_y), gain);
+        poly[k] = __fmul_rn(__fsub_rn(poly[k], pad_x), inv_gain);
+        poly[k + 1] = __fmul_rn(__fsub_rn(poly[k + 1], pad_y), inv_gain);
       }
       poly_to_xyxy(poly, box);
       if (a.polyn) {
@@ -172,8 +175,8 @@ __global__ void __launch_bounds__(VM_THREADS) k_val_match(VmArgs a) {
       rbox_to_poly(P[0], P[1], P[2], P[3], P[4], poly);
 #pragma unroll
       for (int k = 0; k < 8; k += 2) {
-        poly[k] = __fdiv_rn(__fsub_rn(poly[k], pad_x), gain);
-        poly[k + 1] = __fdiv_rn(__fsub_rn(poly[k + 1], pad_y), gain);
+        poly[k] = __fmul_rn(__fsub_rn(poly[k], pad_x), inv_gain);
+        poly[k + 1] = __fmul_rn(__fsub_rn(poly[k + 1], pad_y), inv_gain);
       }
       poly_to_xyxy(poly, box);
       const float area_d = __fmul_rn(__fsub_rn(box[2], box[0]), __fsub_rn(box[3], box[1]));

@@ -113,7 +113,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
   const int per_img = p.tiles_h * p.tiles_w;
 
   if (warp == 0) {
-    if (lane == 0) {
+    // elect.sync, not `lane == 0`: ptxas then issues UTMALDG / UTCHMMA straight from uniform registers instead of wrapping each
+    // one in a per-lane serialisation loop (see conv_sm100.cu)
+    if (ptx::elect_one()) {
       int s = 0;
       uint32_t ph = 0;
       const uint32_t tx = (uint32_t)p.PB * (uint32_t)(a_chunks + ntap * p.b_chunks) * WG_CHUNK;
@@ -150,7 +152,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       int s = 0;
       uint32_t ph = 0;
       const uint64_t desc_hi = make_mnmajor_desc(0u, WG_CHUNK);
