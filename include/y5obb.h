@@ -167,6 +167,10 @@ void y5obb_conv_destroy(y5obb_conv_t* conv);
 /* Profiling aid: CTA 0 of every later run writes clock64() stamps of its producer / MMA / epilogue roles for its first 32
  * tiles into dev_buf ([3][32][8] uint64, device memory; NULL switches it off).  Results are unaffected. */
 int y5obb_conv_debug_timestamps(y5obb_conv_t* conv, unsigned long long* dev_buf);
+/* Profiling aid: resident CTAs per SM the runtime grants the one-CTA (dual = 0, 320 threads) or two-CTA (dual = 1, 192 threads)
+ * instantiation of the kernel for a given dynamic shared-memory size, with its register count and static shared memory. */
+int y5obb_conv_debug_occupancy(int dual, int threads, size_t dyn_smem, int* blocks_per_sm, int* regs, int* static_smem);
+int y5obb_wgrad_debug_occupancy(size_t dyn_smem, int* blocks_per_sm, int* regs);
 
 /* ---- HBM-bound helpers around the conv stack -------------------------------------------------
  * y5obb_stem_s2d: NCHW fp32 image [B,3,H,W] -> 2x2 space-to-depth NHWC bf16 [B,H/2,W/2,16] (channel

@@ -40,7 +40,7 @@ constexpr int NUM_THREADS = 320;          // TMA producer, MMA issuer, 8 epilogu
 constexpr int EPI_WARPS = 8;              // ... or 4 epilogue warps (192 threads) when two CTAs share an SM, see ConvK::epi_warps
 constexpr int EPI_STAGE_CONV = 32 * 64;    // 32 pixels x 32 bf16 channels, 64-byte swizzled
 constexpr int EPI_STAGE_DET = 32 * 128;    // 32 pixels x 32 fp32 outputs, 128-byte swizzled
-constexpr int DUAL_SMEM = 112 * 1024;     // per CTA when two share an SM (228 KB per SM, 1 KB reserved per CTA)
+constexpr int DUAL_SMEM = 110 * 1024;     // per CTA when two share an SM (228 KB per SM, 1 KB reserved per CTA)
 constexpr int SMEM_TOTAL = 224 * 1024;    // dynamic shared memory we ask for at most (227 KB is the hardware cap)
 
 enum Mode : int { MODE_CONV = 0, MODE_DETECT = 1 };
@@ -267,7 +267,11 @@ __device__ __forceinline__ void conv_epi_tile(const EpiTile& e, int& sbuf) {
   }
 }
 
-__global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvK p) {
+// DUAL = false: 320 threads, one CTA per SM.  DUAL = true: launched with 192 threads (producer, MMA issuer, four epilogue
+// warps), two CTAs per SM: 6 warps are allocated as 8, so 2 x 8 x 32 x 120 registers = 61 440 of the SM's 65 536 (at 128
+// registers the runtime grants one CTA only, profiles/r2_occupancy.txt).
+template <bool DUAL>
+__global__ void __launch_bounds__(DUAL ? 192 : NUM_THREADS) __maxnreg__(DUAL ? 120 : 168) conv_tc_kernel(const __grid_constant__ ConvK p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
@@ -876,15 +880,27 @@ int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
     int m_max = 4;
     if (d->flags & Y5OBB_CONV_MSUB1) m_max = 1;
     if (const char* e = getenv("Y5OBB_MSUB_MAX")) m_max = std::max(1, std::min(4, atoi(e)));
-    int dual_ok = (d->flags & Y5OBB_CONV_NO_DUAL) ? 0 : 1;
-    if (const char* e = getenv("Y5OBB_DUAL")) dual_ok = atoi(e) ? 1 : 0;
-    if (dual_ok) {  // the two CTAs must really fit together (registers: 192 threads x the kernel's count)
+    // MEASURED NEGATIVE (profiles/r2_occupancy.txt, r2_dual_experiment.txt): the runtime grants ONE resident CTA per SM to these
+    // kernels whatever their register / shared-memory footprint (even wgrad_kernel: 47 registers, 60 KB), so the dual
+    // configuration only runs as two waves of half-sized CTAs and loses 5-30 % on most layers.  It stays off unless
+    // Y5OBB_DUAL is set (1: if the occupancy query grants two CTAs; 2: unconditionally), and is kept for the A-B record.
+    int dual_ok = 0;
+    int dual_force = 0;
+    if (const char* e = getenv("Y5OBB_DUAL")) {
+      dual_ok = atoi(e) ? 1 : 0;
+      dual_force = atoi(e) == 2;  // 2: skip the runtime's occupancy answer (experiment)
+    }
+    if (dual_ok && dual_force) {
+      cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DUAL_SMEM);
+      cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    }
+    if (dual_ok && !dual_force) {  // the two CTAs must really fit together (registers: 192 threads x the kernel's count)
       static int dual_fits = -1;
       if (dual_fits < 0) {
         int nb = 0;
-        cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
-        cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, conv_tc_kernel, 64 + 4 * 32, DUAL_SMEM) != cudaSuccess) {
+        cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DUAL_SMEM);
+        cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, conv_tc_kernel<true>, 64 + 4 * 32, DUAL_SMEM) != cudaSuccess) {
           (void)cudaGetLastError();
           nb = 0;
         }
@@ -1096,7 +1112,7 @@ int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
   o->hbm_bytes = 2.0 * d->B * ((double)d->Hin * d->Win * (d->hbm_cin ? d->hbm_cin : d->Cin) + (double)Hout * Wout * d->Cout * (d->res ? 2 : 1));
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
     if (e != cudaSuccess) {
       delete o;
       return cuda_fail(e);
@@ -1122,11 +1138,13 @@ int y5obb_conv_run(const y5obb_conv_t* conv, void* stream) {
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel, o->k);
+    cudaError_t e = o->k.epi_warps == 4 ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true>, o->k)
+                                        : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false>, o->k);
     if (e != cudaSuccess) return cuda_fail(e);
     return Y5OBB_OK;
   }
-  conv_tc_kernel<<<o->grid, o->threads, o->smem, (cudaStream_t)stream>>>(o->k);
+  if (o->k.epi_warps == 4) conv_tc_kernel<true><<<o->grid, o->threads, o->smem, (cudaStream_t)stream>>>(o->k);
+  else conv_tc_kernel<false><<<o->grid, o->threads, o->smem, (cudaStream_t)stream>>>(o->k);
   Y5_LAUNCH_CHECK();
   return Y5OBB_OK;
 }
@@ -1145,6 +1163,26 @@ int y5obb_conv_info(const y5obb_conv_t* conv, double* flops, double* hbm_bytes, 
 }
 
 void y5obb_conv_destroy(y5obb_conv_t* conv) { delete reinterpret_cast<ConvObj*>(conv); }
+
+int y5obb_conv_debug_occupancy(int dual, int threads, size_t dyn_smem, int* blocks_per_sm, int* regs, int* static_smem) {
+  if (!blocks_per_sm || !regs || !static_smem) return Y5OBB_EINVAL;
+  cudaFuncAttributes fa;
+  cudaError_t e;
+  if (dual) {
+    cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DUAL_SMEM);
+    cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    e = cudaFuncGetAttributes(&fa, conv_tc_kernel<true>);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, conv_tc_kernel<true>, threads, dyn_smem);
+  } else {
+    cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+    e = cudaFuncGetAttributes(&fa, conv_tc_kernel<false>);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, conv_tc_kernel<false>, threads, dyn_smem);
+  }
+  if (e != cudaSuccess) return cuda_fail(e);
+  *regs = fa.numRegs;
+  *static_smem = (int)fa.sharedSizeBytes;
+  return Y5OBB_OK;
+}
 
 int y5obb_conv_debug_timestamps(y5obb_conv_t* conv, unsigned long long* dev_buf_768) {
   if (!conv) return Y5OBB_EINVAL;

@@ -25,6 +25,7 @@ namespace {
 constexpr int WG_THREADS = 192;
 constexpr int WG_MAX_STAGES = 8;
 constexpr int WG_SMEM = 200 * 1024;
+constexpr int WG_DUAL_SMEM = 110 * 1024;  // per CTA when two share an SM
 // a pixel block (= one TMA box per 64-channel chunk) has bk = 64, 128 or 256 pixels; a chunk is [bk pixels][128 B]
 
 struct WgradK {
@@ -363,10 +364,21 @@ int y5obb_wgrad_create(const y5obb_wgrad_desc* d, y5obb_wgrad_t** out) {
   k.stage_bytes = blk_bytes;
   k.stages = (int)std::min<size_t>(WG_MAX_STAGES, WG_SMEM / k.stage_bytes);
   k.steps = k.nblocks;
+  k.tmem_cols = 64;
+  while (k.tmem_cols < (uint32_t)(k.T * k.b_chunks * 64)) k.tmem_cols <<= 1;
+  // Two CTAs per SM (each <= 256 TMEM columns and <= 112 KB of shared memory) whenever a 3-deep ring still fits: the two
+  // producer / MMA / epilogue pipelines hide each other's hand-shake latencies (no unit of a single pipeline is above ~45 %
+  // busy, profiles/r2_conv_ncu_summary.txt).  Experimental: Y5OBB_WGRAD_DUAL=1 switches it on.
+  bool dual = k.tmem_cols <= 256 && 3 * (size_t)k.stage_bytes + 2048 <= WG_DUAL_SMEM;
+  {  // measured: no gain (the runtime keeps these kernels at one resident CTA per SM, profiles/r2_occupancy.txt): opt-in only
+    const char* e = getenv("Y5OBB_WGRAD_DUAL");
+    dual = dual && e && atoi(e) != 0;
+  }
+  if (dual) k.stages = (int)std::min<size_t>(WG_MAX_STAGES, (WG_DUAL_SMEM - 2048) / k.stage_bytes);
   const int items = k.ngroups * k.co_blks * k.ci_blks;
   {  // split-K: minimise (waves) x (steps per CTA + the fixed cost of a CTA: TMEM alloc, pipeline fill, fp32 atomic
      // epilogue - about 512 pixels' worth of pipeline steps); 1 CTA per SM
-    const int sms = sm_count();
+    const int sms = sm_count() * (dual ? 2 : 1);  // CTAs in flight
     const int fixed = std::max(1, 512 / k.bk);
     long long best_cost2 = -1;
     int bestk = 1;
@@ -381,8 +393,6 @@ int y5obb_wgrad_create(const y5obb_wgrad_desc* d, y5obb_wgrad_t** out) {
     k.ksplit = bestk;
   }
   k.idesc = ptx::make_idesc_bf16(128, 0) | (1u << 15) | (1u << 16);  // A and B MN-major; N is set per instruction
-  k.tmem_cols = 64;
-  while (k.tmem_cols < (uint32_t)(k.T * k.b_chunks * 64)) k.tmem_cols <<= 1;
   {
     cuuint64_t dims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)d->Wo, (cuuint64_t)d->Ho, (cuuint64_t)d->B};
     cuuint64_t strides[3] = {(cuuint64_t)d->dz_pix_stride * 2, (cuuint64_t)d->dz_pix_stride * d->Wo * 2,
@@ -416,11 +426,13 @@ int y5obb_wgrad_create(const y5obb_wgrad_desc* d, y5obb_wgrad_t** out) {
     }
   }
   o->grid = items * k.ksplit;
-  o->smem = std::max<size_t>((size_t)k.stages * k.stage_bytes + 1024, 116 * 1024);
+  o->smem = (size_t)k.stages * k.stage_bytes + 1024;
+  if (!dual) o->smem = std::max<size_t>(o->smem, 116 * 1024);  // one CTA per SM: it may own all 512 TMEM columns
   o->flops = 2.0 * d->B * d->Ho * d->Wo * (double)d->Cout * d->Cin * d->KH * d->KW;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM + 2048);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) {
       delete o;
       return cuda_fail(e);
@@ -436,6 +448,18 @@ int y5obb_wgrad_run(const y5obb_wgrad_t* w, void* stream) {
   const WgradObj* o = reinterpret_cast<const WgradObj*>(w);
   wgrad_kernel<<<o->grid, WG_THREADS, o->smem, (cudaStream_t)stream>>>(o->k);
   Y5_LAUNCH_CHECK();
+  return Y5OBB_OK;
+}
+
+int y5obb_wgrad_debug_occupancy(size_t dyn_smem, int* blocks_per_sm, int* regs) {
+  if (!blocks_per_sm || !regs) return Y5OBB_EINVAL;
+  cudaFuncAttributes fa;
+  cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM + 2048);
+  cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaError_t e = cudaFuncGetAttributes(&fa, wgrad_kernel);
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, wgrad_kernel, WG_THREADS, dyn_smem);
+  if (e != cudaSuccess) return cuda_fail(e);
+  *regs = fa.numRegs;
   return Y5OBB_OK;
 }
 
