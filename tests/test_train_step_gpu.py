@@ -143,3 +143,26 @@ def test_loss_trajectory_against_the_cpu_oracle():
         run_max = max(run_max, abs(emu[i] - ref[i]))      # the emulation's drift so far (running maximum: drift is not monotone)
         assert abs(dev[i] - ref[i]) < 3.0 * run_max + 0.02 * abs(ref[i]) + 1e-3, (i, dev[i], ref[i], emu[i])
     assert min(ref[-4:]) < ref[0] and min(dev[-4:]) < dev[0]
+
+
+def test_warmup_schedule_follows_train_py():
+    """train.py:305-316: during warm-up lr is interpolated from 0 (biases: from warmup_bias_lr = 0.1) to lr0 and the momentum
+    from 0.8 to 0.937.  At iteration 0 weights therefore do not move and biases take a 0.1-lr step; at `warmup_iters` the
+    groups sit at lr0 / 0.937.  The fused SGD kernel reads both from optimizer.param_groups every step."""
+    from yolov5_obb_b200.train_step import TrainStep, param_groups
+    m = build_mirror("n", nc=15, seed=1).train().to(DEV)
+    ts = TrainStep(m, batch_size=64, imgsz=128, warmup_iters=4)
+    imgs = synth_tiles(2, 128, seed=3).to(DEV)
+    tg = torch.from_numpy(synth_targets(2, 20, 128, nc=15, seed=3)).to(DEV)
+    g0, g1, g2 = param_groups(m)
+    w0 = [p.detach().clone() for p in g1[:5]]
+    b0 = [p.detach().clone() for p in g2]
+    ts.step(imgs, tg)
+    assert [g["lr"] for g in ts.optimizer.param_groups] == [0.0, 0.0, 0.1]
+    assert abs(ts.optimizer.param_groups[0]["momentum"] - 0.8) < 1e-12
+    assert all(torch.equal(p, q) for p, q in zip(g1[:5], w0))                   # lr 0: weights untouched
+    assert any(not torch.equal(p, q) for p, q in zip(g2, b0))                   # biases moved
+    for _ in range(4):
+        ts.step(imgs, tg)
+    lrs = [g["lr"] for g in ts.optimizer.param_groups]
+    assert all(abs(v - 0.01) < 1e-9 for v in lrs) and abs(ts.optimizer.param_groups[1]["momentum"] - 0.937) < 1e-9

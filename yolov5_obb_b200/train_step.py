@@ -75,7 +75,11 @@ class ModelEMA:
 class TrainStep:
     """model: yolov5_obb_b200.yolo.Model on a CUDA device, in train() mode.  step(imgs, targets) -> (loss, loss_items)."""
 
-    def __init__(self, model, hyp: Optional[dict] = None, batch_size: int = 16, imgsz: int = 1024, ema: bool = True):
+    def __init__(self, model, hyp: Optional[dict] = None, batch_size: int = 16, imgsz: int = 1024, ema: bool = True,
+                 warmup_iters: int = 0):
+        """warmup_iters > 0: the warm-up of train.py:305-316 over that many iterations (the reference uses
+        max(round(warmup_epochs * batches_per_epoch), 1000)): every group's lr is interpolated from 0 (biases: from
+        hyp['warmup_bias_lr']) to lr0 and the momentum from hyp['warmup_momentum'] to hyp['momentum']."""
         self.model = model
         self.hyp = dict(HYP_FINETUNE_DOTA if hyp is None else hyp)
         nbs = 64
@@ -105,6 +109,7 @@ class TrainStep:
         self.ema = ModelEMA(model) if ema else None
         self.compute_loss = ComputeLoss(model)
         self.ni = 0
+        self.warmup_iters = int(warmup_iters)
         self._last_opt = -1
         self.optimizer.zero_grad(set_to_none=True)
         # optimizer.step() + ema.update() as ONE kernel (csrc/sgd_ema.cu) whenever every batch ends with an
@@ -118,6 +123,13 @@ class TrainStep:
     def step(self, imgs: torch.Tensor, targets: torch.Tensor):
         """imgs: uint8 or float [B,3,H,W] on the device; targets [nt, 187] (image index, class, cx, cy, l, s, theta, CSL row)."""
         model = self.model
+        if self.ni <= self.warmup_iters and self.warmup_iters > 0:   # train.py:305-316 (np.interp on [0, nw]; lf(epoch 0) = 1)
+            f = self.ni / self.warmup_iters
+            for j, g in enumerate(self.optimizer.param_groups):
+                lo = self.hyp["warmup_bias_lr"] if j == 2 else 0.0
+                g["lr"] = lo + f * (self.hyp["lr0"] - lo)
+                if "momentum" in g:
+                    g["momentum"] = self.hyp["warmup_momentum"] + f * (self.hyp["momentum"] - self.hyp["warmup_momentum"])
         pred = model(imgs)                                  # uint8 is normalised inside the stem's loader kernel
         loss, items = self.compute_loss(pred, targets)
         loss.backward()                                     # (x WORLD_SIZE of train.py:328 is folded into the SUM below)
