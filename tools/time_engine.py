@@ -18,7 +18,8 @@ if os.environ.get("Y5OBB_TE_CALIBRATED") == "1":   # the benchmark's 'alive' mod
 else:
     m = build_mirror(size, nc=15, seed=0).cuda()
     x = None
-eng = InferenceEngine(m, B, S, S, torch.device("cuda:0"), conv_flags=int(os.environ.get("Y5OBB_CONV_FLAGS", "0")))
+eng = InferenceEngine(m, B, S, S, torch.device("cuda:0"), conv_flags=int(os.environ.get("Y5OBB_CONV_FLAGS", "0")),
+                      compact_detect=os.environ.get("Y5OBB_TE_RECORDS") == "1")   # 1: the bench's plan (Detect rows as compact records)
 if x is None:
     x = torch.rand(B, 3, S, S, device="cuda")
 for _ in range(3):

@@ -15,6 +15,7 @@
 //                 writes the compacted keep list in score order
 // Algorithmic bytes per box: 24 in (5 floats + score) + 8 out per kept box; the bit-matrix is
 // internal traffic (8 bytes per 64x64 tile row, upper triangle only).
+#include <cooperative_groups.h>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -366,6 +367,109 @@ k_reduce(const NmsSeg* __restrict__ seg, const NmsCtrl* __restrict__ ctrl,
   if (tid == 0) n_keep_out[b] = count;
 }
 
+// The same greedy scan by a CLUSTER of RC CTAs per image (large problems: the single CTA above spends its time pulling the
+// kept rows' mask words - up to gigabytes at 200 k boxes - through one SM).  CTA `rank` owns the words w with w % RC == rank of
+// the removed-set and resolves the 64-row blocks blk with blk % RC == rank: it publishes the block's kept bits in its shared
+// memory, ONE cluster barrier later every CTA reads them through distributed shared memory and ORs the kept rows' mask words
+// of ITS columns.  The word a block's owner needs next (remv[blk]) is its own, so one barrier per block suffices; a CTA's
+// publication slot is rewritten RC blocks (>= 2 barriers) later.  Same keep list, same order as k_reduce.
+constexpr int RC = 8;  // portable cluster size
+
+__global__ void __launch_bounds__(REDUCE_THREADS)
+k_reduce_cluster(const NmsSeg* __restrict__ seg, const NmsCtrl* __restrict__ ctrl, const unsigned long long* __restrict__ mask,
+                 const uint8_t* __restrict__ rowflag, const uint32_t* __restrict__ order, long long max_keep, int n_images,
+                 int64_t* __restrict__ keep_out, int64_t* __restrict__ n_keep_out, int64_t* __restrict__ seg_off_out,
+                 const PreBox* __restrict__ pre, int late_drop_small) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ unsigned long long remv[];  // this CTA's words: remv[w / RC] for w % RC == rank
+  __shared__ unsigned long long s_diag[TB];
+  __shared__ unsigned long long s_pub;          // kept bits of the block this CTA resolved last
+  __shared__ int s_orrows[TB];
+  __shared__ int s_nor;
+
+  const int tid = threadIdx.x;
+  const int rank = (int)cluster.block_rank();
+  const int b = blockIdx.x / RC;
+  const NmsSeg S = seg[b];
+  if (tid == 0 && rank == 0) {
+    seg_off_out[b] = S.off;
+    if (b == 0) seg_off_out[n_images] = seg[n_images].off;
+  }
+  if (ctrl->err) {  // uniform across the cluster: nobody reaches a barrier
+    if (tid == 0 && rank == 0) n_keep_out[b] = -1;
+    return;
+  }
+  const int my_words = (S.nblk - rank + RC - 1) / RC;
+  for (int i = tid; i < my_words; i += REDUCE_THREADS) remv[i] = 0ull;
+  if (tid == 0) s_nor = 0;
+  __syncthreads();
+  if (late_drop_small) {
+    for (int i = tid; i < S.n; i += REDUCE_THREADS) {
+      const int w = i >> 6;
+      if (w % RC != rank) continue;
+      const PreBox& q = pre[S.off + i];
+      if (fminf(q.w, q.h) < 0.001f) atomicOr(&remv[w / RC], 1ull << (i & 63));
+    }
+    __syncthreads();
+  }
+
+  long long count = 0;
+  const unsigned long long* M = mask + S.mask_off;
+  for (int blk = 0; blk < S.nblk; ++blk) {
+    const int owner = blk % RC;
+    const int rows = min(TB, S.n - blk * TB);
+    if (owner == rank) {  // resolve the diagonal chain of this block
+      if (tid < TB) s_diag[tid] = (tid < rows) ? M[(long long)(blk * TB + tid) * S.nblk + blk] : 0ull;
+      __syncthreads();
+      if (tid == 0) {
+        unsigned long long cur = remv[blk / RC], kept = 0ull;
+        if (rows < TB) cur |= ~0ull << rows;
+#pragma unroll
+        for (int i = 0; i < TB; ++i) {
+          const unsigned long long bit = 1ull << i;
+          if (!(cur & bit)) {
+            kept |= bit;
+            cur |= s_diag[i];
+          }
+        }
+        if (max_keep > 0) {
+          long long room = max_keep - count;
+          while ((long long)__popcll(kept) > room) kept &= ~(1ull << (63 - __clzll(kept)));
+        }
+        s_pub = kept;
+      }
+    }
+    cluster.sync();  // the owner's s_pub is visible cluster-wide
+    const unsigned long long kept = *cluster.map_shared_rank(&s_pub, owner);
+    if (tid < TB && ((kept >> tid) & 1ull)) {
+      const int srow = blk * TB + tid;
+      if (owner == rank) {
+        const long long pos = count + __popcll(kept & ((1ull << tid) - 1ull));
+        keep_out[S.off + pos] = (int64_t)order[S.off + srow];
+      }
+      if (rowflag[S.off + srow]) s_orrows[atomicAdd(&s_nor, 1)] = srow;
+    }
+    count += __popcll(kept);
+    __syncthreads();
+    const int nor = s_nor;
+    if (nor) {  // this CTA's columns beyond blk: w = rank, rank + RC, ... with w > blk
+      int w0 = blk + 1;
+      w0 += (rank - w0 % RC + RC) % RC;
+      for (int w = w0 + tid * RC; w < S.nblk; w += REDUCE_THREADS * RC) {
+        unsigned long long acc = 0ull;
+        for (int r = 0; r < nor; ++r) acc |= M[(long long)s_orrows[r] * S.nblk + w];
+        if (acc) remv[w / RC] |= acc;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) s_nor = 0;
+    if (max_keep > 0 && count >= max_keep) break;  // uniform: every CTA counts the same bits
+  }
+  cluster.sync();  // nobody exits while a peer may still read its s_pub
+  if (tid == 0 && rank == 0) n_keep_out[b] = count;
+}
+
 __global__ void k_zero_outputs(int n_images, int64_t* n_keep_out, int64_t* seg_off_out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_images) n_keep_out[i] = 0;
@@ -502,10 +606,32 @@ int nms_impl(const float* dets, const float* scores, const int32_t* image_ids, i
     Y5_CUDA(cudaFuncSetAttribute(k_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
     smem_set = 200 * 1024;
   }
-  k_reduce<<<(unsigned)n_images, REDUCE_THREADS, smem, st>>>(w.seg, w.ctrl, w.mask, w.rowflag, w.vals_b,
-                                                            (long long)max_keep, (int)n_images, keep_out, n_keep_out,
-                                                            seg_off_out, w.pre, late_drop);
-  Y5_LAUNCH_CHECK();
+  // >= 64 blocks of 64 boxes in an image: a cluster of RC CTAs shares the scan (env Y5OBB_NMS_NO_CLUSTER=1 keeps the single CTA)
+  static const bool no_cluster = [] { const char* e = getenv("Y5OBB_NMS_NO_CLUSTER"); return e && e[0] == '1'; }();
+  if (!no_cluster && (max_per_image + TB - 1) / TB >= 64) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)n_images * RC);
+    cfg.blockDim = dim3(REDUCE_THREADS);
+    cfg.dynamicSmemBytes = smem / RC + 64;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = RC;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    Y5_CUDA(cudaLaunchKernelEx(&cfg, k_reduce_cluster, (const NmsSeg*)w.seg, (const NmsCtrl*)w.ctrl,
+                               (const unsigned long long*)w.mask, (const uint8_t*)w.rowflag, (const uint32_t*)w.vals_b,
+                               (long long)max_keep, (int)n_images, keep_out, n_keep_out, seg_off_out, (const PreBox*)w.pre,
+                               late_drop));
+  } else {
+    k_reduce<<<(unsigned)n_images, REDUCE_THREADS, smem, st>>>(w.seg, w.ctrl, w.mask, w.rowflag, w.vals_b,
+                                                              (long long)max_keep, (int)n_images, keep_out, n_keep_out,
+                                                              seg_off_out, w.pre, late_drop);
+    Y5_LAUNCH_CHECK();
+  }
   stage_mark(st);
   return Y5OBB_OK;
 }
