@@ -48,7 +48,9 @@ const char* y5obb_build_info(void);     /* "sm_100a nvcc <ver> <date>" */
 
 #define Y5OBB_NMS_COMPACT_PRED 8     /* y5obb_nms_obb_f32 only: `pred` holds the Detect epilogue's compact records
                                        [batch, anchors, ((nc + 6) + 3) / 4 * 4] = (cx, cy, w, h, obj, cls[nc], theta index, pad)
-                                       instead of the [batch, anchors, no] tensor (y5obb_conv_desc.det_decode = 2) */
+                                       instead of the [batch, anchors, no] tensor (y5obb_conv_desc.det_decode = 2).  The theta
+                                       index is the first maximum of the 180 theta LOGITS (= torch.max over their sigmoids,
+                                       utils/general.py:822, whenever those are distinct) */
 
 /* Workspace needed for n_total boxes over n_images images with at most max_per_image boxes in any one
  * image (pass n_total if unknown). */

@@ -27,7 +27,9 @@ def val(r, k):
 
 data = rows[2:]
 t = [val(r, "us") for r in data]
-start = max(range(len(t)), key=lambda i: t[i] if val(data[i], "dram_wr_MB") < 400 else -1)  # the stem: longest non-Detect launch
+mbs = [val(r, "dram_rd_MB") + val(r, "dram_wr_MB") for r in data]
+# the step starts at the stem: it and the next conv (P2) are the two largest-traffic launches and are adjacent
+start = int(sys.argv[2]) if len(sys.argv) > 2 else max(range(len(t)), key=lambda i: mbs[i] + mbs[(i + 1) % len(t)])
 order = list(range(start, len(data))) + list(range(start))
 print(f"source: {sys.argv[1]} ({len(data)} conv_tc_kernel launches of one step, ncu --set full --clock-control none; cold-cache, serialised)")
 print("  #      us  grid blk regs utchmma% tc-smem-wf%  lsu-wf%  l1tex%   lts%  dram MB (rd+wr)  DRAM GB/s")

@@ -115,12 +115,16 @@ struct ConvK {
   int det_rec_w;           // floats per compact record: (5 + nc + 1) rounded up to 4
   float det_stride;
   float det_anchor[6];
-  unsigned long long* ts;  // debug: clock64 stamps of CTA 0, [role 3][tile 32][slot 8] (y5obb_conv_debug_timestamps)
+  unsigned long long* ts;  // debug: clock64 stamps of CTA ts_cta, [role 3][tile & 31][slot 8] (y5obb_conv_debug_timestamps):
+  int ts_cta;              // the LAST 32 tiles of that CTA survive; slot 7 holds the tile's ordinal + 1
 };
 
 #define Y5_TS(role, it, slot)                                                                  \
   do {                                                                                         \
-    if (p.ts && blockIdx.x == 0 && (it) < 32) p.ts[((role)*32 + (it)) * 8 + (slot)] = clock64(); \
+    if (p.ts && (int)blockIdx.x == p.ts_cta) {                                                 \
+      p.ts[((role)*32 + ((it) & 31)) * 8 + (slot)] = clock64();                                \
+      p.ts[((role)*32 + ((it) & 31)) * 8 + 7] = (unsigned long long)(it) + 1ull;               \
+    }                                                                                          \
   } while (0)
 
 struct TileCoord {
@@ -187,6 +191,7 @@ struct EpiTile {
   int cn0, cw, chh, cb;
   const CUtensorMap* tmu;  // up-sampled copy by TMA (null: per-thread stores through urow)
   int ubh;                 // cb * Hout + chh
+  unsigned long long* ts;  // debug stamps of this tile's first chunk (slots 4..6 of the epilogue row) or null
 };
 
 template <bool ACT, bool RES, bool UP>
@@ -206,9 +211,11 @@ __device__ __forceinline__ void conv_epi_tile(const EpiTile& e, int& sbuf) {
 #pragma unroll
     for (int g = 0; g < 8; ++g) bv[g] = __ldg(b4 + g);
     ptx::tmem_ld_wait();
+    if (e.ts && c0 == e.col_first) e.ts[4] = clock64();
     // the staging buffer about to be overwritten must have been read by its TMA store
     if (e.leader) ptx::tma_store_wait_read<1>();
     __syncwarp();
+    if (e.ts && c0 == e.col_first) e.ts[5] = clock64();
     uint8_t* sb = e.stage + sbuf * e.stage_bytes + e.lane * 64;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {  // 8 channels = one 16-byte chunk
@@ -251,6 +258,7 @@ __device__ __forceinline__ void conv_epi_tile(const EpiTile& e, int& sbuf) {
         }
       }
     }
+    if (e.ts && c0 == e.col_first) e.ts[6] = clock64();
     ptx::fence_proxy_async();
     __syncwarp();
     if (e.leader) {
@@ -550,6 +558,7 @@ __global__ void __launch_bounds__(DUAL ? 192 : NUM_THREADS) __maxnreg__(DUAL ? 1
         et.cb = c.b;
         et.tmu = (p.out2x && p.up_tma) ? &p.tmU : nullptr;
         et.ubh = c.b * p.Hout + hsub + box_h0;
+        et.ts = (ts_on && m == 0 && p.ts && (int)blockIdx.x == p.ts_cta) ? p.ts + (2 * 32 + (it & 31)) * 8 : nullptr;
         // one specialised instantiation per layer flavour: nothing of the unused paths is issued
         const int flavour = (p.act ? 1 : 0) | (p.res ? 2 : 0) | (p.out2x ? 4 : 0);
         switch (flavour) {
@@ -565,15 +574,18 @@ __global__ void __launch_bounds__(DUAL ? 192 : NUM_THREADS) __maxnreg__(DUAL ? 1
       } else if (p.det_decode == 2) {
         // Detect, compact records for the fused post-process (the [B, A, no] tensor is never written): per anchor row
         // rec_w floats = (cx, cy, w, h, obj, cls[nc], theta index) - everything non_max_suppression_obb reads of a row
-        // (utils/general.py:781-832).  Same sigmoid and decode arithmetic as the full-tensor mode below; the theta index is
-        // the first maximum over the 180 sigmoid values, as torch.max returns it (:822).  Every warp owns whole tiles here.
-        // The warp's 32 records are staged densely ([32][rec_w] fp32) and leave through ONE TMA store whose tensor map views
-        // the record buffer as (rec_w, W, H, anchor, image).
+        // (utils/general.py:781-832).  Box / obj / class columns: same sigmoid and decode arithmetic as the full-tensor mode
+        // below.  The theta index is the first maximum of the 180 LOGITS (accumulator + bias): the sigmoid is monotone, so this
+        // is the index torch.max returns on the activated values (:822) whenever those are distinct - and the 180 MUFU ops and
+        // their arithmetic per row, which bounded this epilogue, are not needed.  (On the tanh.approx sigmoid of the
+        // full-tensor mode two logits closer than its 2^-11 error can order differently; the tests bound that.)
+        // Every warp owns whole tiles here.  The warp's 32 records are staged densely ([32][rec_w] fp32) and leave through
+        // ONE TMA store whose tensor map views the record buffer as (rec_w, W, H, anchor, image).
         const int a = c.nt;
         const int nfix = p.det_no - 180;                    // 5 + nc leading columns
         if (leader) ptx::tma_store_wait_read<1>();
         __syncwarp();
-        float* rec = reinterpret_cast<float*>(stage + sbuf * p.epi_stage_bytes) + lane * p.det_rec_w;
+        const uint32_t rec_s = ptx::smem_u32(stage + sbuf * p.epi_stage_bytes) + (uint32_t)(lane * p.det_rec_w) * 4u;
         float best = -INFINITY;
         int bk = 0;
         for (int c0 = 0; c0 < p.det_no; c0 += 32) {
@@ -581,40 +593,70 @@ __global__ void __launch_bounds__(DUAL ? 192 : NUM_THREADS) __maxnreg__(DUAL ? 1
           ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)c0, r);
           ptx::tmem_ld_wait();
           const float4* b4 = reinterpret_cast<const float4*>(p.bias + c.n0 + c0);
+          float v[32];
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
-            const int col = c0 + 4 * g;
-            if (col >= p.det_no) break;
             const float4 bv = __ldg(b4 + g);
-            float v[4];
-            v[0] = sigmoid_fast(__uint_as_float(r[g * 4 + 0]) + bv.x);
-            v[1] = sigmoid_fast(__uint_as_float(r[g * 4 + 1]) + bv.y);
-            v[2] = sigmoid_fast(__uint_as_float(r[g * 4 + 2]) + bv.z);
-            v[3] = sigmoid_fast(__uint_as_float(r[g * 4 + 3]) + bv.w);
-            if (col == 0) {  // xy, wh (models/yolo.py:73-74)
-              v[0] = (v[0] * 2.0f - 0.5f + (float)w) * p.det_stride;
-              v[1] = (v[1] * 2.0f - 0.5f + (float)h) * p.det_stride;
-              v[2] = (v[2] * 2.0f) * (v[2] * 2.0f) * p.det_anchor[2 * a];
-              v[3] = (v[3] * 2.0f) * (v[3] * 2.0f) * p.det_anchor[2 * a + 1];
-            }
-            if (col + 3 < nfix) {
-              *reinterpret_cast<float4*>(rec + col) = make_float4(v[0], v[1], v[2], v[3]);
-            } else {
+            v[4 * g + 0] = __uint_as_float(r[g * 4 + 0]) + bv.x;
+            v[4 * g + 1] = __uint_as_float(r[g * 4 + 1]) + bv.y;
+            v[4 * g + 2] = __uint_as_float(r[g * 4 + 2]) + bv.z;
+            v[4 * g + 3] = __uint_as_float(r[g * 4 + 3]) + bv.w;
+          }
+          const int lo = nfix - c0;          // entries [lo, hi) of this chunk are theta bins
+          const int hi = p.det_no - c0;
+          if (lo > 0) {  // (warp-uniform) the chunk holds box / obj / class columns: activate, decode, stage them
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const int cc = col + k;
-                if (cc < nfix) {
-                  rec[cc] = v[k];
-                } else if (cc < p.det_no && v[k] > best) {
-                  best = v[k];
-                  bk = cc - nfix;
+            for (int g = 0; g < 8; ++g) {
+              if (4 * g < lo) {
+                float s0 = sigmoid_fast(v[4 * g]), s1 = sigmoid_fast(v[4 * g + 1]);
+                float s2 = sigmoid_fast(v[4 * g + 2]), s3 = sigmoid_fast(v[4 * g + 3]);
+                if (c0 == 0 && g == 0) {  // xy, wh (models/yolo.py:73-74)
+                  s0 = (s0 * 2.0f - 0.5f + (float)w) * p.det_stride;
+                  s1 = (s1 * 2.0f - 0.5f + (float)h) * p.det_stride;
+                  s2 = (s2 * 2.0f) * (s2 * 2.0f) * p.det_anchor[2 * a];
+                  s3 = (s3 * 2.0f) * (s3 * 2.0f) * p.det_anchor[2 * a + 1];
+                }
+                const uint32_t dst = rec_s + (uint32_t)(c0 + 4 * g) * 4u;
+                if (4 * g + 3 < lo) {
+                  ptx::st_shared_v4(dst, s0, s1, s2, s3);
+                } else {  // the group straddles the first theta bin
+                  ptx::st_shared_f32(dst, s0);
+                  if (4 * g + 1 < lo) ptx::st_shared_f32(dst + 4, s1);
+                  if (4 * g + 2 < lo) ptx::st_shared_f32(dst + 8, s2);
                 }
               }
             }
           }
+          if (lo > 0 || hi < 32) {  // (warp-uniform) first / last chunk: entries that are not theta bins never win
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+              if (k < lo || k >= hi) v[k] = -INFINITY;
+          }
+          // a 5-level tournament over the chunk (the first maximum wins ties: the higher index replaces the lower only if
+          // strictly greater), then ONE comparison against the running best - a 180-step dependent chain otherwise
+          int id[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const bool take = v[2 * k + 1] > v[2 * k];
+            v[k] = take ? v[2 * k + 1] : v[2 * k];
+            id[k] = 2 * k + (take ? 1 : 0);
+          }
+#pragma unroll
+          for (int half = 8; half >= 1; half >>= 1) {
+#pragma unroll
+            for (int k = 0; k < half; ++k) {
+              const bool take = v[2 * k + 1] > v[2 * k];
+              v[k] = take ? v[2 * k + 1] : v[2 * k];
+              id[k] = take ? id[2 * k + 1] : id[2 * k];
+            }
+          }
+          if (v[0] > best) {
+            best = v[0];
+            bk = c0 + id[0] - nfix;
+          }
         }
-        rec[nfix] = (float)bk;
-        for (int cc = nfix + 1; cc < p.det_rec_w; ++cc) rec[cc] = 0.0f;  // padding columns
+        ptx::st_shared_f32(rec_s + (uint32_t)nfix * 4u, (float)bk);
+        for (int cc = nfix + 1; cc < p.det_rec_w; ++cc) ptx::st_shared_f32(rec_s + (uint32_t)cc * 4u, 0.0f);  // padding columns
         ptx::fence_proxy_async();
         __syncwarp();
         if (leader) {  // rows beyond the image are clipped by the tensor map
@@ -1187,6 +1229,8 @@ int y5obb_conv_debug_occupancy(int dual, int threads, size_t dyn_smem, int* bloc
 int y5obb_conv_debug_timestamps(y5obb_conv_t* conv, unsigned long long* dev_buf_768) {
   if (!conv) return Y5OBB_EINVAL;
   reinterpret_cast<ConvObj*>(conv)->k.ts = dev_buf_768;
+  const char* c = getenv("Y5OBB_TS_CTA");  // which CTA stamps (default 0)
+  reinterpret_cast<ConvObj*>(conv)->k.ts_cta = c ? atoi(c) : 0;
   return Y5OBB_OK;
 }
 

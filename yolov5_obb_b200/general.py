@@ -14,7 +14,8 @@ MAX_NMS = 30000   # general.py:794
 
 class DetectRecords:
     """What yolo.Model.detect_records returns: `data` [B, A, rec_w] fp32 rows (cx, cy, w, h, obj, cls[nc], theta index, pad)
-    written by the Detect epilogue (engine-owned buffer, overwritten by the next forward), and the class count."""
+    written by the Detect epilogue (engine-owned buffer, overwritten by the next forward), and the class count.  The theta index
+    is the first maximum of the row's 180 theta logits, i.e. what torch.max returns on their sigmoids (utils/general.py:822)."""
 
     def __init__(self, data: torch.Tensor, nc: int):
         self.data, self.nc = data, int(nc)
