@@ -122,8 +122,9 @@ typedef struct y5obb_conv y5obb_conv_t;
                                       first global-memory access; also switched off by the environment variable Y5OBB_NO_PDL=1) */
 #define Y5OBB_CONV_MSUB1 128       /* flags: 128-pixel tiles only (default: up to four 128-pixel sub-tiles per tile) */
 #define Y5OBB_CONV_NO_UP_TMA 2048  /* flags: the 2x up-sampled copy through per-thread stores (default: four TMA stores of the staged tile) */
-#define Y5OBB_CONV_NO_DUAL 4096    /* flags: always one CTA per SM (default: two CTAs per SM - 256 TMEM columns, half the shared memory
-                                      and four epilogue warps each - wherever a 3-deep operand ring still fits) */
+#define Y5OBB_CONV_NO_DUAL 4096    /* flags: always one CTA per SM.  (Two CTAs per SM - 256 TMEM columns, half the shared memory and four
+                                      epilogue warps each - is an opt-in experiment, environment variable Y5OBB_DUAL; measured slower) */
+#define Y5OBB_CONV_EPI2 8192       /* flags: reserved (two staging buffers per epilogue warp are the default; four: environment variable Y5OBB_EPI_BUFS=4, measured slower) */
 #define Y5OBB_CONV_ACC2 64         /* flags: two TMEM accumulator stages only (A-B comparison; default: as many as 512 columns hold) */
 
 typedef struct {

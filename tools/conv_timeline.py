@@ -40,7 +40,7 @@ for ci, cv in enumerate(eng.convs):
     order = sorted((int(t[1, k, 7]), k) for k in range(32) if int(t[1, k, 7]))
     print(f"--- conv {ci}: BN={inf['block_n']} BK={inf['block_k']} stages={inf['stages']} grid={inf['grid']} launch {e0.elapsed_time(e1) * 1e3:.1f} us "
           f"(the CTA's LAST 32 tiles; cycles since the earliest surviving stamp; P=producer [wait-empty, got, loads issued], M=mma [wait-tmem, got, "
-          f"first full, issued, committed], E=epilogue [wait-full, got, done, arrived | first chunk: tmem loaded, staging free, staged]; E rows: the epilogue group that owns the tile)")
+          f"first full, issued, committed], E=epilogue [wait-full, got, done, arrived | first chunk: before tcgen05.ld, after wait::ld, staged]; E rows: the epilogue group that owns the tile)")
     for ordinal, it in order:
         f = lambda r, n: " ".join(f"{int(t[r, it, k]) - t0:7d}" if int(t[r, it, k]) else "      -" for k in range(n))
         print(f"tile {ordinal - 1:3d}  P {f(0, 3)} | M {f(1, 5)} | E {f(2, 4)} | {" ".join(f"{int(t[2, it, k]) - t0:7d}" if int(t[2, it, k]) else "      -" for k in (4, 5, 6))}")

@@ -2,12 +2,14 @@
 // memory, K-major, 128B swizzle) issued back to back by ONE elected thread, and by TWO warps at once (different accumulators).
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o mma_rate tools/micro/mma_rate.cu && ./mma_rate
 #include <cstdio>
+#include <cstdlib>
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include "../../yolov5_obb_b200/csrc/ptx.cuh"
 using namespace y5obb;
 
-__global__ void __launch_bounds__(128, 1) k(int N, int n_batches, int n_warps, int reps, long long* out) {
+__global__ void __launch_bounds__(128, 1) k(int N, int n_batches, int n_warps, int reps, long long* out, int mode = 0, uint32_t a_step = 0,
+                                            uint32_t b_step = 0) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar[2];
   __shared__ uint32_t tmem_base_s;
@@ -40,10 +42,33 @@ __global__ void __launch_bounds__(128, 1) k(int N, int n_batches, int n_warps, i
       long long t_issue = 0, t_done = 0;
       for (int r = 0; r < reps; ++r) {
         const long long t0 = clock64();
-        for (int bt = 0; bt < n_batches; ++bt) {  // 8 MMAs per batch, compile-time operand offsets, no index arithmetic
+        if (mode == 0) {
+          for (int bt = 0; bt < n_batches; ++bt) {  // 8 MMAs per batch, compile-time operand offsets, no index arithmetic
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            ptx::umma_bf16(d, da0 + (uint64_t)((j >> 2) * 1024 + (j & 3) * 2), db0 + (uint64_t)((j & 3) * 2), idesc, (bt | j) ? 1u : 0u);
+            for (int j = 0; j < 8; ++j)
+              ptx::umma_bf16(d, da0 + (uint64_t)((j >> 2) * 1024 + (j & 3) * 2), db0 + (uint64_t)((j & 3) * 2), idesc, (bt | j) ? 1u : 0u);
+          }
+        } else if (mode == 1) {  // the conv kernel's issue_unit<2, 4>: operand offsets from RUNTIME steps (64-bit descriptor adds)
+          for (int bt = 0; bt < n_batches; ++bt) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                ptx::umma_bf16(d, da0 + (uint64_t)(u * a_step + 2 * j), db0 + (uint64_t)(u * b_step + 2 * j), idesc, (bt | u | j) ? 1u : 0u);
+          }
+        } else {  // same offsets, the low descriptor word advanced by 32-bit adds, high word constant
+          const uint32_t hi32 = (uint32_t)(hi >> 32), a_lo = (uint32_t)da0, b_lo = (uint32_t)db0;
+          for (int bt = 0; bt < n_batches; ++bt) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint64_t da, db;
+                asm volatile("mov.b64 %0, {%1, %2};" : "=l"(da) : "r"(a_lo + u * a_step + 2 * j), "r"(hi32));
+                asm volatile("mov.b64 %0, {%1, %2};" : "=l"(db) : "r"(b_lo + u * b_step + 2 * j), "r"(hi32));
+                ptx::umma_bf16(d, da, db, idesc, (bt | u | j) ? 1u : 0u);
+              }
+          }
         }
         const long long t1 = clock64();
         ptx::umma_commit(&bar[warp]);
@@ -74,6 +99,19 @@ int main() {
   cudaMalloc(&d, 16);
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   printf("  N  n_mma warps | issue cycles (per mma) | until complete (per mma)   [tensor floor per mma = N/2 cycles]\n");
+  const int only_mode = getenv("MMA_RATE_MODES") ? 1 : 0;   // set: compare the three descriptor-arithmetic modes (1 warp)
+  if (only_mode) {
+    for (int mode : {0, 1, 2})
+      for (int N : {32, 64, 256})
+        for (int nb : {2, 8}) {
+          k<<<148, 128, 200 * 1024>>>(N, nb, 1, 6, d, mode, 64u, 0u);
+          long long h[2];
+          if (cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+          printf("mode %d N %3d n_mma %3d | issue %6lld (%5.1f per mma) | complete %6lld (%5.1f)\n", mode, N, nb * 8, h[0], (double)h[0] / (nb * 8), h[1],
+                 (double)h[1] / (nb * 8));
+        }
+    return 0;
+  }
   for (int N : {16, 32, 64, 128, 256})
     for (int nb : {1, 2, 8, 32})
       for (int nw : {1, 2}) {

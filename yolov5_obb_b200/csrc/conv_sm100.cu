@@ -90,6 +90,9 @@ struct ConvK {
                        // columns, half the shared memory and one epilogue group - two independent producer / MMA / epilogue
                        // pipelines whose hand-shake bubbles overlap (ncu: no unit of the single pipeline is above 45 % busy)
   int tmem_cols;       // 512 or 256
+  int mma_loop;        // 1: the MMA issuer uses the compact runtime loop for every unit shape (A-B against the unrolled sequences)
+  int wait_suspend;    // 1: the epilogue warps' wait on the accumulator uses the suspend-hint form of mbarrier.try_wait
+  int epi_bufs;        // staging buffers per epilogue warp (2 or 4): a buffer is reused only after its TMA store has read it
   int epi_tile_split;  // 1: epilogue warp group g handles the tiles whose accumulator is g (all columns); 0: both
                        // groups work on every tile and split its columns (few tiles per CTA)
   int rowshift;    // 1: one A stage holds Ht + KH - 1 image rows; the KH taps of a column read it at row offsets
@@ -174,6 +177,102 @@ __device__ __forceinline__ void issue_unit(uint32_t d_tmem, uint64_t da0, uint64
   }
 }
 
+// The same with the descriptors' low words (address >> 4 | LBO) advanced by 32-bit adds and the constant high word attached by a
+// register-pair move: no 64-bit arithmetic between the MMAs (the issuing thread is instruction bound: ncu source view, r2)
+__device__ __forceinline__ uint64_t desc_from(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm volatile("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+template <int KSUB, int NK>
+__device__ __forceinline__ void issue_unit_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t a_step, uint32_t b_step,
+                                              uint32_t idesc, uint32_t accumulate) {
+#pragma unroll
+  for (int u = 0; u < KSUB; ++u) {
+#pragma unroll
+    for (int j = 0; j < NK; ++j) {
+      ptx::umma_bf16(d_tmem, desc_from(a_lo + (uint32_t)u * a_step + 2u * j, hi), desc_from(b_lo + (uint32_t)u * b_step + 2u * j, hi), idesc,
+                     (u | j) ? 1u : accumulate);
+    }
+  }
+}
+
+struct MmaCtx {
+  uint64_t *full_bar, *empty_bar, *tmem_full, *tmem_empty;
+  uint32_t tmem_base, ring_lo, res_lo, hi;  // descriptor low words of the operand ring / the resident weights, common high word
+  uint32_t stage16, unit16;                 // pipeline stage / unit size in 16-byte units
+  int total_tiles, ksub;
+};
+
+// The MMA issuer's whole tile loop, specialised on the unit shape (KSUB vertical taps x NK 16-channel sub-blocks of a full K
+// chunk; 0, 0 = any shape through runtime loops).  Everything loop invariant sits in registers, the ring position and the resident
+// weight tile advance incrementally, and the ragged last K chunk (Cin not a multiple of BK) takes the runtime loop.
+template <int KSUB, int NK>
+__device__ __forceinline__ void mma_role(const ConvK& p, const MmaCtx& x) {
+  const uint32_t a_step = p.row_shift_bytes >> 4;  // per vertical tap: one image row of the tile ...
+  const uint32_t bst16 = p.b_stage_bytes >> 4;
+  const uint32_t b_step = p.b_resident ? (uint32_t)(p.KW * p.kchunks) * bst16 : bst16;  // ... and KW weight tiles (resident) or one
+  const uint32_t a_bytes16 = p.a_bytes >> 4, a_sub16 = p.a_sub16, idesc = p.idesc, hi = x.hi;
+  const int n_units = p.n_units, group = p.group, kchunks = p.kchunks, m_sub = p.m_sub, sub_cols = p.sub_cols, stages = p.stages;
+  const int nk_last = ((p.Cin - (kchunks - 1) * p.BK) + 15) >> 4;  // MMAs per tap of the last (possibly ragged) K chunk
+  const bool resident = p.b_resident != 0, no_mma = (p.dbg & 2) != 0;
+  int s = 0, it = 0;
+  uint32_t ph = 0, s_lo = x.ring_lo;
+  for (int t = blockIdx.x; t < x.total_tiles; t += gridDim.x, ++it) {
+    const int acc = it & (p.n_acc - 1);
+    const uint32_t acc_ph = (uint32_t)(it >> p.acc_shift) & 1u;
+    Y5_TS(1, it, 0);
+    ptx::mbar_wait(&x.tmem_empty[acc], acc_ph ^ 1u);
+    ptx::tc_fence_after();
+    Y5_TS(1, it, 1);
+    const uint32_t d_tmem = x.tmem_base + (uint32_t)(acc * p.acc_stride);
+    uint32_t accumulate = 0u, bres_lo = x.res_lo;
+    int kc = 0;
+    for (int u0 = 0; u0 < n_units; u0 += group) {
+      const int ng = min(group, n_units - u0);
+      ptx::mbar_wait(&x.full_bar[s], ph);
+      ptx::tc_fence_after();
+      if (u0 == 0) Y5_TS(1, it, 2);
+      uint32_t a_lo = s_lo;
+      for (int g = 0; g < ng; ++g) {
+        const uint32_t b_lo = resident ? bres_lo : a_lo + a_bytes16;
+        const bool last = kc + 1 == kchunks;
+        if (!no_mma) {
+          if (NK > 0 && (!last || nk_last == NK)) {
+            for (int m = 0; m < m_sub; ++m)  // the m_sub sub-tiles of the tile share this unit's weights
+              issue_unit_lo<KSUB, NK>(d_tmem + (uint32_t)(m * sub_cols), a_lo + (uint32_t)m * a_sub16, b_lo, hi, a_step, b_step, idesc, accumulate);
+          } else {
+            const int nk = last ? nk_last : (p.BK >> 4);
+            for (int m = 0; m < m_sub; ++m) {
+              uint32_t acc_m = accumulate;
+              for (int u = 0; u < x.ksub; ++u)
+                for (int j = 0; j < nk; ++j) {
+                  ptx::umma_bf16(d_tmem + (uint32_t)(m * sub_cols), desc_from(a_lo + (uint32_t)m * a_sub16 + (uint32_t)u * a_step + 2u * j, hi),
+                                 desc_from(b_lo + (uint32_t)u * b_step + 2u * j, hi), idesc, acc_m);
+                  acc_m = 1u;
+                }
+            }
+          }
+        }
+        accumulate = 1u;
+        a_lo += x.unit16;
+        bres_lo += bst16;
+        kc = last ? 0 : kc + 1;
+      }
+      ptx::umma_commit(&x.empty_bar[s]);
+      s_lo += x.stage16;
+      if (++s == stages) {
+        s = 0;
+        ph ^= 1u;
+        s_lo = x.ring_lo;
+      }
+    }
+    Y5_TS(1, it, 3);
+    ptx::umma_commit(&x.tmem_full[acc]);
+    Y5_TS(1, it, 4);
+  }
+}
+
 // ---- epilogue of one MODE_CONV tile for one warp -----------------------------------------------------
 struct EpiTile {
   uint32_t taddr;     // TMEM address of this warp's lane quarter, column 0 of the accumulator
@@ -182,8 +281,9 @@ struct EpiTile {
   uint32_t swz;       // (lane >> 1) & 3
   int lane;
   bool leader;        // the warp's elected thread (elect.sync once per kernel): issues and tracks the TMA stores
-  const float* bias;  // + n0; holds 0.5 * bias when the layer has SiLU (Y5OBB_CONV_BIAS_HALVED)
+  uint32_t bias;      // shared-memory address of the bias (+ n0); holds 0.5 * bias when the layer has SiLU (Y5OBB_CONV_BIAS_HALVED)
   const __nv_bfloat16* rrow;  // residual row of this thread's pixel (+ n0) or null
+  const __nv_bfloat16* rrow_next;  // the same for the tile's next sub-tile (null after the last): its first chunk is fetched one step ahead
   __nv_bfloat16* urow;        // up-sampled destination of this thread's pixel (+ n0) or null
   long long up_pix, up_row;
   int nvalid, col_first, col_step;
@@ -192,36 +292,45 @@ struct EpiTile {
   const CUtensorMap* tmu;  // up-sampled copy by TMA (null: per-thread stores through urow)
   int ubh;                 // cb * Hout + chh
   unsigned long long* ts;  // debug stamps of this tile's first chunk (slots 4..6 of the epilogue row) or null
+  int nbuf;                // staging buffers of this warp (2 or 4)
 };
 
+// rvn: this thread's residual values of the NEXT chunk to be processed (16-byte loads issued one chunk ahead - across
+// sub-tiles too, and for a tile's first chunk before the wait on its accumulator - so the L2 / HBM latency of the residual
+// (~1-3k cycles per chunk in the in-kernel timelines) is off the epilogue's critical path)
 template <bool ACT, bool RES, bool UP>
-__device__ __forceinline__ void conv_epi_tile(const EpiTile& e, int& sbuf) {
+__device__ __forceinline__ void conv_epi_tile(const EpiTile& e, int& sbuf, uint4 (&rvn)[4]) {
   for (int c0 = e.col_first; c0 < e.nvalid; c0 += e.col_step) {
     uint32_t r[32];
+    if (e.ts && c0 == e.col_first) e.ts[4] = clock64();
     ptx::tmem_ld_32x32b_x32(e.taddr + (uint32_t)c0, r);
     uint4 rv[4];
-    if (RES) {  // all four 16-byte residual loads are in flight before anything waits on them
+    if (RES) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) rv[g] = rvn[g];
+      const int cn = c0 + e.col_step;
+      const bool same = cn < e.nvalid;
+      const __nv_bfloat16* nx = same ? e.rrow : e.rrow_next;
+      const int cc = same ? cn : e.col_first;
 #pragma unroll
       for (int g = 0; g < 4; ++g)
-        rv[g] = (e.rrow && c0 + g * 8 < e.nvalid) ? *reinterpret_cast<const uint4*>(e.rrow + c0 + g * 8)
-                                                   : make_uint4(0, 0, 0, 0);
+        rvn[g] = (nx && cc + g * 8 < e.nvalid) ? *reinterpret_cast<const uint4*>(nx + cc + g * 8) : make_uint4(0, 0, 0, 0);
     }
-    const float4* b4 = reinterpret_cast<const float4*>(e.bias + c0);
-    float4 bv[8];
-#pragma unroll
-    for (int g = 0; g < 8; ++g) bv[g] = __ldg(b4 + g);
+    const uint32_t b4 = e.bias + (uint32_t)c0 * 4u;  // shared memory, the same address in every lane (a broadcast)
     ptx::tmem_ld_wait();
-    if (e.ts && c0 == e.col_first) e.ts[4] = clock64();
-    // the staging buffer about to be overwritten must have been read by its TMA store
-    if (e.leader) ptx::tma_store_wait_read<1>();
-    __syncwarp();
     if (e.ts && c0 == e.col_first) e.ts[5] = clock64();
+    // the staging buffer about to be overwritten must have been read by its TMA store
+    if (e.leader) {
+      if (e.nbuf == 4) ptx::tma_store_wait_read<3>();
+      else ptx::tma_store_wait_read<1>();
+    }
+    __syncwarp();
     uint8_t* sb = e.stage + sbuf * e.stage_bytes + e.lane * 64;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {  // 8 channels = one 16-byte chunk
       float v[8];
-      const float bb[8] = {bv[2 * g].x, bv[2 * g].y, bv[2 * g].z, bv[2 * g].w,
-                           bv[2 * g + 1].x, bv[2 * g + 1].y, bv[2 * g + 1].z, bv[2 * g + 1].w};
+      const float4 bv0 = ptx::ld_shared_v4(b4 + 32u * g), bv1 = ptx::ld_shared_v4(b4 + 32u * g + 16u);
+      const float bb[8] = {bv0.x, bv0.y, bv0.z, bv0.w, bv1.x, bv1.y, bv1.z, bv1.w};
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const float acc = __uint_as_float(r[g * 8 + k]);
@@ -271,7 +380,95 @@ __device__ __forceinline__ void conv_epi_tile(const EpiTile& e, int& sbuf) {
       }
       ptx::tma_store_commit();
     }
-    sbuf ^= 1;
+    sbuf = (sbuf + 1) & (e.nbuf - 1);
+  }
+}
+
+struct EpiCtx {
+  uint64_t *tmem_full, *tmem_empty;
+  uint32_t tmem_base;
+  uint8_t* stage;    // this warp's staging buffers
+  uint32_t bias_s;   // shared-memory address of the layer's bias
+  int lane, e, q, half, hl, wl, box_w0, box_h0, col_first, col_step, total_tiles;
+  bool leader, one_group;
+};
+
+// The MODE_CONV epilogue's whole tile loop, specialised on the layer flavour (activation, residual, 2x up-sampled copy): the
+// flavour is chosen once per kernel instead of through an indirect branch per sub-tile, what is constant over a tile is set up
+// once per tile, and per sub-tile only the accumulator columns, the output row and the residual / up-sampling rows move.
+template <bool ACT, bool RES, bool UP>
+__device__ __forceinline__ void epi_role_conv(const ConvK& p, const EpiCtx& x) {
+  int sbuf = 0, it = 0;
+  EpiTile et;
+  et.stage = x.stage;
+  et.stage_bytes = p.epi_stage_bytes;
+  et.swz = (uint32_t)((x.lane >> 1) & 3);
+  et.lane = x.lane;
+  et.leader = x.leader;
+  et.up_pix = p.out2x_pix_stride;
+  et.up_row = (long long)(2 * p.Wout) * p.out2x_pix_stride;
+  et.col_first = x.col_first;
+  et.col_step = x.col_step;
+  et.tm = &p.tmO;
+  et.tmu = (UP && p.up_tma) ? &p.tmU : nullptr;
+  et.nbuf = p.epi_bufs;
+  const long long rstep = (long long)p.Ht * p.res_row_stride;                                 // residual: one sub-tile down
+  const long long ustep = (long long)(2 * p.Ht) * (2 * p.Wout) * p.out2x_pix_stride;           // up-sampled copy: one sub-tile down
+  const uint32_t lane_quarter = (uint32_t)(x.q * 32) << 16;
+  for (int t = blockIdx.x; t < x.total_tiles; t += gridDim.x, ++it) {
+    const int acc = it & (p.n_acc - 1);
+    if (p.epi_tile_split && !x.one_group && (it & 1) != x.half) continue;  // the other warp group owns this tile
+    const TileCoord c = decode_tile(p, t);
+    const uint32_t acc_ph = (uint32_t)(it >> p.acc_shift) & 1u;
+    const bool ts_on = x.leader && (x.e & 3) == 0 && (p.epi_tile_split || x.one_group || x.e == 0);
+    const int h0 = c.h0 + x.hl, w = c.w0 + x.wl;
+    const bool wvalid = w < p.Wout;
+    const int nvalid = min(p.BN, p.Cout - c.n0);
+    // this thread's pixel in sub-tile 0: residual row and up-sampled destination (sub-tile m: + m * rstep / ustep)
+    const __nv_bfloat16* rbase =
+        RES ? p.res + (long long)c.b * p.res_img_stride + (long long)h0 * p.res_row_stride + (long long)w * p.res_pix_stride + c.n0 : nullptr;
+    __nv_bfloat16* ubase =
+        (UP && !et.tmu) ? p.out2x + (((long long)c.b * 2 * p.Hout + 2 * h0) * (2 * p.Wout) + 2 * w) * p.out2x_pix_stride + c.n0 : nullptr;
+    auto res_row = [&](int m) -> const __nv_bfloat16* {
+      return (RES && p.res && m < p.m_sub && wvalid && h0 + m * p.Ht < p.Hout) ? rbase + m * rstep : nullptr;
+    };
+    uint4 rvn[4];
+    if (RES) {  // the tile's first residual chunk is in flight while we wait for the accumulator
+      const __nv_bfloat16* r0 = res_row(0);
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        rvn[g] = (r0 && x.col_first + g * 8 < nvalid) ? *reinterpret_cast<const uint4*>(r0 + x.col_first + g * 8) : make_uint4(0, 0, 0, 0);
+    }
+    et.bias = x.bias_s + (uint32_t)c.n0 * 4u;
+    et.nvalid = nvalid;
+    et.cn0 = c.n0;
+    et.cw = c.w0 + x.box_w0;
+    et.cb = c.b;
+    if (ts_on) Y5_TS(2, it, 0);
+    if (p.wait_suspend) ptx::mbar_wait_suspend(&x.tmem_full[acc], acc_ph);
+    else ptx::mbar_wait(&x.tmem_full[acc], acc_ph);
+    ptx::tc_fence_after();
+    if (ts_on) Y5_TS(2, it, 1);
+    if (!(p.dbg & 4)) {
+      uint32_t taddr = x.tmem_base + (uint32_t)(acc * p.acc_stride) + lane_quarter;
+      int chh = c.h0 + x.box_h0;
+      for (int m = 0; m < p.m_sub; ++m) {  // the tile's 128-pixel sub-tiles, stacked along H
+        et.taddr = taddr;
+        et.chh = chh;
+        et.ubh = c.b * p.Hout + chh;
+        et.rrow = res_row(m);
+        et.rrow_next = res_row(m + 1);
+        et.urow = (UP && !et.tmu && wvalid && h0 + m * p.Ht < p.Hout) ? ubase + m * ustep : nullptr;
+        et.ts = (ts_on && m == 0 && p.ts && (int)blockIdx.x == p.ts_cta) ? p.ts + (2 * 32 + (it & 31)) * 8 : nullptr;
+        conv_epi_tile<ACT, RES, UP>(et, sbuf, rvn);
+        taddr += (uint32_t)p.sub_cols;
+        chh += p.Ht;
+      }
+    }
+    if (ts_on) Y5_TS(2, it, 2);
+    ptx::tc_fence_before();
+    ptx::mbar_arrive(&x.tmem_empty[acc]);
+    if (ts_on) Y5_TS(2, it, 3);
   }
 }
 
@@ -342,7 +539,7 @@ __global__ void __launch_bounds__(DUAL ? 192 : NUM_THREADS) __maxnreg__(DUAL ? 1
         for (int tap = 0; tap < p.KH * p.KW; ++tap)
           for (int kc = 0; kc < p.kchunks; ++kc)
             ptx::tma_load_2d(smem_res + (size_t)(tap * p.kchunks + kc) * p.b_stage_bytes, &p.tmB, &wres_bar, kc * p.BK,
-                             tap * p.cout_pad);
+                             tap * p.cout_pad + (int)(blockIdx.x % (unsigned)p.n_tiles_n) * p.BN);  // this CTA's N tile (see the host plan)
       }
       int s = 0;
       uint32_t ph = 0;
@@ -401,90 +598,44 @@ __global__ void __launch_bounds__(DUAL ? 192 : NUM_THREADS) __maxnreg__(DUAL ? 1
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (ptx::elect_one()) {
-      int s = 0;
-      uint32_t ph = 0;
-      int it = 0;
-      const uint32_t row_bytes = (uint32_t)p.BK * 2u;
       if (p.b_resident) {
         ptx::mbar_wait(&wres_bar, 0u);
         ptx::tc_fence_after();
       }
-      const uint32_t sres = ptx::smem_u32(smem_res);
-      const uint32_t ring_u32 = ptx::smem_u32(smem);
-      const uint64_t desc_hi = ptx::make_kmajor_desc(0u, row_bytes);
-      // per vertical tap u (row-shift mode): A moves by one image row of the tile, B by KW weight tiles (resident:
-      // tap = u * KW + kw) or by one streamed tile; both in units of 16 bytes
-      const uint32_t a_step = p.row_shift_bytes >> 4;
-      const uint32_t b_step = (p.b_resident ? (uint32_t)(p.KW * p.kchunks) * p.b_stage_bytes : p.b_stage_bytes) >> 4;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-        const int acc = it & (p.n_acc - 1);
-        const uint32_t acc_ph = (uint32_t)(it >> p.acc_shift) & 1u;
-        Y5_TS(1, it, 0);
-        ptx::mbar_wait(&tmem_empty[acc], acc_ph ^ 1u);
-        ptx::tc_fence_after();
-        Y5_TS(1, it, 1);
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
-        uint32_t accumulate = 0u;
-        int tap_outer = 0, kc = 0;
-        for (int u0 = 0; u0 < p.n_units; u0 += p.group) {
-          const int ng = min(p.group, p.n_units - u0);
-          ptx::mbar_wait(&full_bar[s], ph);
-          ptx::tc_fence_after();
-          if (u0 == 0) Y5_TS(1, it, 2);
-          const uint32_t sbase = ring_u32 + (uint32_t)s * stage_bytes;
-          for (int g = 0; g < ng; ++g) {
-            // K sub-blocks of 16 that hold real channels (the zero-filled tail of a ragged chunk is skipped)
-            const int nk = (min(p.BK, p.Cin - kc * p.BK) + 15) >> 4;
-            const uint32_t sa = sbase + (uint32_t)g * unit_bytes;
-            // descriptors differ only in the 14-bit (address >> 4) field
-            const uint64_t da0 = desc_hi | (uint64_t)((sa & 0x3FFFFu) >> 4);
-            const uint32_t b0 = p.b_resident ? sres + (uint32_t)(tap_outer * p.kchunks + kc) * p.b_stage_bytes
-                                             : sa + p.a_bytes;
-            const uint64_t db0 = desc_hi | (uint64_t)((b0 & 0x3FFFFu) >> 4);
-            if (!(p.dbg & 2)) {
-              // fully unrolled issue sequences; the m_sub sub-tiles of the tile share this unit's weights
-              for (int m = 0; m < p.m_sub; ++m) {
-                const uint32_t dm = d_tmem + (uint32_t)(m * p.sub_cols);
-                const uint64_t dam = da0 + (uint64_t)((uint32_t)m * p.a_sub16);
-                if (ksub == 3) {
-                  switch (nk) {
-                    case 1: issue_unit<3, 1>(dm, dam, db0, a_step, b_step, p.idesc, accumulate); break;
-                    case 2: issue_unit<3, 2>(dm, dam, db0, a_step, b_step, p.idesc, accumulate); break;
-                    case 3: issue_unit<3, 3>(dm, dam, db0, a_step, b_step, p.idesc, accumulate); break;
-                    default: issue_unit<3, 4>(dm, dam, db0, a_step, b_step, p.idesc, accumulate); break;
-                  }
-                } else if (ksub == 1) {
-                  switch (nk) {
-                    case 1: issue_unit<1, 1>(dm, dam, db0, a_step, b_step, p.idesc, accumulate); break;
-                    case 2: issue_unit<1, 2>(dm, dam, db0, a_step, b_step, p.idesc, accumulate); break;
-                    case 3: issue_unit<1, 3>(dm, dam, db0, a_step, b_step, p.idesc, accumulate); break;
-                    default: issue_unit<1, 4>(dm, dam, db0, a_step, b_step, p.idesc, accumulate); break;
-                  }
-                } else {
-                  uint32_t acc_m = accumulate;
-                  for (int u = 0; u < ksub; ++u)
-                    for (int j = 0; j < nk; ++j) {
-                      ptx::umma_bf16(dm, dam + (uint64_t)(u * a_step + 2 * j), db0 + (uint64_t)(u * b_step + 2 * j), p.idesc, acc_m);
-                      acc_m = 1u;
-                    }
-                }
-              }
-              accumulate = 1u;
-            }
-            if (++kc == p.kchunks) {
-              kc = 0;
-              ++tap_outer;
-            }
-          }
-          ptx::umma_commit(&empty_bar[s]);
-          if (++s == p.stages) {
-            s = 0;
-            ph ^= 1u;
-          }
+      MmaCtx x;
+      x.full_bar = full_bar;
+      x.empty_bar = empty_bar;
+      x.tmem_full = tmem_full;
+      x.tmem_empty = tmem_empty;
+      x.tmem_base = tmem_base;
+      // descriptors differ only in the 14-bit (address >> 4) field of the low word; K-major, SBO = 8 rows
+      const uint64_t desc0 = ptx::make_kmajor_desc(0u, (uint32_t)p.BK * 2u);
+      x.hi = (uint32_t)(desc0 >> 32);
+      x.ring_lo = (uint32_t)desc0 | ((ptx::smem_u32(smem) & 0x3FFFFu) >> 4);
+      x.res_lo = (uint32_t)desc0 | ((ptx::smem_u32(smem_res) & 0x3FFFFu) >> 4);
+      x.stage16 = stage_bytes >> 4;
+      x.unit16 = unit_bytes >> 4;
+      x.total_tiles = total_tiles;
+      x.ksub = ksub;
+      const int nkf = (min(p.BK, p.Cin) + 15) >> 4;  // MMAs per tap of a full K chunk
+      if (p.mma_loop) {
+        mma_role<0, 0>(p, x);
+      } else if (ksub == 3) {
+        switch (nkf) {
+          case 1: mma_role<3, 1>(p, x); break;
+          case 2: mma_role<3, 2>(p, x); break;
+          case 3: mma_role<3, 3>(p, x); break;
+          default: mma_role<3, 4>(p, x); break;
         }
-        Y5_TS(1, it, 3);
-        ptx::umma_commit(&tmem_full[acc]);
-        Y5_TS(1, it, 4);
+      } else if (ksub == 1) {
+        switch (nkf) {
+          case 1: mma_role<1, 1>(p, x); break;
+          case 2: mma_role<1, 2>(p, x); break;
+          case 3: mma_role<1, 3>(p, x); break;
+          default: mma_role<1, 4>(p, x); break;
+        }
+      } else {
+        mma_role<0, 0>(p, x);
       }
     }
   } else {
@@ -501,12 +652,50 @@ __global__ void __launch_bounds__(DUAL ? 192 : NUM_THREADS) __maxnreg__(DUAL ? 1
     // this warp's 32 pixels as a TMA box: {32 ch, bw, 32 / bw, 1}
     const int bw = min(p.Wt, 32);
     const int box_h0 = (q * 32) / p.Wt, box_w0 = (q * 32) % p.Wt;
-    uint8_t* stage = smem + (size_t)p.stages * stage_bytes + (size_t)e * (2 * p.epi_stage_bytes);
+    uint8_t* stage = smem + (size_t)p.stages * stage_bytes + (size_t)e * ((size_t)p.epi_bufs * p.epi_stage_bytes);
+    // the layer's bias in shared memory: with 224 KB of the SM configured as shared memory the L1 that is left is a few KB, the
+    // residual stream evicts the bias line at every chunk and each 32-column chunk then waited an L2 round trip (~700+ cycles
+    // in the in-kernel stamps) for the SAME 128 bytes
+    float* bias_s = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes + (size_t)p.epi_warps * p.epi_bufs * p.epi_stage_bytes);
+    for (int i = (int)threadIdx.x - 64; i < p.cout_pad + 32; i += 32 * p.epi_warps) bias_s[i] = __ldg(p.bias + i);
+    asm volatile("bar.sync 1, %0;" ::"r"(32 * p.epi_warps) : "memory");
     int sbuf = 0;
     int it = 0;
     const bool one_group = p.epi_warps == 4;                              // a single epilogue group takes every tile, every column
     const int col_first = (p.epi_tile_split || one_group) ? 0 : half * 32;  // first 32-column chunk of this warp
     const int col_step = (p.epi_tile_split || one_group) ? 32 : 64;
+    if (p.mode == MODE_CONV) {  // one specialised instantiation of the whole loop per layer flavour
+      EpiCtx x;
+      x.tmem_full = tmem_full;
+      x.tmem_empty = tmem_empty;
+      x.tmem_base = tmem_base;
+      x.stage = stage;
+      x.bias_s = ptx::smem_u32(bias_s);
+      x.lane = lane;
+      x.e = e;
+      x.q = q;
+      x.half = half;
+      x.hl = hl;
+      x.wl = wl;
+      x.box_w0 = box_w0;
+      x.box_h0 = box_h0;
+      x.col_first = col_first;
+      x.col_step = col_step;
+      x.total_tiles = total_tiles;
+      x.leader = leader;
+      x.one_group = one_group;
+      const int flavour = (p.act ? 1 : 0) | (p.res ? 2 : 0) | (p.out2x ? 4 : 0);
+      switch (flavour) {
+        case 0: epi_role_conv<false, false, false>(p, x); break;
+        case 1: epi_role_conv<true, false, false>(p, x); break;
+        case 2: epi_role_conv<false, true, false>(p, x); break;
+        case 3: epi_role_conv<true, true, false>(p, x); break;
+        case 5: epi_role_conv<true, false, true>(p, x); break;
+        case 4:
+        case 6: epi_role_conv<false, true, true>(p, x); break;  // generic paths tolerate null rrow / urow
+        default: epi_role_conv<true, true, true>(p, x); break;
+      }
+    } else
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int acc = it & (p.n_acc - 1);
       if (p.epi_tile_split && !one_group && (it & 1) != half) continue;  // the other warp group owns this tile
@@ -515,7 +704,8 @@ __global__ void __launch_bounds__(DUAL ? 192 : NUM_THREADS) __maxnreg__(DUAL ? 1
 
       const bool ts_on = leader && (e & 3) == 0 && (p.epi_tile_split || one_group || e == 0);
       if (ts_on) Y5_TS(2, it, 0);
-      ptx::mbar_wait(&tmem_full[acc], acc_ph);
+      if (p.wait_suspend) ptx::mbar_wait_suspend(&tmem_full[acc], acc_ph);
+      else ptx::mbar_wait(&tmem_full[acc], acc_ph);
       ptx::tc_fence_after();
       if (ts_on) Y5_TS(2, it, 1);
       if (p.dbg & 4) {
@@ -526,52 +716,9 @@ __global__ void __launch_bounds__(DUAL ? 192 : NUM_THREADS) __maxnreg__(DUAL ? 1
       for (int m = 0; m < p.m_sub; ++m) {  // the tile's 128-pixel sub-tiles, stacked along H
       const int hsub = c.h0 + m * p.Ht;
       const int h = hsub + hl, w = c.w0 + wl;
-      const bool valid = (h < p.Hout) && (w < p.Wout);
       const uint32_t taddr = tmem_base + (uint32_t)(acc * p.acc_stride + m * p.sub_cols) + ((uint32_t)(q * 32) << 16);
 
-      if (p.mode == MODE_CONV) {
-        const __nv_bfloat16* rrow =
-            p.res ? p.res + (long long)c.b * p.res_img_stride + (long long)h * p.res_row_stride + (long long)w * p.res_pix_stride + c.n0
-                  : nullptr;
-        __nv_bfloat16* urow = nullptr;
-        if (p.out2x) urow = p.out2x + (((long long)c.b * 2 * p.Hout + 2 * h) * (2 * p.Wout) + 2 * w) * p.out2x_pix_stride + c.n0;
-        const int nvalid = min(p.BN, p.Cout - c.n0);
-        EpiTile et;
-        et.taddr = taddr;
-        et.stage = stage;
-        et.stage_bytes = p.epi_stage_bytes;
-        et.swz = (uint32_t)((lane >> 1) & 3);
-        et.lane = lane;
-        et.leader = leader;
-        et.bias = p.bias + c.n0;
-        et.rrow = valid ? rrow : nullptr;
-        et.urow = valid ? urow : nullptr;
-        et.up_pix = p.out2x_pix_stride;
-        et.up_row = (long long)(2 * p.Wout) * p.out2x_pix_stride;
-        et.nvalid = nvalid;
-        et.col_first = col_first;
-        et.col_step = col_step;
-        et.tm = &p.tmO;
-        et.cn0 = c.n0;
-        et.cw = c.w0 + box_w0;
-        et.chh = hsub + box_h0;
-        et.cb = c.b;
-        et.tmu = (p.out2x && p.up_tma) ? &p.tmU : nullptr;
-        et.ubh = c.b * p.Hout + hsub + box_h0;
-        et.ts = (ts_on && m == 0 && p.ts && (int)blockIdx.x == p.ts_cta) ? p.ts + (2 * 32 + (it & 31)) * 8 : nullptr;
-        // one specialised instantiation per layer flavour: nothing of the unused paths is issued
-        const int flavour = (p.act ? 1 : 0) | (p.res ? 2 : 0) | (p.out2x ? 4 : 0);
-        switch (flavour) {
-          case 0: conv_epi_tile<false, false, false>(et, sbuf); break;
-          case 1: conv_epi_tile<true, false, false>(et, sbuf); break;
-          case 2: conv_epi_tile<false, true, false>(et, sbuf); break;
-          case 3: conv_epi_tile<true, true, false>(et, sbuf); break;
-          case 5: conv_epi_tile<true, false, true>(et, sbuf); break;
-          case 4:
-          case 6: conv_epi_tile<false, true, true>(et, sbuf); break;  // generic paths tolerate null rrow / urow
-          default: conv_epi_tile<true, true, true>(et, sbuf); break;
-        }
-      } else if (p.det_decode == 2) {
+      if (p.det_decode == 2) {
         // Detect, compact records for the fused post-process (the [B, A, no] tensor is never written): per anchor row
         // rec_w floats = (cx, cy, w, h, obj, cls[nc], theta index) - everything non_max_suppression_obb reads of a row
         // (utils/general.py:781-832).  Box / obj / class columns: same sigmoid and decode arithmetic as the full-tensor mode
@@ -592,11 +739,11 @@ __global__ void __launch_bounds__(DUAL ? 192 : NUM_THREADS) __maxnreg__(DUAL ? 1
           uint32_t r[32];
           ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)c0, r);
           ptx::tmem_ld_wait();
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + c.n0 + c0);
+          const uint32_t b4 = ptx::smem_u32(bias_s + c.n0 + c0);
           float v[32];
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
-            const float4 bv = __ldg(b4 + g);
+            const float4 bv = ptx::ld_shared_v4(b4 + 16u * g);
             v[4 * g + 0] = __uint_as_float(r[g * 4 + 0]) + bv.x;
             v[4 * g + 1] = __uint_as_float(r[g * 4 + 1]) + bv.y;
             v[4 * g + 2] = __uint_as_float(r[g * 4 + 2]) + bv.z;
@@ -677,10 +824,10 @@ __global__ void __launch_bounds__(DUAL ? 192 : NUM_THREADS) __maxnreg__(DUAL ? 1
           if (leader) ptx::tma_store_wait_read<1>();
           __syncwarp();
           uint8_t* sb = stage + sbuf * p.epi_stage_bytes;
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + c.n0 + c0);
+          const uint32_t b4 = ptx::smem_u32(bias_s + c.n0 + c0);
 #pragma unroll
           for (int g = 0; g < 8; ++g) {  // 4 floats = one 16-byte chunk
-            const float4 bv = __ldg(b4 + g);
+            const float4 bv = ptx::ld_shared_v4(b4 + 16u * g);
             float v[4];
             v[0] = __uint_as_float(r[g * 4 + 0]) + bv.x;
             v[1] = __uint_as_float(r[g * 4 + 1]) + bv.y;
@@ -852,8 +999,17 @@ int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
   if (d->mode == MODE_DETECT && d->det_decode == 2)
     k.epi_stage_bytes = std::max<uint32_t>(EPI_STAGE_DET, (uint32_t)align_up((size_t)32 * det_rec_w * 4, 128));
   // operand ring (+ resident weights): everything but the epilogue staging; `dual` = two CTAs per SM, each with half of it
-  size_t SMEM_BUDGET = (size_t)SMEM_TOTAL - 1024 - (size_t)EPI_WARPS * 2 * k.epi_stage_bytes;
-  const size_t BUDGET_ONE = SMEM_BUDGET, BUDGET_DUAL = (size_t)DUAL_SMEM - 1024 - (size_t)4 * 2 * k.epi_stage_bytes;
+  // staging depth: in-kernel stamps show ~100 cycles between "accumulator loaded" and "staging buffer free" with two buffers per
+  // warp, i.e. the TMA stores are not what the epilogue waits for
+  k.wait_suspend = 1;
+  k.mma_loop = 0;
+  if (const char* ml = getenv("Y5OBB_MMA_LOOP")) k.mma_loop = atoi(ml) ? 1 : 0;
+  if (const char* ws = getenv("Y5OBB_WAIT_SUSPEND")) k.wait_suspend = atoi(ws) ? 1 : 0;
+  k.epi_bufs = 2;  // four buffers measured slower (they cost operand-ring depth): opt-in through Y5OBB_EPI_BUFS=4
+  if (const char* eb = getenv("Y5OBB_EPI_BUFS")) k.epi_bufs = (atoi(eb) == 4 && d->mode == MODE_CONV) ? 4 : 2;
+  const size_t bias_bytes = align_up((size_t)(cout_pad + 32) * 4, 128);  // the bias lives in shared memory behind the staging buffers
+  size_t SMEM_BUDGET = (size_t)SMEM_TOTAL - 1024 - (size_t)EPI_WARPS * k.epi_bufs * k.epi_stage_bytes - bias_bytes;
+  const size_t BUDGET_ONE = SMEM_BUDGET, BUDGET_DUAL = (size_t)DUAL_SMEM - 1024 - (size_t)4 * k.epi_bufs * k.epi_stage_bytes - bias_bytes;
   // Row-shift mode (stride-1 convs with KH > 1): an 8 x 16 pixel tile whose A stage holds Ht + KH - 1 image
   // rows; the KH vertical taps read the same stage at row offsets that are whole 8-row swizzle groups, so each
   // input row crosses L2 -> shared memory (Ht + KH - 1) / Ht times per kw instead of KH times.  Taken when the
@@ -893,8 +1049,10 @@ int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
     k.a_bytes = (uint32_t)a_stage;  // ring slots are 1024-aligned; the TMA box fills the first a_rows * Wt rows
     const size_t b_all = (size_t)d->KH * d->KW * k.kchunks * k.b_stage_bytes;
     // weights stay resident when every tile uses the same ones (one N tile) and they leave room for >= 3 A stages
+    // (several N tiles: the grid is made a multiple of their count, so that tile t = blockIdx.x + i * gridDim.x keeps ONE N tile
+    // per CTA - the Detect head's three anchors - and that tile's weights are the resident ones)
     k.b_resident =
-        (nt == 1 && b_all + 3 * a_stage <= SMEM_BUDGET && !(d->flags & Y5OBB_CONV_NO_RESIDENT)) ? 1 : 0;
+        ((nt == 1 || nt <= 4) && b_all + 3 * a_stage <= SMEM_BUDGET && !(d->flags & Y5OBB_CONV_NO_RESIDENT)) ? 1 : 0;
     k.b_res_bytes = k.b_resident ? (uint32_t)b_all : 0u;
     k.b_per_stage = k.b_resident ? 0 : (rowshift ? d->KH : 1);
     const size_t unit_bytes = a_stage + (size_t)k.b_per_stage * k.b_stage_bytes;
@@ -1138,13 +1296,14 @@ int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
   }
   const int total = k.n_tiles_m * k.n_tiles_n;
   o->grid = std::min(total, sm_count() * (k.epi_warps == 4 ? 2 : 1));
+  if (k.b_resident && k.n_tiles_n > 1) o->grid = o->grid / k.n_tiles_n * k.n_tiles_n;  // one N tile per CTA (resident weights)
   o->threads = 64 + 32 * k.epi_warps;
   // many tiles per CTA: the two epilogue groups alternate tiles (two epilogues in flight, any BN);
   // few tiles per CTA: they split the columns of each tile (shortest single-tile latency)
   k.epi_tile_split = (total >= 4 * o->grid && k.epi_warps == 8) ? 1 : 0;
   if (d->mode == MODE_DETECT && d->det_decode == 2 && k.epi_warps == 8) k.epi_tile_split = 1;  // a record is assembled by one thread over all columns
   // >= 116 KB so that two CTAs (each owning all 512 TMEM columns) can never share an SM
-  o->smem = k.b_res_bytes + (size_t)k.stages * stage_bytes + (size_t)k.epi_warps * 2 * k.epi_stage_bytes + 1024;
+  o->smem = k.b_res_bytes + (size_t)k.stages * stage_bytes + (size_t)k.epi_warps * k.epi_bufs * k.epi_stage_bytes + bias_bytes + 1024;
   if (k.epi_warps == 8) o->smem = std::max<size_t>(o->smem, 116 * 1024);
   else if (o->smem > (size_t)DUAL_SMEM) {
     delete o;
