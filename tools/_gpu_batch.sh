@@ -1,6 +1,6 @@
 set +e
-timeout 900 python -m pytest tests/test_conv_gpu.py tests/test_engine_gpu.py tests/test_pipeline_gpu.py tests/test_train_forward_gpu.py tests/test_train_backward_gpu.py tests/test_train_step_gpu.py -q -x 2>&1 | tail -3
-Y5OBB_TE_CALIBRATED=1 Y5OBB_TE_RECORDS=1 timeout 300 python tools/time_engine.py s 16 1024 > gpurun_out/r2_te_epi6.txt 2>&1
-tail -n 2 gpurun_out/r2_te_epi6.txt
-timeout 600 python bench.py --no-train --no-eager --no-nms-sweep --no-extra-models --no-cpu-baseline > gpurun_out/r2_bench_g.json 2> gpurun_out/r2_bench_g.err
-cut -c1-200 gpurun_out/r2_bench_g.json; tail -2 gpurun_out/r2_bench_g.err
+timeout 1500 python -m pytest tests -q -m gpu > gpurun_out/r2_gpu_tests_final.txt 2>&1
+tail -n 3 gpurun_out/r2_gpu_tests_final.txt
+timeout 1200 python bench.py > gpurun_out/r2_bench_final2.json 2> gpurun_out/r2_bench_final2.err
+cut -c1-300 gpurun_out/r2_bench_final2.json; tail -2 gpurun_out/r2_bench_final2.err
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/r2_smoke2.txt 2>&1; tail -2 gpurun_out/r2_smoke2.txt

@@ -90,6 +90,8 @@ struct ConvK {
                        // columns, half the shared memory and one epilogue group - two independent producer / MMA / epilogue
                        // pipelines whose hand-shake bubbles overlap (ncu: no unit of the single pipeline is above 45 % busy)
   int tmem_cols;       // 512 or 256
+  int res_prefetch;    // 1: the epilogue requests its next tile's residual lines into L2 (A-B: Y5OBB_RES_PREFETCH=0)
+  int no_full_fence;   // 1: no tcgen05.fence::after_thread_sync after the operand-ring wait (A-B)
   int mma_loop;        // 1: the MMA issuer uses the compact runtime loop for every unit shape (A-B against the unrolled sequences)
   int wait_suspend;    // 1: the epilogue warps' wait on the accumulator uses the suspend-hint form of mbarrier.try_wait
   int epi_bufs;        // staging buffers per epilogue warp (2 or 4): a buffer is reused only after its TMA store has read it
@@ -231,7 +233,9 @@ __device__ __forceinline__ void mma_role(const ConvK& p, const MmaCtx& x) {
     for (int u0 = 0; u0 < n_units; u0 += group) {
       const int ng = min(group, n_units - u0);
       ptx::mbar_wait(&x.full_bar[s], ph);
-      ptx::tc_fence_after();
+      // (no tcgen05.fence here: the operands were written by TMA, whose completion this mbarrier phase is; the fence is for
+      // ordering against other threads' tcgen05 operations - the accumulator hand-back above)
+      if (!p.no_full_fence) ptx::tc_fence_after();
       if (u0 == 0) Y5_TS(1, it, 2);
       uint32_t a_lo = s_lo;
       for (int g = 0; g < ng; ++g) {
@@ -438,6 +442,25 @@ __device__ __forceinline__ void epi_role_conv(const ConvK& p, const EpiCtx& x) {
 #pragma unroll
       for (int g = 0; g < 4; ++g)
         rvn[g] = (r0 && x.col_first + g * 8 < nvalid) ? *reinterpret_cast<const uint4*>(r0 + x.col_first + g * 8) : make_uint4(0, 0, 0, 0);
+    }
+    if (RES && p.res_prefetch) {
+      // The residual of the early layers comes from HBM (it left L2 two layers ago) and is fetched by the epilogue threads
+      // themselves, 64 bytes per thread and chunk, one chunk ahead: too few bytes in flight for a 2-3 k cycle latency.  So the
+      // lines this thread will need in its NEXT tile are requested into L2 now, a whole tile time ahead (no registers, no
+      // shared memory); the loads above then see an L2 hit.
+      const int tn = t + (int)gridDim.x * ((p.epi_tile_split && !x.one_group) ? 2 : 1);
+      if (tn < x.total_tiles) {
+        const TileCoord cn = decode_tile(p, tn);
+        const int hn = cn.h0 + x.hl, wn = cn.w0 + x.wl;
+        if (wn < p.Wout) {
+          const __nv_bfloat16* rn =
+              p.res + (long long)cn.b * p.res_img_stride + (long long)hn * p.res_row_stride + (long long)wn * p.res_pix_stride + cn.n0;
+          const int nvn = min(p.BN, p.Cout - cn.n0);
+          for (int m = 0; m < p.m_sub; ++m)
+            if (hn + m * p.Ht < p.Hout)
+              for (int c0 = x.col_first; c0 < nvn; c0 += x.col_step) ptx::prefetch_l2(rn + m * rstep + c0);
+        }
+      }
     }
     et.bias = x.bias_s + (uint32_t)c.n0 * 4u;
     et.nvalid = nvalid;
@@ -1003,6 +1026,10 @@ int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
   // warp, i.e. the TMA stores are not what the epilogue waits for
   k.wait_suspend = 1;
   k.mma_loop = 0;
+  k.no_full_fence = 0;
+  k.res_prefetch = 1;
+  if (const char* rp = getenv("Y5OBB_RES_PREFETCH")) k.res_prefetch = atoi(rp) ? 1 : 0;
+  if (const char* nf = getenv("Y5OBB_NO_FULL_FENCE")) k.no_full_fence = atoi(nf) ? 1 : 0;
   if (const char* ml = getenv("Y5OBB_MMA_LOOP")) k.mma_loop = atoi(ml) ? 1 : 0;
   if (const char* ws = getenv("Y5OBB_WAIT_SUSPEND")) k.wait_suspend = atoi(ws) ? 1 : 0;
   k.epi_bufs = 2;  // four buffers measured slower (they cost operand-ring depth): opt-in through Y5OBB_EPI_BUFS=4
