@@ -124,6 +124,8 @@ typedef struct y5obb_conv y5obb_conv_t;
 #define Y5OBB_CONV_NO_UP_TMA 2048  /* flags: the 2x up-sampled copy through per-thread stores (default: four TMA stores of the staged tile) */
 #define Y5OBB_CONV_NO_DUAL 4096    /* flags: always one CTA per SM.  (Two CTAs per SM - 256 TMEM columns, half the shared memory and four
                                       epilogue warps each - is an opt-in experiment, environment variable Y5OBB_DUAL; measured slower) */
+#define Y5OBB_CONV_NO_RES_RED 16384 /* flags: when `res` IS `out` (in-place Bottleneck add) the default adds the tile into memory with a TMA
+                                      reduce-add (bf16 add at L2: the sum is rounded twice); this flag keeps the epilogue's own fp32 add */
 #define Y5OBB_CONV_EPI2 8192       /* flags: reserved (two staging buffers per epilogue warp are the default; four: environment variable Y5OBB_EPI_BUFS=4, measured slower) */
 #define Y5OBB_CONV_ACC2 64         /* flags: two TMEM accumulator stages only (A-B comparison; default: as many as 512 columns hold) */
 

@@ -130,6 +130,31 @@ def test_conv_slices_residual_and_upsample():
     assert (up[..., :64] == 0).all()
 
 
+@pytest.mark.parametrize("cout,hw", [(32, 40), (64, 24), (256, 16)])
+def test_inplace_residual_reduce_add_equals_epilogue_add(cout, hw):
+    """The Bottleneck chain adds in place (out = res).  Default: the tile is ADDED into memory by the TMA store (bf16 add at L2, the
+    epilogue loads no residual); flag NO_RES_RED (16384): the epilogue loads the residual and adds in fp32.  Both must match the fp32
+    reference within the kernel's tolerance, and each other within one extra bf16 rounding of the sum."""
+    from yolov5_obb_b200.conv import Conv, Slice, pack_weights
+    B, H, W = 2, hw, hw + 8
+    g = torch.Generator(device="cpu").manual_seed(11)
+    w = (torch.randn(cout, cout, 3, 3, generator=g) / (3 * cout ** 0.5)).to(DEV)
+    b = (torch.randn(cout, generator=g) * 0.1).to(DEV)
+    wp, bp = pack_weights(w, b)
+    x = _mk(B, H, W, cout, 21)
+    res0 = _mk(B, H, W, 2 * cout, 22)
+    outs = []
+    for flags in (0, 16384):
+        buf = res0.clone()                      # the chain lives in channels [0, cout) of a wider (concat) buffer
+        Conv(Slice.full(x), wp, bp, cout, 3, 1, 1, True, out=Slice(buf, 0, cout), res=Slice(buf, 0, cout), flags=flags).run()
+        torch.cuda.synchronize()
+        _check(buf[..., :cout], _ref_conv(x, w, b, 1, 1, True, res=res0[..., :cout]), f"in-place residual flags={flags}")
+        assert torch.equal(buf[..., cout:], res0[..., cout:]), "neighbouring channels untouched"
+        outs.append(buf[..., :cout].float())
+    d = (outs[0] - outs[1]).abs()
+    assert float((d / (outs[1].abs() + 1e-2)).max()) <= 2.0 ** -7, "reduce-add differs from the fp32 add by more than one bf16 rounding"
+
+
 @pytest.mark.parametrize("decode", [True, False])
 def test_detect_head(decode):
     """models/yolo.py:63-81: 1x1 conv -> [B,3,H,W,no] (train) or sigmoid+decode rows of [B, A, no] (eval)."""

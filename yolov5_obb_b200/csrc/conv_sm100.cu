@@ -90,7 +90,9 @@ struct ConvK {
                        // columns, half the shared memory and one epilogue group - two independent producer / MMA / epilogue
                        // pipelines whose hand-shake bubbles overlap (ncu: no unit of the single pipeline is above 45 % busy)
   int tmem_cols;       // 512 or 256
-  int res_prefetch;    // 1: the epilogue requests its next tile's residual lines into L2 (A-B: Y5OBB_RES_PREFETCH=0)
+  int res_red;         // 1: the residual IS the output buffer (in-place Bottleneck add) and the tile leaves as a TMA reduce-add: no
+                       // residual loads in the epilogue (the kernel then runs its no-residual flavour)
+  int res_prefetch;    // 1: the epilogue requests its next tile's residual lines into L2 (opt-in: Y5OBB_RES_PREFETCH=1; measured neutral)
   int no_full_fence;   // 1: no tcgen05.fence::after_thread_sync after the operand-ring wait (A-B)
   int mma_loop;        // 1: the MMA issuer uses the compact runtime loop for every unit shape (A-B against the unrolled sequences)
   int wait_suspend;    // 1: the epilogue warps' wait on the accumulator uses the suspend-hint form of mbarrier.try_wait
@@ -297,6 +299,7 @@ struct EpiTile {
   int ubh;                 // cb * Hout + chh
   unsigned long long* ts;  // debug stamps of this tile's first chunk (slots 4..6 of the epilogue row) or null
   int nbuf;                // staging buffers of this warp (2 or 4)
+  bool red;                // the staged tile is ADDED to the destination (in-place residual) instead of stored
 };
 
 // rvn: this thread's residual values of the NEXT chunk to be processed (16-byte loads issued one chunk ahead - across
@@ -376,7 +379,8 @@ __device__ __forceinline__ void conv_epi_tile(const EpiTile& e, int& sbuf, uint4
     __syncwarp();
     if (e.leader) {
       // rows beyond the image and channels beyond Cout are clipped by the tensor map
-      ptx::tma_store_4d(e.tm, e.stage + sbuf * e.stage_bytes, e.cn0 + c0, e.cw, e.chh, e.cb);
+      if (e.red) ptx::tma_reduce_add_4d(e.tm, e.stage + sbuf * e.stage_bytes, e.cn0 + c0, e.cw, e.chh, e.cb);
+      else ptx::tma_store_4d(e.tm, e.stage + sbuf * e.stage_bytes, e.cn0 + c0, e.cw, e.chh, e.cb);
       if (UP && e.tmu) {  // nn.Upsample(2x nearest): the same staged tile lands on the four (dy, dx) phases
 #pragma unroll
         for (int ph = 0; ph < 4; ++ph)
@@ -416,6 +420,7 @@ __device__ __forceinline__ void epi_role_conv(const ConvK& p, const EpiCtx& x) {
   et.tm = &p.tmO;
   et.tmu = (UP && p.up_tma) ? &p.tmU : nullptr;
   et.nbuf = p.epi_bufs;
+  et.red = p.res_red != 0;
   const long long rstep = (long long)p.Ht * p.res_row_stride;                                 // residual: one sub-tile down
   const long long ustep = (long long)(2 * p.Ht) * (2 * p.Wout) * p.out2x_pix_stride;           // up-sampled copy: one sub-tile down
   const uint32_t lane_quarter = (uint32_t)(x.q * 32) << 16;
@@ -707,7 +712,7 @@ __global__ void __launch_bounds__(DUAL ? 192 : NUM_THREADS) __maxnreg__(DUAL ? 1
       x.total_tiles = total_tiles;
       x.leader = leader;
       x.one_group = one_group;
-      const int flavour = (p.act ? 1 : 0) | (p.res ? 2 : 0) | (p.out2x ? 4 : 0);
+      const int flavour = (p.act ? 1 : 0) | ((p.res && !p.res_red) ? 2 : 0) | (p.out2x ? 4 : 0);
       switch (flavour) {
         case 0: epi_role_conv<false, false, false>(p, x); break;
         case 1: epi_role_conv<true, false, false>(p, x); break;
@@ -1027,7 +1032,7 @@ int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
   k.wait_suspend = 1;
   k.mma_loop = 0;
   k.no_full_fence = 0;
-  k.res_prefetch = 1;
+  k.res_prefetch = 0;  // measured neutral to slightly negative (op 4: 65.4 -> 67.6 us): opt-in
   if (const char* rp = getenv("Y5OBB_RES_PREFETCH")) k.res_prefetch = atoi(rp) ? 1 : 0;
   if (const char* nf = getenv("Y5OBB_NO_FULL_FENCE")) k.no_full_fence = atoi(nf) ? 1 : 0;
   if (const char* ml = getenv("Y5OBB_MMA_LOOP")) k.mma_loop = atoi(ml) ? 1 : 0;
@@ -1185,6 +1190,16 @@ int y5obb_conv_create(const y5obb_conv_desc* d, y5obb_conv_t** out) {
   k.res_pix_stride = d->res_pix_stride;
   k.res_row_stride = geom ? d->res_row_stride : d->res_pix_stride * Wout;
   k.res_img_stride = geom ? d->res_img_stride : d->res_pix_stride * Wout * Hout;
+  // In-place residual (the Bottleneck chain: out = chain = res): the add can be done by the TMA store itself (a bf16 reduce-add at
+  // L2), which removes the epilogue's residual loads - they queue behind the producer's outstanding TMA loads (2-3 k cycles) and
+  // bounded the residual layers.  The sum is then rounded twice (conv + SiLU to bf16, then the bf16 add) instead of once.
+  // (Y5OBB_RES_RED=0 or the flag Y5OBB_CONV_NO_RES_RED: the epilogue loads the residual and adds in fp32, one rounding)
+  k.res_red = (d->res && d->res == d->out && d->res_pix_stride == d->out_pix_stride && !d->out2x && !(d->flags & Y5OBB_CONV_NO_RES_RED) &&
+               (!geom || (d->res_row_stride == d->out_row_stride && d->res_img_stride == d->out_img_stride)))
+                  ? 1
+                  : 0;
+  if (const char* rr = getenv("Y5OBB_RES_RED"))
+    if (!atoi(rr)) k.res_red = 0;
   k.out2x = static_cast<__nv_bfloat16*>(d->out2x);
   k.out2x_pix_stride = d->out2x_pix_stride;
   k.det_out = d->det_out;
