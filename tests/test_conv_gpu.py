@@ -151,8 +151,10 @@ def test_inplace_residual_reduce_add_equals_epilogue_add(cout, hw):
         _check(buf[..., :cout], _ref_conv(x, w, b, 1, 1, True, res=res0[..., :cout]), f"in-place residual flags={flags}")
         assert torch.equal(buf[..., cout:], res0[..., cout:]), "neighbouring channels untouched"
         outs.append(buf[..., :cout].float())
+    # one extra rounding of the conv + SiLU term (= sum - residual) to bf16, then both sums round to bf16
     d = (outs[0] - outs[1]).abs()
-    assert float((d / (outs[1].abs() + 1e-2)).max()) <= 2.0 ** -7, "reduce-add differs from the fp32 add by more than one bf16 rounding"
+    bound = 2.0 ** -8 * (outs[1] - res0[..., :cout].float()).abs() + 2.0 ** -7 * outs[1].abs() + 1e-3
+    assert bool((d <= bound).all()), "reduce-add differs from the fp32 add by more than one bf16 rounding"
 
 
 @pytest.mark.parametrize("decode", [True, False])
