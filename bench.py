@@ -585,6 +585,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # stdout carries exactly ONE JSON line: NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION / INFO, from the environment or
+        # an nccl.conf, writes it to stdout) goes to a per-rank file instead
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/y5obb_nccl_%h_%p.log")
         dist.init_process_group("nccl", device_id=dev)
 
     B = args.batch

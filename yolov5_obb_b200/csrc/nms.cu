@@ -196,14 +196,11 @@ k_tiles(const PreBox* __restrict__ pre, const NmsSeg* __restrict__ seg, int n_im
   // they are only taken for ordinary thresholds
   const float thr_lo = thr >= 0.01f ? thr * 0.999f : -1.0f;
 
-  // the work-unit counter is fetched one unit ahead: the atomic's round trip (~700 cycles) overlaps the current unit
-  long long next_u = 0;
-  if (tid == 0) s_unit = (long long)atomicAdd(&ctrl->next_unit, 1ull);
   for (;;) {
+    if (tid == 0) s_unit = (long long)atomicAdd(&ctrl->next_unit, 1ull);
     __syncthreads();
     const long long u = s_unit;
     if (u >= total) break;
-    if (tid == 0) next_u = (long long)atomicAdd(&ctrl->next_unit, 1ull);
 
     // image lookup: last b with unit_off <= u
     int lo = 0, hi = n_images - 1;
@@ -249,28 +246,11 @@ k_tiles(const PreBox* __restrict__ pre, const NmsSeg* __restrict__ seg, int n_im
       if (tid == 0) s_ncand = 0;
     };
 
-    // column blocks are fetched one block ahead into registers (threads 64..127, one box each): the global-memory latency of a
-    // block overlaps the pair tests of the previous one instead of standing between two barriers
-    float4 nx0 = make_float4(0.f, 0.f, 0.f, 0.f), nx1 = nx0;
-    if (tid >= TB && tid - TB < min(TB, S.n - cb0 * TB)) {
-      const float4* src = reinterpret_cast<const float4*>(&pre[S.off + cb0 * TB + (tid - TB)]);
-      nx0 = src[0];
-      nx1 = src[1];
-    }
     for (int cb = cb0; cb < cb1; ++cb) {
       const int ncol = min(TB, S.n - cb * TB);
       __syncthreads();  // s_col free (previous phase 1 done), s_row / s_ncand visible
-      if (tid >= TB && tid - TB < ncol) {
-        float4* dst = reinterpret_cast<float4*>(&s_col[tid - TB]);
-        dst[0] = nx0;
-        dst[1] = nx1;
-      }
+      if (tid >= TB && tid - TB < ncol) load_prebox(&s_col[tid - TB], &pre[S.off + cb * TB + (tid - TB)]);
       __syncthreads();
-      if (cb + 1 < cb1 && tid >= TB && tid - TB < min(TB, S.n - (cb + 1) * TB)) {
-        const float4* src = reinterpret_cast<const float4*>(&pre[S.off + (cb + 1) * TB + (tid - TB)]);
-        nx0 = src[0];
-        nx1 = src[1];
-      }
       {  // phase 1: exact reject of pairs whose circumscribed circles do not touch
         const int r = tid & (TB - 1);
         const int half = tid >> 6;
@@ -311,8 +291,7 @@ k_tiles(const PreBox* __restrict__ pre, const NmsSeg* __restrict__ seg, int n_im
       mask[S.mask_off + (long long)(rb * TB + r) * S.nblk + cb0 + cbl] = w;
       if (w) rowflag[S.off + rb * TB + r] = 1;
     }
-    __syncthreads();             // everyone has read s_unit / s_mask of this unit
-    if (tid == 0) s_unit = next_u;
+    __syncthreads();
   }
 }
 
