@@ -18,7 +18,8 @@ val.py:378-383).  Metric: images/s.
              fused Detect-records plan checked equal to Model.forward + non_max_suppression_obb
   nms        the other half of the metric: rotated-NMS boxes/s and pair-IoUs/s, 1k-200k candidates, beside the reference's own
              CUDA kernel K1 on the same GPU and its CPU kernel
-  extra.eager_torch_b200   the reference's GPU path restated with eager PyTorch/cuDNN fp16 + K1 on this GPU (the bar, not the target)
+  extra.eager_torch_b200   the reference's GPU path restated with eager PyTorch/cuDNN fp16 + K1 on this GPU (the bar, not the target);
+  train.eager_torch_b200   the same for the training step (autocast + GradScaler + SGD)
   cpu_baseline   the oracle port (fp32 torch restatement of the reference's eager CPU path + the reference's
              own CPU NMS kernel from oracle/_ref when present) on the host cores, bounded sample
 
@@ -297,6 +298,48 @@ def cpu_train_arm(size, budget_s=30.0):
     return dict(value=1.0 / dt, unit="images/s", cores=cores, kind="port", ms_per_step=dt * 1e3,
                 sample=f"yolov5{size} fp32 eager-torch restatement of train.py --device cpu (forward, ComputeLoss, autograd "
                        f"backward, SGD-Nesterov), {n} steps of 1 tile 1024x1024, {cores} threads")
+
+
+def eager_train_arm(size, dev, batch, steps=5, warmup=2):
+    """The reference's own GPU training step restated with eager PyTorch on this GPU (train.py:318-336: amp.autocast forward +
+    ComputeLoss, GradScaler backward, SGD-Nesterov step; cudnn.benchmark; no EMA update, which only flatters this bar): the bar
+    the hand-written step has to beat on its own box, not the target."""
+    import torch
+    from oracle import model_ref, loss_ref
+    from tests.modelgen import build_mirror
+    torch.backends.cudnn.benchmark = True
+    m = build_mirror(size, nc=NC, seed=0).train().to(dev)
+    det = m.model[-1]
+    hyp = loss_ref.scaled_hyp(loss_ref.DEFAULT_HYP, det.nl, NC, IMG)
+    opt = torch.optim.SGD(m.parameters(), lr=0.01, momentum=0.937, nesterov=True)
+    scaler = torch.amp.GradScaler("cuda")
+    imgs, tg = train_inputs(batch, 0)
+    imgs, tg = imgs.to(dev), tg.to(dev)
+    anchors, stride = det.anchors.to(dev), det.stride.to(dev)
+
+    def step():
+        with torch.enable_grad():
+            with torch.autocast("cuda", dtype=torch.float16):
+                pred = model_ref.forward_with_grad(m, imgs.float() / 255, training=True)
+            loss, _ = loss_ref.compute_loss([p.float() for p in pred], tg, anchors, stride, hyp, NC)
+            scaler.scale(loss).backward()
+        scaler.step(opt)
+        scaler.update()
+        opt.zero_grad(set_to_none=True)
+        return loss
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        last = step()
+    torch.cuda.synchronize(dev)
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": batch / dt, "unit": "images/s", "ms_per_step": dt * 1e3, "steps": steps, "loss_last": float(last),
+            "what": f"eager PyTorch {torch.__version__} / cuDNN {torch.backends.cudnn.version()}: yolov5{size} train step on this GPU, "
+                    f"{batch} tiles 1024x1024, torch.autocast(fp16) forward + fp32 ComputeLoss + GradScaler backward + SGD-Nesterov "
+                    "(train.py:318-336), cudnn.benchmark=True, NCHW, no EMA; wall clock with a synchronize around the timed steps"}
 
 
 def run_train_leg(args, dev, world, rank, dist, pk):
@@ -584,10 +627,12 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # stdout carries exactly ONE JSON line: until it is printed, file descriptor 1 points at stderr, so that whatever native
+    # libraries write to stdout (NCCL's "NCCL version ..." banner at communicator creation) cannot end up in front of it
+    sys.stdout.flush()
+    _saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # stdout carries exactly ONE JSON line: NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION / INFO, from the environment or
-        # an nccl.conf, writes it to stdout) goes to a per-rank file instead
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/y5obb_nccl_%h_%p.log")
         dist.init_process_group("nccl", device_id=dev)
 
     B = args.batch
@@ -822,12 +867,21 @@ def run_ours(args):
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "split_ms", "value_without_nms")}
     if train is not None:
         line["train"] = train
+        if world == 1 and not args.no_eager:
+            try:
+                train["eager_torch_b200"] = eager_train_arm(args.train_model, dev, train.get("global_batch", 8))
+            except Exception as e:  # pragma: no cover
+                train["eager_torch_b200"] = {"unavailable": f"{type(e).__name__}: {e}"}
+            torch.cuda.empty_cache()
         if not args.no_cpu_baseline and world == 1:
             tb = cpu_train_arm(args.train_model)
             train["cpu_baseline"] = {k: tb[k] for k in ("value", "unit", "cores", "kind", "sample")}
-    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(_saved_stdout, 1)
+    os.close(_saved_stdout)
+    print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

@@ -1,5 +1,5 @@
 set +e
-timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 20 --warmup 3 --no-eager --no-nms-sweep --no-extra-models --no-cpu-baseline > gpurun_out/r2_bench_2gpu.json 2> gpurun_out/r2_bench_2gpu.err
-head -c 300 gpurun_out/r2_bench_2gpu.json; echo; tail -3 gpurun_out/r2_bench_2gpu.err
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 bench.py --impl reference --gpus 2 --steps 1 --warmup 1 > gpurun_out/r2_bench_2gpu_ref.json 2> gpurun_out/r2_bench_2gpu_ref.err
-head -c 300 gpurun_out/r2_bench_2gpu_ref.json; echo
+timeout 900 python -m pytest tests/test_nms_gpu.py tests/test_postprocess_gpu.py tests/test_pipeline_gpu.py tests/test_poly_gpu.py -q -x 2>&1 | tail -3
+timeout 900 python bench.py --no-nms-sweep --no-extra-models --no-cpu-baseline > gpurun_out/r2_bench_j.json 2> gpurun_out/r2_bench_j.err
+wc -l gpurun_out/r2_bench_j.json; tail -2 gpurun_out/r2_bench_j.err; python -c "
+import json; d=json.load(open('gpurun_out/r2_bench_j.json')); print(d['value'], d.get('step_breakdown')); print(d['train'].get('eager_torch_b200'))"

@@ -10,7 +10,7 @@ ROOT = Path(__file__).resolve().parents[1]
 so = ROOT / "yolov5_obb_b200" / "liby5obb.so"
 out = subprocess.run(["cuobjdump", "-sass", str(so)], capture_output=True, text=True).stdout
 pat = {"UTCHMMA (tcgen05.mma kind::f16)": r"\bUTCHMMA\b", "UTCBAR (tcgen05.commit)": r"\bUTCBAR\b", "LDTM (tcgen05.ld)": r"\bLDTM\b",
-       "UTMALDG (TMA load)": r"\bUTMALDG\b", "UTMASTG (TMA store)": r"\bUTMASTG\b", "UTCATOMSWS/alloc (tcgen05.alloc)": r"\bUTCATOMSWS\b",
+       "UTMALDG (TMA load)": r"\bUTMALDG\b", "UTMASTG (TMA store)": r"\bUTMASTG\b", "UTMAREDG (TMA reduce-add store)": r"\bUTMAREDG\b", "UTCATOMSWS/alloc (tcgen05.alloc)": r"\bUTCATOMSWS\b",
        "SYNCS (mbarrier)": r"\bSYNCS\b", "ELECT": r"\bELECT\b", "BRA.U.ANY (per-lane serialisation loops)": r"BRA\.U\.ANY",
        "HMMA (legacy mma.sync)": r"\bHMMA\b", "ACQBULK/griddepcontrol": r"ACQBULK|\bDEPBAR\b"}
 cur, per = None, defaultdict(Counter)

@@ -184,6 +184,7 @@ k_tiles(const PreBox* __restrict__ pre, const NmsSeg* __restrict__ seg, int n_im
         unsigned long long* __restrict__ mask, uint8_t* __restrict__ rowflag, float thr, int strict) {
   __shared__ __align__(16) PreBox s_row[TB];
   __shared__ __align__(16) PreBox s_col[TB];
+  __shared__ float4 s_colq[TB];  // (cx, cy, rad, area) of the column boxes: what the far-pair test reads
   __shared__ unsigned long long s_mask[TB * CHUNK];  // [row][col block of the unit]
   __shared__ unsigned short s_cand[CAND_CAP];        // row (6 bits) | col block in unit (3) | col (6)
   __shared__ int s_ncand;
@@ -249,32 +250,49 @@ k_tiles(const PreBox* __restrict__ pre, const NmsSeg* __restrict__ seg, int n_im
     for (int cb = cb0; cb < cb1; ++cb) {
       const int ncol = min(TB, S.n - cb * TB);
       __syncthreads();  // s_col free (previous phase 1 done), s_row / s_ncand visible
-      if (tid >= TB && tid - TB < ncol) load_prebox(&s_col[tid - TB], &pre[S.off + cb * TB + (tid - TB)]);
+      if (tid >= TB) {
+        const int j = tid - TB;
+        if (j < ncol) {
+          load_prebox(&s_col[j], &pre[S.off + cb * TB + j]);
+          s_colq[j] = make_float4(s_col[j].cx, s_col[j].cy, s_col[j].rad, s_col[j].area);
+        } else {
+          s_colq[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
       __syncthreads();
-      {  // phase 1: exact reject of pairs whose circumscribed circles do not touch
+      {  // phase 1: exact reject of pairs whose circumscribed circles do not touch; four columns per step (one 16-byte
+         // shared-memory load each, one vote for the four: most steps find nothing)
         const int r = tid & (TB - 1);
         const int half = tid >> 6;
         const bool rvalid = r < nrow;
         const float rx = s_row[r].cx, ry = s_row[r].cy, rr = s_row[r].rad, ra = s_row[r].area;
         const int tag = (r << 9) | ((cb - cb0) << 6);
-#pragma unroll 4
-        for (int jj = 0; jj < TB / 2; ++jj) {
-          const int j = half * (TB / 2) + jj;
-          bool c = false;
-          if (rvalid && j < ncol && (cb > rb || j > r)) {
-            float dx = rx - s_col[j].cx, dy = ry - s_col[j].cy;
-            float R = rr + s_col[j].rad;
-            c = (dx * dx + dy * dy) <= R * R;
+        const bool diag = cb == rb;  // on the diagonal block only j > r counts
+#pragma unroll 2
+        for (int jj = 0; jj < TB / 2; jj += 4) {
+          const int j0 = half * (TB / 2) + jj;
+          bool c[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int j = j0 + q;
+            const float4 b = s_colq[j];  // cx, cy, rad, area
+            const float dx = rx - b.x, dy = ry - b.y, R = rr + b.z;
+            bool cc = rvalid && j < ncol && (!diag || j > r) && (dx * dx + dy * dy) <= R * R;
             // IoU <= min(area) / max(area): boxes of very different size can never reach the threshold
-            const float ca = s_col[j].area;
-            if (ra >= 0.f && ca >= 0.f && fminf(ra, ca) < thr_lo * fmaxf(ra, ca)) c = false;
+            if (ra >= 0.f && b.w >= 0.f && fminf(ra, b.w) < thr_lo * fmaxf(ra, b.w)) cc = false;
+            c[q] = cc;
           }
-          const unsigned bal = __ballot_sync(0xffffffffu, c);
-          if (bal) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&s_ncand, __popc(bal));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (c) s_cand[base + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)(tag | j);
+          if (__ballot_sync(0xffffffffu, c[0] | c[1] | c[2] | c[3])) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const unsigned bal = __ballot_sync(0xffffffffu, c[q]);
+              if (bal) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&s_ncand, __popc(bal));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (c[q]) s_cand[base + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)(tag | (j0 + q));
+              }
+            }
           }
         }
       }
