@@ -68,6 +68,7 @@ def parse():
     ap.add_argument("--no-eager", action="store_true", help="skip the eager-PyTorch-on-this-GPU bar (`extra.eager_torch_b200`)")
     ap.add_argument("--no-extra-models", action="store_true", help="skip the yolov5m b16 inference line (`extra.yolov5m_b16_inference`)")
     ap.add_argument("--no-parity-gate", action="store_true", help="skip the engine-vs-oracle check of the benchmarked plan")
+    ap.add_argument("--slots", type=int, default=2, help="batches in flight per GPU, one stream + one plan each (DetectPipeline slots)")
     return ap.parse_args()
 
 
@@ -252,6 +253,8 @@ def workload_config(args):
     return {"workload": f"yolov5{args.model}-OBB inference b{args.batch} 1024x1024 (BASELINE configs[1], val.py --task speed: "
                         f"pre-process + Model.forward + non_max_suppression_obb conf {CONF} iou {IOU} multi_label)",
             "batch_per_gpu": args.batch, "imgsz": IMG, "nc": NC, "parallelism": f"replicas x{args.gpus} (no collective)",
+            "in_flight": f"{getattr(args, 'slots', 1)} batches per GPU, each on its own stream with its own plan (DetectPipeline slots); "
+                         "ms_per_step = timed region / steps (throughput time, not the latency of one batch: see single_stream)",
             "l2": "per-step working set (activations > 3 GB) exceeds the 126 MB L2; no explicit flush"}
 
 
@@ -669,14 +672,23 @@ def run_ours(args):
     L = _lib.lib()
     conv_handles = {c._h.value for c in eng.convs}
 
+    from yolov5_obb_b200.pipeline import DetectPipeline
+    pipe = DetectPipeline(model, CONF, IOU, MAX_DET, multi_label=True, device=dev, slots=args.slots)
+    last = {}
+
     def step_device():
-        """pre-process + forward + NMS of one resident batch; the result stays on the device as the packed
-        ([B, max_det, 7], rows per image) pair, so consecutive steps queue back to back (no host read per step)."""
+        """pre-process + forward + NMS of one resident batch through the public pipeline object (DetectPipeline.submit =
+        Model.detect_records + non_max_suppression_obb on the next slot's stream); the result stays on the device as the packed
+        ([B, max_det, 7], rows per image) pair, so consecutive steps queue back to back (no host read per step) and
+        `slots` batches are in flight at once."""
+        slot = pipe._next
+        last[slot] = pipe.submit(x_dev)
+        return last[slot]
+
+    def step_single():
+        """the same step with ONE batch in flight, on the current stream (what round 1 and the first half of round 2 timed)"""
         rec = model.detect_records(x_dev)   # Model.forward with the Detect rows written as compact records (fused post-process)
         return non_max_suppression_obb(rec, CONF, IOU, multi_label=True, max_det=MAX_DET, return_packed="async")
-
-    from yolov5_obb_b200.pipeline import DetectPipeline
-    pipe = DetectPipeline(model, CONF, IOU, MAX_DET, multi_label=True, device=dev)
 
     def run_e2e(steps):
         """`steps` batches from pinned host memory through the public pipeline API: H2D of batch i+1 overlaps the
@@ -691,13 +703,17 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, pipeline=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        if pipeline is not None:
+            pipeline.fork()     # the slot streams start after e0 ...
         r = None
         for _ in range(steps):
             r = fn()
+        if pipeline is not None:
+            pipeline.join()     # ... and e1 is recorded after every slot stream has finished its last batch
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
@@ -712,15 +728,25 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     # one blocking call first: it sizes the candidate capacity for this workload (sticky hint, general._CAP_HINT)
     non_max_suppression_obb(model.detect_records(x_dev), CONF, IOU, multi_label=True, max_det=MAX_DET)
-    for _ in range(max(args.warmup, 3)):
+    n_warm = max(args.warmup, 3) * pipe.slots    # every slot captures its graphs on its third call
+    pipe.fork()
+    for _ in range(n_warm):
         dets = step_device()
-    ms_total, dets = timed(step_device, args.steps)
+    pipe.join()
+    ms_total, dets = timed(step_device, args.steps, pipe)
     clocks = sampler.stop() if sampler else None
-    rows = dets[1].tolist()
-    if rows[B] > dets[2] or min(rows) < 0:
-        raise RuntimeError("NMS candidate capacity exceeded in the timed steps: the measurement would be invalid")
+    for dd in last.values():                     # the last batch of every slot
+        rows = dd[1].tolist()
+        if rows[B] > dd[2] or min(rows) < 0:
+            raise RuntimeError("NMS candidate capacity exceeded in the timed steps: the measurement would be invalid")
     det_per_img = float(sum(rows[:B])) / B
     ms_step = ms_total / args.steps
+    # the same step with one batch in flight (for the comparison with earlier rounds, and as the step the per-launch
+    # roofline shares refer to)
+    for _ in range(3):
+        step_single()
+    ms_single, _ = timed(step_single, min(args.steps, 20))
+    ms_single /= min(args.steps, 20)
     # where the step goes (a few extra steps with events between the two public calls; not part of the timed region)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     bd = [0.0, 0.0]
@@ -737,7 +763,8 @@ def run_ours(args):
         torch.cuda.synchronize()
         bd[0] += ev[0].elapsed_time(ev[1])
         bd[1] += ev[1].elapsed_time(ev[2])
-    breakdown = {"forward_ms": bd[0] / 5, "post_process_ms": bd[1] / 5, "host_enqueue_ms": host_s / 5 * 1e3}
+    breakdown = {"forward_ms": bd[0] / 5, "post_process_ms": bd[1] / 5, "host_enqueue_ms": host_s / 5 * 1e3,
+                 "note": "one batch in flight, events between the two public calls"}
     value = world * B / (ms_step / 1e3)
 
     run_e2e(3)
@@ -789,7 +816,8 @@ def run_ours(args):
             "peak_sustained": pk["tflops_sustained"], "traffic": traffic, "traffic_source": traffic_src,
             "algorithmic_bytes_per_launch": eng.hbm_bytes / n_conv, "peak_source": pk["src"],
             "launches_per_step": n_conv, "flops_per_launch": sum(conv_flops) / n_conv,
-            "mean_launch_us": tot_conv_ms / n_conv * 1e3, "conv_share_of_step": tot_conv_ms / ms_step,
+            "mean_launch_us": tot_conv_ms / n_conv * 1e3, "conv_share_of_step": tot_conv_ms / ms_single,
+            "conv_share_note": "sum of the conv launches / the single-stream step (launches timed one batch in flight)",
             "hbm_view": {"algorithmic_GB_per_step": eng.hbm_bytes / 1e9,
                          "achieved_GBps": eng.hbm_bytes / (tot_conv_ms / 1e3) / 1e9, "peak_GBps": pk["hbm"]}}
 
@@ -810,27 +838,32 @@ def run_ours(args):
             mm = copy.deepcopy(build_model("m")).to(dev)
             non_max_suppression_obb(mm.detect_records(x_dev), CONF, IOU, multi_label=True, max_det=MAX_DET)   # capacity hint
 
+            pipe_m = DetectPipeline(mm, CONF, IOU, MAX_DET, multi_label=True, device=dev, slots=args.slots)
+
             def step_m():
-                return non_max_suppression_obb(mm.detect_records(x_dev), CONF, IOU, multi_label=True, max_det=MAX_DET,
-                                               return_packed="async")
-            for _ in range(4):
+                return pipe_m.submit(x_dev)
+            pipe_m.fork()
+            for _ in range(4 * pipe_m.slots):
                 dm = step_m()
-            ms_m, dm = timed(step_m, min(args.steps, 20))
+            pipe_m.join()
+            ms_m, dm = timed(step_m, min(args.steps, 20), pipe_m)
             eng_m = mm._engines[("records", tuple(x_dev.shape), dev.index)]
             ms_m /= min(args.steps, 20)
             extra_m = {"workload": "yolov5m-OBB inference b16 1024x1024 (north_star's model; same step: pre-process + Model.forward + NMS)",
                        "value": B / (ms_m / 1e3), "unit": "images/s", "ms_per_step": ms_m,
                        "conv_algorithmic_TFLOP_per_step": eng_m.flops / 1e12,
                        "whole_step_TFLOPs": eng_m.flops / (ms_m / 1e3) / 1e12, "detections_per_image": float(sum(dm[1].tolist()[:B])) / B}
-            del mm, eng_m
+            del mm, eng_m, pipe_m
             torch.cuda.empty_cache()
         except Exception as e:  # pragma: no cover
             extra_m = {"unavailable": f"{type(e).__name__}: {e}"}
 
     # train-step leg (all ranks take part: the gradient all-reduce is the path's one exchange step)
     train = None
+    pipe_slots = pipe.slots
     if not args.no_train:
         del pipe
+        last.clear()
         model._engines.clear()
         torch.cuda.empty_cache()
         train = run_train_leg(args, dev, world, rank, dist, pk)
@@ -841,13 +874,16 @@ def run_ours(args):
         return
     line = {
         "metric": "images/s", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": n_warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic (seeded DOTA-shaped uint8 tiles, seeded random-init weights with calibrated BN/Detect statistics)",
         "config": workload_config(args),
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(x_host.numel()),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps,
                 "api": "yolov5_obb_b200.pipeline.DetectPipeline (pinned host uint8 in, per-image host detections out; "
-                       "two-deep software pipeline: H2D of batch i+1 and host read-out of batch i-1 overlap batch i)"},
+                       f"{pipe_slots} batches in flight on their own streams, H2D of batch i+1 on a copy stream, host read-out of "
+                       "batch i-slots while the later ones compute)"},
+        "single_stream": {"ms_per_step": ms_single, "value": world * B / (ms_single / 1e3), "unit": "images/s",
+                          "what": "the same device-resident step with ONE batch in flight on one stream"},
         "gpu_launches": (1 + len(eng.ops) + 25) * args.steps,  # layout pass + conv / pool launches + the post-process kernels (profiles/r2_launches_infer.csv: 79 per step)
         "detections_per_image": det_per_img, "step_breakdown": breakdown,
         "clocks": clocks, "roofline": roof,

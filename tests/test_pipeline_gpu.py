@@ -12,11 +12,15 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-def test_pipeline_equals_blocking_calls():
+@pytest.mark.parametrize("slots,fused", [(1, True), (2, True), (3, True), (2, False)])
+def test_pipeline_equals_blocking_calls(slots, fused):
+    """slots batches in flight on their own streams (own plan and post-process graph each): every batch - all distinct -
+    must come back in order with exactly the blocking calls' rows; 7 batches so that every slot is used after its graphs
+    were captured (third use) and the pinned result slots wrap around."""
     from yolov5_obb_b200.general import non_max_suppression_obb
     from yolov5_obb_b200.pipeline import DetectPipeline
     m = build_mirror("n", nc=15, seed=0, obj_bias=1.0, cls_bias=-1.0, det_gain=6.0).to(DEV)
-    batches = [synth_tiles(2, 256, seed=s).pin_memory() for s in (1, 2, 3, 4, 5)]
+    batches = [synth_tiles(2, 256, seed=s).pin_memory() for s in range(1, 4 * slots + 2)]
     kw = dict(conf_thres=0.25, iou_thres=0.45, multi_label=True, max_det=300)
     want = []
     for xb in batches:
@@ -29,8 +33,11 @@ def test_pipeline_equals_blocking_calls():
         assert c[:2] == counts == [d.shape[0] for d in dets], (c, counts, [d.shape[0] for d in dets])
         for b in range(2):
             assert torch.equal(packed[b, :counts[b]], dets[b]) and torch.equal(out[b, :counts[b]], dets[b])
+        if fused:   # the pipeline's own entry point, blocking (the tensor path's rows equal it up to theta near-ties: below)
+            dets = non_max_suppression_obb(m.detect_records(xb.to(DEV)), **kw)
         want.append([d.cpu() for d in dets])
-    pipe = DetectPipeline(m, 0.25, 0.45, 300, multi_label=True, device=DEV)
+    pipe = DetectPipeline(m, 0.25, 0.45, 300, multi_label=True, device=DEV, slots=slots, fused_detect=fused)
+    assert pipe.slots == (slots if fused else 1)
     got = list(pipe(iter(batches)))
     assert len(got) == len(want)
     assert sum(d.shape[0] for w in want for d in w) > 0
@@ -39,6 +46,33 @@ def test_pipeline_equals_blocking_calls():
         for a, b in zip(g, w):
             assert not a.is_cuda and torch.equal(a, b)
     assert pipe.h2d_bytes == sum(x.numel() for x in batches)
+
+
+def test_submit_fork_join_device_resident():
+    """DetectPipeline.submit: device-resident batches round-robin over the slot streams, bracketed by fork() / join(); each
+    slot's last result equals the blocking call on that batch (distinct batches, so a slot mix-up cannot pass)."""
+    from yolov5_obb_b200.general import non_max_suppression_obb
+    from yolov5_obb_b200.pipeline import DetectPipeline
+    m = build_mirror("n", nc=15, seed=0, obj_bias=1.0, cls_bias=-1.0, det_gain=6.0).to(DEV)
+    xs = [synth_tiles(2, 256, seed=s).to(DEV) for s in range(1, 9)]
+    kw = dict(conf_thres=0.25, iou_thres=0.45, multi_label=True, max_det=300)
+    want = [non_max_suppression_obb(m.detect_records(x), **kw) for x in xs]
+    want = [[d.clone() for d in w] for w in want]
+    pipe = DetectPipeline(m, 0.25, 0.45, 300, multi_label=True, device=DEV, slots=2)
+    pipe.fork()
+    outs = []
+    for i, x in enumerate(xs):
+        o = pipe.submit(x)
+        if i >= len(xs) - 2:
+            outs.append((i, o))
+    pipe.join()
+    torch.cuda.synchronize()
+    for i, (packed, counts, cap) in outs:
+        c = counts.tolist()
+        assert 0 <= c[2] <= cap
+        for b in range(2):
+            assert torch.equal(packed[b, :c[b]], want[i][b])
+    assert sum(d.shape[0] for w in want for d in w) > 0
 
 
 @pytest.mark.parametrize("size,B,S", [("n", 3, 160), ("s", 2, 256)])

@@ -128,7 +128,9 @@ def _launch(args, cap, keep_ws=False):
     with torch.cuda.device(dev):
         nbytes = L.y5obb_nms_obb_workspace_bytes(B, A, cap, MAX_NMS)
         # a captured graph owns its workspace (the shared grow-only buffer may be re-allocated later)
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev) if keep_ws else _lib.workspace(nbytes, dev, "nms_obb")
+        # (the shared grow-only buffer is per stream: calls on different streams may be in flight together)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev) if keep_ws else \
+            _lib.workspace(nbytes, dev, f"nms_obb:{_lib.stream_ptr(dev)}")
         rc = L.y5obb_nms_obb_f32(pred.data_ptr(), B, A, no, nc, float(conf_thres), float(iou_thres), mask,
                                  int(bool(agnostic)), int(bool(multi_label)), int(max_det), MAX_NMS, float(MAX_WH),
                                  _lib.NMS_STRICT_GT | (_lib.NMS_NO_CLASS_SPLIT if nosplit else 0) | (_lib.NMS_COMPACT_PRED if compact else 0),

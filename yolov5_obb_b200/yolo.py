@@ -319,17 +319,19 @@ class Model(nn.Module):
             eng._weights_sig = sig
         return eng.forward(x), None
 
-    def detect_records(self, x):
+    def detect_records(self, x, slot: int = 0):
         """Eval-mode forward for the fused post-process: instead of the [B, A, nc+185] tensor the Detect epilogue writes, per
         anchor row, the compact record (cx, cy, w, h, obj, cls[nc], theta index) - everything non_max_suppression_obb reads
         (utils/general.py:781-832) - so 96 B instead of 800 B per row cross HBM, once instead of three times.  Returns a
         general.DetectRecords, accepted by yolov5_obb_b200.general.non_max_suppression_obb in place of the prediction
-        tensor (bit-identical detections: same sigmoid / decode arithmetic, same first-maximum theta rule)."""
+        tensor (bit-identical detections: same sigmoid / decode arithmetic, same first-maximum theta rule).
+        `slot` selects one of several independent plans of the same shape (own activation and record buffers, own captured
+        graph): batches in flight on DIFFERENT streams must use different slots (pipeline.DetectPipeline does)."""
         if self.training:
             raise RuntimeError("detect_records is an inference entry point (model.eval())")
         from .engine import InferenceEngine
         from .general import DetectRecords
-        key = ("records", tuple(x.shape), x.device.index)
+        key = ("records", tuple(x.shape), x.device.index) + ((int(slot),) if slot else ())
         eng = self._engines.get(key)
         sig = self._weights_signature()
         if eng is None or eng._weights_sig != sig:
