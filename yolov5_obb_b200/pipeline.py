@@ -7,7 +7,7 @@ val.py:183-207 (pre-process, inference, NMS), software-pipelined:
   (measured on B200, yolov5s b16 1024^2: 1.95 ms per step with one batch in flight, 1.71 with two, 1.69 with three -
   tools/time_streams.py).  Results are bit-identical to the blocking calls: the same kernels run on the same data, only
   their interleaving changes.
-* the host->device copy of batch i+1 runs on a copy stream while batch i computes (one device input buffer per slot,
+* the host->device copy of batch i+1 runs on a copy stream while batch i computes (max(2, slots) device input buffers,
   event-ordered), and the device->host copy of batch i's detections is asynchronous, so the host turns batch i-slots into
   per-image tensors while the GPU works on the batches after it (no stream is drained inside the loop)."""
 from typing import Iterable, Iterator, List, Optional
@@ -37,9 +37,12 @@ class DetectPipeline:
         # slot 0 with a single slot = the caller's current stream (the behaviour of a plain loop of blocking-free calls)
         self.streams = [torch.cuda.Stream(self.device) for _ in range(self.slots)] if self.slots > 1 else [None]
         self.copy_stream = torch.cuda.Stream(self.device)
-        self._bufs = [None] * self.slots
-        self._copied = [torch.cuda.Event() for _ in range(self.slots)]
-        self._consumed = [torch.cuda.Event() for _ in range(self.slots)]
+        # device input buffers: batch i+1 is uploaded while batch i is being queued, so there are at least two
+        self.n_in = max(2, self.slots)
+        self._bufs = [None] * self.n_in
+        self._copied = [torch.cuda.Event() for _ in range(self.n_in)]
+        self._consumed = [torch.cuda.Event() for _ in range(self.n_in)]
+        self._reader = [0] * self.n_in          # the slot whose stream read the buffer last
         self._hslots = None
         self._next = 0
         self.h2d_bytes = 0
@@ -89,17 +92,17 @@ class DetectPipeline:
                                  for _ in range(self.slots + 1)]
         return hs[j]
 
-    def _upload(self, slot: int, x_host: torch.Tensor, first_use: bool) -> None:
-        if self._bufs[slot] is None or self._bufs[slot].shape != x_host.shape or self._bufs[slot].dtype != x_host.dtype:
+    def _upload(self, j: int, x_host: torch.Tensor, first_use: bool) -> None:
+        if self._bufs[j] is None or self._bufs[j].shape != x_host.shape or self._bufs[j].dtype != x_host.dtype:
             if not first_use:
-                self._stream(slot).synchronize()   # (shape change mid-stream: the old buffer may still be read)
-            self._bufs[slot] = torch.empty(x_host.shape, dtype=x_host.dtype, device=self.device)
+                self._stream(self._reader[j]).synchronize()   # (shape change mid-stream: the old buffer may still be read)
+            self._bufs[j] = torch.empty(x_host.shape, dtype=x_host.dtype, device=self.device)
             first_use = True
         with torch.cuda.stream(self.copy_stream):
             if not first_use:
-                self.copy_stream.wait_event(self._consumed[slot])  # the engine finished reading this buffer
-            self._bufs[slot].copy_(x_host, non_blocking=True)
-            self._copied[slot].record(self.copy_stream)
+                self.copy_stream.wait_event(self._consumed[j])  # the engine finished reading this buffer
+            self._bufs[j].copy_(x_host, non_blocking=True)
+            self._copied[j].record(self.copy_stream)
         self.h2d_bytes += x_host.numel() * x_host.element_size()
 
     def __call__(self, host_batches: Iterable[torch.Tensor]) -> Iterator[List[torch.Tensor]]:
@@ -109,25 +112,25 @@ class DetectPipeline:
         cur = next(it, None)
         if cur is None:
             return
-        N = self.slots
-        used = [False] * N
+        N, NB = self.slots, self.n_in
+        used = [False] * NB
         self.fork()
         self._upload(0, cur, True)
         used[0] = True
         i = 0
         pending = []
         while cur is not None:
-            slot = i % N
-            nslot = (i + 1) % N
+            slot, j, jn = i % N, i % NB, (i + 1) % NB
             nxt = next(it, None)
-            if nxt is not None:
-                self._upload(nslot, nxt, not used[nslot])
-                used[nslot] = True
+            if nxt is not None:   # (its previous user, batch i + 1 - NB <= i - 1, has been queued: _consumed[jn] is its event)
+                self._upload(jn, nxt, not used[jn])
+                used[jn] = True
             compute = self._stream(slot)
             with torch.cuda.stream(compute):
-                compute.wait_event(self._copied[slot])
-                pred = self.model.detect_records(self._bufs[slot], slot=slot) if self.fused else self.model(self._bufs[slot])[0]
-                self._consumed[slot].record(compute)  # the layout pass has consumed the input by now (stream order)
+                compute.wait_event(self._copied[j])
+                pred = self.model.detect_records(self._bufs[j], slot=slot) if self.fused else self.model(self._bufs[j])[0]
+                self._consumed[j].record(compute)  # the layout pass has consumed the input by now (stream order)
+                self._reader[j] = slot
                 packed, counts, cap = non_max_suppression_obb(pred, return_packed="async", **self.kw)
                 # batch i - (N + 1), the previous user of this pinned slot, was handed to the caller before this point
                 hout, hcnt, ev = self._host_slot(i % (N + 1), packed.shape[0], packed.shape[1])
