@@ -65,6 +65,13 @@ class BackwardPlan:
         self._L = L
         self.gbuf: Dict[int, torch.Tensor] = {}
         self.steps = []  # (name, closure(stream))
+        # The weight gradients are leaves of the backward chain (bn_bwd(l) -> {wgrad(l), dgrad(l)} -> bn_bwd(l-1) -> ...): they
+        # run on a second stream, each ordered after the kernel that produced its dz, and are joined before the few
+        # re-mapping copies at the end - so wgrad_kernel (tensor-bound, one 60 KB CTA per SM) shares the SMs with the
+        # HBM-bound BatchNorm backward passes and fills the tails of the dgrad launches.  Every wgrad reads buffers nothing
+        # writes after its producer (its own dz, the saved activation) and accumulates into its own slice of the flat
+        # gradient buffer, so only the interleaving changes.  Y5OBB_WGRAD_STREAM=0 keeps everything on one stream.
+        self.side = torch.cuda.Stream(dev) if os.environ.get("Y5OBB_WGRAD_STREAM", "1") == "1" else None
         self.prof = None  # set to {} to collect per-step-kind device times (ms) during run()
 
         def add(tag, fn):
@@ -324,7 +331,20 @@ class BackwardPlan:
         det = eng.model.model[-1]
         with torch.no_grad():
             self.flat.zero_()
-            if self.prof is None:
+            if self.prof is None and self.side is not None:
+                cur, side = torch.cuda.current_stream(eng.device), self.side
+                side.wait_stream(cur)                       # fork (after the flat buffer was zeroed)
+                for tag, step in self.steps:
+                    if tag in ("wgrad", "zero"):            # ("zero": the stem's own dw buffer, cleared on the wgrad's stream)
+                        ev = torch.cuda.Event()
+                        ev.record(cur)                      # the step before it on the main chain produced its dz
+                        side.wait_event(ev)
+                        with torch.cuda.stream(side):
+                            step(side.cuda_stream)
+                    else:
+                        step(st)
+                cur.wait_stream(side)                       # join: the copies below read the weight gradients
+            elif self.prof is None:
                 for _, step in self.steps:
                     step(st)
             else:  # debug: CUDA events around every step, summed per kind (and listed per wgrad / dgrad layer)
