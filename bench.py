@@ -372,15 +372,15 @@ def run_train_leg(args, dev, world, rank, dist, pk):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(n):
-            if e2e:  # inputs from pinned host memory, the step's loss read back
-                imgs_d.copy_(imgs_h, non_blocking=True)
-                tg_d.copy_(tg_h, non_blocking=True)
-            loss, items = ts.step(imgs_d, tg_d)
-            if not first_loss:
-                first_loss.append(float(loss.cpu()))        # the very first optimisation step (warm-up region, untimed)
-            if e2e:
-                losses.append(float(loss.cpu()))
+        if e2e:  # the public loop over HOST batches (TrainStep.run: inputs from pinned host memory every step - the copy of
+            # batch i+1 overlaps step i - and every step's loss read back to the host)
+            for loss, items in ts.run((imgs_h, tg_h) for _ in range(n)):
+                losses.append(float(loss))
+        else:
+            for _ in range(n):
+                loss, items = ts.step(imgs_d, tg_d)
+                if not first_loss:
+                    first_loss.append(float(loss.cpu()))    # the very first optimisation step (warm-up region, untimed)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)

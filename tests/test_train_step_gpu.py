@@ -166,3 +166,30 @@ def test_warmup_schedule_follows_train_py():
         ts.step(imgs, tg)
     lrs = [g["lr"] for g in ts.optimizer.param_groups]
     assert all(abs(v - 0.01) < 1e-9 for v in lrs) and abs(ts.optimizer.param_groups[1]["momentum"] - 0.937) < 1e-9
+
+
+def test_run_over_host_batches_equals_the_step_loop():
+    """TrainStep.run (uploads of batch i+1 on a copy stream, loss read one step late) against the plain loop
+    `step(imgs.to(device), targets.to(device))` from the same initial weights, over distinct batches with different target
+    counts: the first loss is the same number (the forward is deterministic), the later ones agree to within the noise the
+    fp32 atomics of the weight-gradient kernel put on an optimisation step, and every batch comes back in order."""
+    from yolov5_obb_b200.train_step import TrainStep
+    B, S = 2, 128
+    batches = [(synth_tiles(B, S, seed=10 + i).pin_memory(),
+                torch.from_numpy(synth_targets(B, 10 + 7 * i, S, nc=15, seed=20 + i)).pin_memory()) for i in range(5)]
+    ma = build_mirror("n", nc=15, seed=4).train().to(DEV)
+    mb = copy.deepcopy(ma)
+    ta, tb = TrainStep(ma, batch_size=64, imgsz=S), TrainStep(mb, batch_size=64, imgsz=S)
+    want = []
+    for x, t in batches:
+        l, it = ta.step(x.to(DEV), t.to(DEV))
+        want.append((l.item(), it.cpu()))
+    got = list(tb.run(iter(batches)))
+    assert len(got) == len(want)
+    for k, ((l, it), (lw, itw)) in enumerate(zip(got, want)):
+        assert not l.is_cuda and it.shape == itw.shape
+        tol = 1e-5 if k == 0 else 3e-2
+        assert abs(l.item() - lw) <= tol * max(1.0, abs(lw)), (k, l.item(), lw)
+    # a second call reuses the buffers (and waits for their last consumer)
+    got2 = list(tb.run(iter(batches[:2])))
+    assert len(got2) == 2 and all(math.isfinite(l.item()) for l, _ in got2)

@@ -1,8 +1,4 @@
 set +e
-export PYTHONPATH=.
-(timeout 400 python -m pytest tests/test_train_backward_gpu.py tests/test_train_step_gpu.py tests/test_sgd_ema_gpu.py -q 2>&1 | tail -8) > gpurun_out/r2_wgrad_stream.txt
-echo "--- Y5OBB_WGRAD_STREAM=0" >> gpurun_out/r2_wgrad_stream.txt
-(Y5OBB_WGRAD_STREAM=0 timeout 200 python tools/time_train.py m 8 1024 4 2>&1 | head -6) >> gpurun_out/r2_wgrad_stream.txt
-echo "--- Y5OBB_WGRAD_STREAM=1" >> gpurun_out/r2_wgrad_stream.txt
-(Y5OBB_WGRAD_STREAM=1 timeout 200 python tools/time_train.py m 8 1024 4 2>&1 | head -6) >> gpurun_out/r2_wgrad_stream.txt
-cat gpurun_out/r2_wgrad_stream.txt
+timeout 280 python bench.py --no-nms-sweep --no-extra-models --no-cpu-baseline --no-eager > gpurun_out/r2_bench_final_slots.json 2> gpurun_out/r2_bench_final_slots.err
+wc -l gpurun_out/r2_bench_final_slots.json; tail -3 gpurun_out/r2_bench_final_slots.err; python -c "
+import json; d=json.load(open('gpurun_out/r2_bench_final_slots.json')); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['single_stream']['value'], d['roofline']['frac']); t=d['train']; print(t['value'], t['ms_per_step'], t['e2e']['value'], t['tensor']['frac'], t['loss_first_last'])"

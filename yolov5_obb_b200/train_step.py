@@ -147,6 +147,84 @@ class TrainStep:
         self.ni += 1
         return loss.detach(), items
 
+    def run(self, host_batches):
+        """The batch loop of train.py:296-342 over HOST batches (what the dataloader yields: pinned uint8 images [B,3,H,W] and
+        float targets [nt, 187 | 8 | 7]): yields (loss, loss_items) per batch, in order, as HOST tensors.
+        `imgs.to(device, non_blocking=True)` of train.py:300 becomes a copy of batch i+1 on a second stream while step i
+        computes (two device buffers per input, event-ordered), and the loss of step i - the one device->host read the loop
+        needs (train.py:344-348 mloss) - is fetched after step i+1 has been queued, so the compute stream never drains."""
+        dev = next(self.model.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("TrainStep.run needs the model on a CUDA device; there is no CPU path")
+        main = torch.cuda.current_stream(dev)
+        io = getattr(self, "_io", None)
+        if io is None:
+            ev = torch.cuda.Event
+            io = self._io = dict(copy=torch.cuda.Stream(dev), img=[None, None], tg=[None, None], copied=[ev(), ev()],
+                                 consumed=[ev(), ev()], host=[None, None], done=[ev(), ev()])
+        copy = io["copy"]
+
+        def upload(j, batch, wait):
+            imgs_h, tg_h = batch
+            nt = int(tg_h.shape[0])
+            if io["img"][j] is None or io["img"][j].shape != imgs_h.shape or io["img"][j].dtype != imgs_h.dtype:
+                if wait:
+                    io["consumed"][j].synchronize()
+                    wait = False
+                io["img"][j] = torch.empty(imgs_h.shape, dtype=imgs_h.dtype, device=dev)
+            t = io["tg"][j]
+            if t is None or t.shape[0] < nt or t.shape[1:] != tg_h.shape[1:] or t.dtype != tg_h.dtype:
+                if wait:
+                    io["consumed"][j].synchronize()
+                    wait = False
+                io["tg"][j] = torch.empty((max(nt, 64) * 2,) + tuple(tg_h.shape[1:]), dtype=tg_h.dtype, device=dev)
+            with torch.cuda.stream(copy):
+                if wait:
+                    copy.wait_event(io["consumed"][j])      # the step that used these buffers has been through them
+                io["img"][j].copy_(imgs_h, non_blocking=True)
+                if nt:
+                    io["tg"][j][:nt].copy_(tg_h, non_blocking=True)
+                io["copied"][j].record(copy)
+            return nt
+
+        def finish(p):
+            h, e = p
+            e.synchronize()
+            return h[0].clone(), h[1:].clone()
+
+        it = iter(host_batches)
+        cur = next(it, None)
+        if cur is None:
+            return
+        for e in io["consumed"]:       # a previous run() that was abandoned half-way may still own the buffers
+            e.synchronize()
+        copy.wait_stream(main)
+        used = [False, False]
+        nt = upload(0, cur, False)
+        used[0] = True
+        i, pending = 0, None
+        while cur is not None:
+            j = i & 1
+            nxt = next(it, None)
+            nt_next = 0
+            if nxt is not None:
+                nt_next = upload(j ^ 1, nxt, used[j ^ 1])
+                used[j ^ 1] = True
+            main.wait_event(io["copied"][j])
+            loss, items = self.step(io["img"][j], io["tg"][j][:nt])
+            io["consumed"][j].record(main)
+            if io["host"][j] is None or io["host"][j].numel() != 1 + items.numel():
+                io["host"][j] = torch.empty(1 + items.numel(), dtype=torch.float32).pin_memory()
+            io["host"][j].copy_(torch.cat([loss.detach().reshape(1).float(), items.detach().reshape(-1).float()]), non_blocking=True)
+            io["done"][j].record(main)
+            if pending is not None:
+                yield finish(pending)
+            pending = (io["host"][j], io["done"][j])
+            cur, nt = nxt, nt_next
+            i += 1
+        if pending is not None:
+            yield finish(pending)
+
     def _fused_step(self):
         """train.py:336-342 (optimizer.step, zero_grad, ema.update) as one launch over a device-resident tensor table.
         Gradients are read in place from the backward plan's flat fp32 buffer (all-reduced in place first when N > 1);
