@@ -17,6 +17,15 @@ import torch
 from .general import non_max_suppression_obb
 
 
+def schedule(i: int, slots: int, n_in: int):
+    """Which resources batch i uses: (compute slot, device input buffer, input buffer of batch i+1, pinned result slot).
+    The loop below queues batch i AFTER uploading batch i+1 and hands batch i - slots to the caller after queueing batch i, so
+    * an input buffer is re-filled only when its previous user (batch i + 1 - n_in <= i - 1) has been queued: n_in >= 2;
+    * a pinned result slot is re-filled only when its previous user (batch i - (slots + 1)) has been handed over.
+    (tests/test_pipeline_host_cpu.py replays these rules without a GPU.)"""
+    return i % slots, i % n_in, (i + 1) % n_in, i % (slots + 1)
+
+
 class DetectPipeline:
     def __init__(self, model, conf_thres: float = 0.25, iou_thres: float = 0.45, max_det: int = 1500,
                  multi_label: bool = True, classes=None, agnostic: bool = False, device=None, fused_detect: bool = True,
@@ -120,7 +129,7 @@ class DetectPipeline:
         i = 0
         pending = []
         while cur is not None:
-            slot, j, jn = i % N, i % NB, (i + 1) % NB
+            slot, j, jn, hs = schedule(i, N, NB)
             nxt = next(it, None)
             if nxt is not None:   # (its previous user, batch i + 1 - NB <= i - 1, has been queued: _consumed[jn] is its event)
                 self._upload(jn, nxt, not used[jn])
@@ -133,7 +142,7 @@ class DetectPipeline:
                 self._reader[j] = slot
                 packed, counts, cap = non_max_suppression_obb(pred, return_packed="async", **self.kw)
                 # batch i - (N + 1), the previous user of this pinned slot, was handed to the caller before this point
-                hout, hcnt, ev = self._host_slot(i % (N + 1), packed.shape[0], packed.shape[1])
+                hout, hcnt, ev = self._host_slot(hs, packed.shape[0], packed.shape[1])
                 hout.copy_(packed, non_blocking=True)   # D2H of this batch's result, one copy; nobody waits for it here
                 hcnt.copy_(counts, non_blocking=True)
                 ev.record(compute)
