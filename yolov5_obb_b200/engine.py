@@ -216,6 +216,13 @@ class InferenceEngine:
                 add_conv(cat, w3, b3, 1, 1, 0, True, out[i])
             elif _is(m, "SPPF"):
                 x = out[fs[0]]
+                # the pooling kernel is the 5x5 / stride 1 / pad 2 window of every shipped yaml (common.py:183-196); the mirror
+                # keeps `k`, the reference's module keeps the nn.MaxPool2d as `m`
+                pk = getattr(m, "k", None)
+                if pk is None and hasattr(m, "m"):
+                    pk = m.m.kernel_size if isinstance(m.m.kernel_size, int) else m.m.kernel_size[0]
+                if pk != 5:
+                    raise RuntimeError(f"SPPF with a {pk}x{pk} pooling window is not planned (the kernel is 5x5)")
                 c_ = m.cv1.conv.out_channels
                 cat4 = new(hw[i][0], hw[i][1], 4 * c_)
                 w1, b1 = _conv_params(m.cv1)
