@@ -253,8 +253,9 @@ def workload_config(args):
     return {"workload": f"yolov5{args.model}-OBB inference b{args.batch} 1024x1024 (BASELINE configs[1], val.py --task speed: "
                         f"pre-process + Model.forward + non_max_suppression_obb conf {CONF} iou {IOU} multi_label)",
             "batch_per_gpu": args.batch, "imgsz": IMG, "nc": NC, "parallelism": f"replicas x{args.gpus} (no collective)",
-            "in_flight": f"{getattr(args, 'slots', 1)} batches per GPU, each on its own stream with its own plan (DetectPipeline slots); "
-                         "ms_per_step = timed region / steps (throughput time, not the latency of one batch: see single_stream)",
+            "in_flight": f"our arm: {getattr(args, 'slots', 1)} batches per GPU, each on its own stream with its own plan (DetectPipeline "
+                         "slots); ms_per_step = timed region / steps (throughput time, not the latency of one batch: see "
+                         "single_stream).  The reference arm processes one batch at a time",
             "l2": "per-step working set (activations > 3 GB) exceeds the 126 MB L2; no explicit flush"}
 
 
