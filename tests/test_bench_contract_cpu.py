@@ -15,6 +15,7 @@ def test_defaults_and_workload_description(monkeypatch):
     assert (a.train_model, a.train_batch) == ("m", 8)           # BASELINE configs[2]: yolov5m, 8 tiles per GPU
     cfg = bench.workload_config(a)
     assert "yolov5s-OBB inference b16 1024x1024" in cfg["workload"] and cfg["imgsz"] == 1024 and "l2" in cfg
+    assert a.slots == 2 and "2 batches per GPU" in cfg["in_flight"]   # the pipelined step is declared in the config
     json.dumps(cfg)
 
 
